@@ -1,0 +1,129 @@
+/*
+ * ndpb200.h -- C ABI of libndpb200.so, the B200 (sm_100a) implementation of
+ * ndpolator's batched `ndpolate` hot path.
+ *
+ * This is the drop-in boundary.  It sits beside the reference's CPython
+ * extension `cndpolator` (reference src/ndp_py.c) at the seam between
+ * ndpolator/ndpolator.py and native code: every entry point below replaces one
+ * `cndpolator.*` call (or the C function behind it), takes plain pointers and
+ * sizes, and returns an int status.  INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - All arrays are C-contiguous.  float64 for coordinates/values, int32 for
+ *     indices/flags (the reference's `int`), int64_t for element counts.
+ *   - Every data pointer may be a HOST pointer (pageable or pinned) or a
+ *     DEVICE pointer on the table's GPU; the library detects which
+ *     (cudaPointerGetAttributes) and stages host buffers through the GPU in
+ *     pipelined chunks.  Outputs are caller-allocated.
+ *   - Enum values equal the reference's (src/ndpolator.h:28-63).
+ *   - There is NO CPU fallback: with no usable CUDA device every call returns
+ *     NDPB_ERR_CUDA and ndpb_last_error() says why.
+ *   - Calls on one table are serialised internally; different tables may be
+ *     used from different threads.
+ */
+#ifndef NDPB200_H
+#define NDPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDPB_MAX_AXES 12
+
+/* reference src/ndpolator.h:28-32 (ndp_extrapolation_method) */
+enum { NDPB_METHOD_NONE = 0, NDPB_METHOD_NEAREST = 1, NDPB_METHOD_LINEAR = 2 };
+/* reference src/ndpolator.h:44-47 (ndp_search_algorithm) */
+enum { NDPB_SEARCH_KDTREE = 0, NDPB_SEARCH_LINEAR = 1 };
+/* reference src/ndpolator.h:59-63 (ndp_vertex_flag; ON_VERTEX|OUT_OF_BOUNDS = 3 occurs) */
+enum { NDPB_ON_GRID = 0, NDPB_ON_VERTEX = 1, NDPB_OUT_OF_BOUNDS = 2 };
+
+/* status codes (the reference has only NDP_SUCCESS / NDP_INVALID_TYPE, src/ndp_types.h:48-51) */
+enum {
+    NDPB_OK = 0,
+    NDPB_ERR_INVALID = 1,   /* bad argument (shape, enum, NULL) */
+    NDPB_ERR_CUDA = 2,      /* CUDA runtime failure or no device */
+    NDPB_ERR_NOMEM = 3,     /* device allocation failed */
+    NDPB_ERR_STATE = 4      /* call not valid for this table (e.g. axes-only table) */
+};
+
+typedef struct ndpb_table ndpb_table;
+
+/* Replaces ndp_table_new_from_python -> ndp_axes_new_from_data +
+ * ndp_table_new_from_data (reference src/ndp_py.c:91-124, src/ndp_types.c:51-68,
+ * :159-269): uploads axes and grid to GPU `device`, computes strides, the
+ * defined-vertex mask and the fully-defined-hypercube mask on the GPU, and (when
+ * it pays and fits) a cell-major copy of the grid for single-burst gathers.
+ * `axes[a]` has `axlen[a]` ticks; the first `nbasic` axes are basic
+ * (nbasic == 0 means all).  `grid` holds prod(axlen) * vdim doubles; grid ==
+ * NULL creates an axes-only table on which only ndpb_find is valid (the
+ * reference's cndpolator.find builds exactly that, src/ndp_py.c:157-165). */
+int ndpb_table_create(const double *const *axes, const int32_t *axlen, int naxes, int nbasic,
+                      const double *grid, int vdim, int device, ndpb_table **out);
+
+/* Replaces ndp_table_free via py_table_capsule_destructor (src/ndp_py.c:335-340). */
+int ndpb_table_destroy(ndpb_table *t);
+
+/* Replaces cndpolator.find -> ndp_query_pts_import (src/ndp_py.c:131-193,
+ * src/ndpolator.c:354-414).  query_pts: n x naxes.  Outputs n x naxes each. */
+int ndpb_find(ndpb_table *t, const double *query_pts, int64_t n,
+              int32_t *indices, int32_t *flags, double *normed);
+
+/* Replaces cndpolator.hypercubes -> ndp_find_hypercubes (src/ndp_py.c:254-318,
+ * src/ndpolator.c:416-508).  Inputs are what ndpb_find returned.  `v` has a
+ * fixed slot of 2^naxes * vdim doubles per query, of which the first
+ * 2^dim[i] * vdim are written (corner-major, first free axis = most significant
+ * bit, as in the reference); fdhc is the reference's ndp_hypercube.fdhc, which
+ * its Python API does not expose. */
+int ndpb_hypercubes(ndpb_table *t, const double *normed, const int32_t *indices, const int32_t *flags,
+                    int64_t n, int32_t *dim, int32_t *fdhc, double *v);
+
+/* Parity tap for ndp_find_nearest (src/ndpolator.c:188-352), C-only in the
+ * reference.  Takes raw query points (imports them first), searches for EVERY
+ * point, returns coords (n x naxes: nearest vertex, or superior corner of the
+ * nearest fully defined hypercube) and the squared index-space distance. */
+int ndpb_find_nearest(ndpb_table *t, const double *query_pts, int64_t n, int method, int search,
+                      int32_t *coords, double *dist);
+
+/* Replaces cndpolator.ndpolate -> ndp_query_pts_import + ndpolate
+ * (src/ndp_py.c:343-409, src/ndpolator.c:510-671).  interps: n x vdim;
+ * dists: n (0 for points interpolated inside a fully defined hypercube). */
+int ndpb_ndpolate(ndpb_table *t, const double *query_pts, int64_t n, int method, int search,
+                  double *interps, double *dists);
+
+/* Replaces cndpolator.distance (src/ndp_py.c:196-251): LINEAR method, KDTREE
+ * search, for every point. */
+int ndpb_distance(ndpb_table *t, const double *query_pts, int64_t n, double *dists);
+
+/* Register-time products, for parity tests of src/ndp_types.c:174-258.
+ * vmask/hcmask: nverts int32 each (host or device). */
+int64_t ndpb_table_nverts(const ndpb_table *t);
+int ndpb_table_masks(ndpb_table *t, int32_t *vmask, int32_t *hcmask);
+
+/* Shape of the reference's insertion-ordered kd-tree (src/ndpolator.c:114-136 +
+ * external/kdtree/kdtree.c:167-209) as rebuilt on the GPU for exact tie
+ * resolution: parent vertex id (-1 root, -2 not in tree) and depth (-1 not in
+ * tree) per basic vertex.  method is NDPB_METHOD_NEAREST or _LINEAR. */
+int ndpb_table_tree_topology(ndpb_table *t, int method, int32_t *parent, int32_t *depth);
+
+/* Tuning knobs that never change results.  Keys: "gather" = 0 auto | 1 strided
+ * (original layout) | 2 cell-major; "linear_search" = 0 auto | 1 brute force |
+ * 2 lattice; "chunk" = queries per staged chunk for host buffers. */
+int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t value);
+
+/* Per-table counters of the last call, for bench.py / tests:
+ * "launches" kernels launched, "offgrid" queries sent to the search,
+ * "hard" queries that needed the tree/lattice descent, "ties" queries resolved
+ * through the kd topology, "h2d_bytes", "d2h_bytes", "cellmajor" (0/1),
+ * "kernel_ns" device time of the main gather kernel (CUDA events). */
+int64_t ndpb_table_stat(const ndpb_table *t, const char *key);
+
+const char *ndpb_last_error(void);
+const char *ndpb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDPB200_H */
