@@ -1,0 +1,54 @@
+"""In-tree build of libndpb200.so (the CUDA kernels + C ABI) for sm_100a.
+
+nvcc cross-compiles without a GPU.  -fmad=false is part of the numerics contract
+(no FMA contraction: every lerp keeps the reference's three roundings)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libndpb200.so')
+SOURCES = ['ndp_api.cu']
+HEADERS = ['ndp_core.cuh', 'ndp_kernels.cuh', 'ndp_table.cuh', os.path.join('..', '..', 'include', 'ndpb200.h')]
+
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a',
+    '-lineinfo', '-O3', '-std=c++17', '--extended-lambda',
+    '-fmad=false',
+    '-Xcompiler', '-fPIC', '-shared',
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError('nvcc not found: libndpb200.so cannot be built (there is no CPU fallback)')
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    built = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles csrc/*.cu into ndpolator_b200/libndpb200.so if missing or out of date."""
+    if not force and not stale():
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        print(' '.join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force=True, verbose=True))

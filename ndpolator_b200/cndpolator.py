@@ -1,0 +1,240 @@
+"""Drop-in for the reference's CPython extension module ``cndpolator``
+(reference src/ndp_py.c:448-456): the same four entry points with the same
+argument names and return shapes, running on a B200 through libndpb200.so.
+
+    ndpolate(capsule=None, query_pts=None, axes=None, grid=None, nbasic=0,
+             extrapolation_method=0, search_algorithm=0)   src/ndp_py.c:343-409
+    find(axes, query_pts, nbasic)                            src/ndp_py.c:131-193
+    hypercubes(normed_query_pts, indices, axes, flags, grid, nbasic=0)
+                                                             src/ndp_py.c:254-318
+    distance(query_pts, capsule=None, axes=None, grid=None, nbasic=0)
+                                                             src/ndp_py.c:196-251
+
+The "capsule" is a :class:`Table` (device-resident axes, grid, masks, cell-major
+grid copy and lazily built kd topology) instead of a PyCapsule around an
+``ndp_table``.  Query points may be numpy arrays (results come back as numpy
+arrays, staged through pipelined H2D/D2H chunks) or CUDA tensors / anything with
+``__cuda_array_interface__`` (results stay on the device as torch tensors).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import weakref
+
+import numpy as np
+
+from . import _lib
+
+
+class ExtrapolationMethod(enum.IntEnum):      # src/ndp_py.c:433-437, src/ndpolator.h:28-32
+    NONE = 0
+    NEAREST = 1
+    LINEAR = 2
+
+
+class SearchAlgorithm(enum.IntEnum):          # src/ndp_py.c:439-442, src/ndpolator.h:44-47
+    KDTREE = 0
+    LINEAR = 1
+
+
+def _is_cuda(x) -> bool:
+    return hasattr(x, '__cuda_array_interface__') or (hasattr(x, 'is_cuda') and x.is_cuda)
+
+
+def _ptr(x) -> int:
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, 'data_ptr'):
+        return x.data_ptr()
+    return x.__cuda_array_interface__['data'][0]
+
+
+def _host_f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _prep_queries(query_pts, naxes):
+    """-> (array kept alive, pointer, n, on_device)"""
+    if _is_cuda(query_pts):
+        import torch
+        q = query_pts if isinstance(query_pts, torch.Tensor) else torch.as_tensor(query_pts, device='cuda')
+        if q.dtype != torch.float64 or not q.is_contiguous():
+            q = q.to(torch.float64).contiguous()
+        if q.dim() == 1:
+            q = q.reshape(-1, naxes)
+        if q.dim() != 2 or q.shape[1] != naxes:
+            raise ValueError(f'query_pts must have shape (N, {naxes})')
+        return q, q.data_ptr(), q.shape[0], True
+    q = _host_f64(query_pts)
+    if q.ndim == 1:
+        q = q.reshape(-1, naxes)
+    if q.ndim != 2 or q.shape[1] != naxes:
+        raise ValueError(f'query_pts must have shape (N, {naxes})')
+    return q, q.ctypes.data, q.shape[0], False
+
+
+def _empty(shape, dtype, like_device, device_index):
+    if like_device:
+        import torch
+        tdt = {np.float64: torch.float64, np.int32: torch.int32}[dtype]
+        return torch.empty(shape, dtype=tdt, device=f'cuda:{device_index}')
+    return np.empty(shape, dtype=dtype)
+
+
+class Table:
+    """Device-resident registered table; stands where the reference keeps its
+    PyCapsule(ndp_table) (src/ndp_py.c:370)."""
+
+    def __init__(self, axes, grid, nbasic=0, device=None):
+        L = _lib.lib()
+        self.device = _lib.default_device() if device is None else int(device)
+        self.axes = tuple(_host_f64(a) for a in axes)
+        self.naxes = len(self.axes)
+        self.nbasic = int(nbasic) if nbasic else self.naxes
+        axlen = (C.c_int32 * self.naxes)(*[len(a) for a in self.axes])
+        axptr = (C.c_void_p * self.naxes)(*[a.ctypes.data for a in self.axes])
+        if grid is None:
+            gptr, self.vdim, self._grid = None, 1, None
+        elif _is_cuda(grid):
+            import torch
+            g = grid if isinstance(grid, torch.Tensor) else torch.as_tensor(grid, device='cuda')
+            g = g.to(torch.float64).contiguous()
+            gptr, self.vdim, self._grid = g.data_ptr(), int(g.shape[-1]), g
+        else:
+            # like PyArray_FROM_OTF(grid, NPY_DOUBLE, NPY_ARRAY_CARRAY), src/ndp_py.c:120
+            g = _host_f64(grid)
+            gptr, self.vdim, self._grid = g.ctypes.data, int(g.shape[-1]), g
+        if grid is not None:
+            want = int(np.prod([len(a) for a in self.axes])) * self.vdim
+            have = int(np.prod(self._grid.shape))
+            if want != have:
+                raise ValueError(f'grid has {have} elements, axes x vdim need {want}')
+        h = C.c_void_p()
+        _lib.check(L.ndpb_table_create(axptr, axlen, self.naxes, self.nbasic, gptr, self.vdim, self.device, C.byref(h)))
+        self._h = h
+        self._grid = None          # the library made its own device copy
+        self._finalizer = weakref.finalize(self, L.ndpb_table_destroy, h)
+
+    # -- bookkeeping -----------------------------------------------------------
+    def close(self):
+        self._finalizer()
+
+    def set_option(self, key: str, value: int):
+        _lib.check(_lib.lib().ndpb_table_set_option(self._h, key.encode(), int(value)))
+
+    def stat(self, key: str) -> int:
+        return int(_lib.lib().ndpb_table_stat(self._h, key.encode()))
+
+    @property
+    def nverts(self) -> int:
+        return int(_lib.lib().ndpb_table_nverts(self._h))
+
+    def masks(self):
+        vm = np.empty(self.nverts, np.int32)
+        hm = np.empty(self.nverts, np.int32)
+        _lib.check(_lib.lib().ndpb_table_masks(self._h, vm.ctypes.data, hm.ctypes.data))
+        return vm, hm
+
+    def tree_topology(self, method):
+        parent = np.empty(self.nverts, np.int32)
+        depth = np.empty(self.nverts, np.int32)
+        _lib.check(_lib.lib().ndpb_table_tree_topology(self._h, int(method), parent.ctypes.data, depth.ctypes.data))
+        return parent, depth
+
+    # -- hot path ----------------------------------------------------------------
+    def find(self, query_pts):
+        q, qp, n, dev = _prep_queries(query_pts, self.naxes)
+        idx = _empty((n, self.naxes), np.int32, dev, self.device)
+        flg = _empty((n, self.naxes), np.int32, dev, self.device)
+        nrm = _empty((n, self.naxes), np.float64, dev, self.device)
+        _lib.check(_lib.lib().ndpb_find(self._h, qp, n, _ptr(idx), _ptr(flg), _ptr(nrm)))
+        return idx, flg, nrm
+
+    def hypercubes_raw(self, normed, indices, flags):
+        nrm = _host_f64(normed)
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        flg = np.ascontiguousarray(flags, dtype=np.int32)
+        n = idx.shape[0]
+        slot = (1 << self.naxes) * self.vdim
+        dim = np.empty(n, np.int32)
+        fdhc = np.empty(n, np.int32)
+        v = np.empty((n, slot), np.float64)
+        _lib.check(_lib.lib().ndpb_hypercubes(self._h, nrm.ctypes.data, idx.ctypes.data, flg.ctypes.data, n,
+                                               dim.ctypes.data, fdhc.ctypes.data, v.ctypes.data))
+        return dim, fdhc, v
+
+    def find_nearest(self, query_pts, method, search):
+        q, qp, n, dev = _prep_queries(query_pts, self.naxes)
+        coords = _empty((n, self.naxes), np.int32, dev, self.device)
+        dist = _empty((n,), np.float64, dev, self.device)
+        _lib.check(_lib.lib().ndpb_find_nearest(self._h, qp, n, int(method), int(search), _ptr(coords), _ptr(dist)))
+        return coords, dist
+
+    def ndpolate(self, query_pts, method=0, search=0, out=None):
+        q, qp, n, dev = _prep_queries(query_pts, self.naxes)
+        if out is None:
+            interps = _empty((n, self.vdim), np.float64, dev, self.device)
+            dists = _empty((n, 1), np.float64, dev, self.device)
+        else:
+            interps, dists = out
+        _lib.check(_lib.lib().ndpb_ndpolate(self._h, qp, n, int(method), int(search), _ptr(interps), _ptr(dists)))
+        return interps, dists
+
+    def distance(self, query_pts):
+        q, qp, n, dev = _prep_queries(query_pts, self.naxes)
+        dists = _empty((n, 1), np.float64, dev, self.device)
+        _lib.check(_lib.lib().ndpb_distance(self._h, qp, n, _ptr(dists)))
+        return dists
+
+
+# ---------------------------------------------------------------------------
+# module-level functions with the reference's signatures
+# ---------------------------------------------------------------------------
+
+def ndpolate(capsule=None, query_pts=None, axes=None, grid=None, nbasic=0,
+             extrapolation_method=0, search_algorithm=0):
+    """-> (interps, dists) with a valid capsule, else (interps, dists, capsule)."""
+    if isinstance(capsule, Table):
+        interps, dists = capsule.ndpolate(query_pts, extrapolation_method, search_algorithm)
+        return interps, dists
+    if query_pts is not None and axes is not None and grid is not None:
+        table = Table(axes, grid, nbasic)
+        interps, dists = table.ndpolate(query_pts, extrapolation_method, search_algorithm)
+        return interps, dists, table
+    # the reference returns NULL without an exception here (src/ndp_py.c:372-374) -> SystemError
+    raise SystemError('ndpolate() needs either a capsule or query_pts, axes and grid')
+
+
+def find(axes, query_pts, nbasic):
+    """-> (indices int32, flags int32, normed float64), each shaped like query_pts."""
+    table = Table(axes, None, nbasic)
+    try:
+        return table.find(query_pts)
+    finally:
+        table.close()
+
+
+def hypercubes(normed_query_pts, indices, axes, flags, grid, nbasic=0, capsule=None):
+    """-> tuple of N arrays of shape (2,)*dim + (vdim,)."""
+    table = capsule if isinstance(capsule, Table) else Table(axes, grid, nbasic)
+    try:
+        dim, fdhc, v = table.hypercubes_raw(normed_query_pts, indices, flags)
+    finally:
+        if table is not capsule:
+            table.close()
+    vdim = table.vdim
+    return tuple(v[i, :(1 << int(d)) * vdim].reshape((2,) * int(d) + (vdim,)).copy() for i, d in enumerate(dim))
+
+
+def distance(query_pts, capsule=None, axes=None, grid=None, nbasic=0):
+    """-> (N, 1) squared index-space distances to the nearest fully defined hypercube."""
+    if isinstance(capsule, Table):
+        return capsule.distance(query_pts)
+    if axes is None or grid is None:
+        raise ValueError('Either capsule must be valid or axes and grid must be provided')   # src/ndp_py.c:212-216
+    table = Table(axes, grid, nbasic if nbasic else np.shape(grid)[0])   # src/ndp_py.c:224 (sic)
+    try:
+        return table.distance(query_pts)
+    finally:
+        table.close()

@@ -1,0 +1,874 @@
+// ndp_api.cu -- the C ABI of libndpb200.so (include/ndpb200.h): device table
+// object, host<->device staging pipeline and kernel launches.  No CPU fallback:
+// every entry point fails with NDPB_ERR_CUDA when there is no usable device.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ndpb200.h"
+#include "ndp_core.cuh"
+#include "ndp_kernels.cuh"
+#include "ndp_table.cuh"
+
+static_assert(NDPB_MAX_AXES == NDP_MAX_AXES, "header and core disagree on the axis limit");
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? NDPB_ERR_NOMEM : NDPB_ERR_CUDA;        \
+            return fail(code_, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+        }                                                                                          \
+    } while (0)
+
+extern "C" const char *ndpb_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *ndpb_version(void) { return "ndpb200 0.1.0 (sm_100a; parity target ndpolator 1.3.0)"; }
+
+// ---------------------------------------------------------------------------
+// table
+// ---------------------------------------------------------------------------
+struct Pyramid {
+    NdpPyramid dev{};                       // device pointers inside
+    std::vector<uint32_t *> owned;
+    int count = 0;                          // set bits at level 0
+};
+
+struct Topology {
+    int *parent = nullptr, *depth = nullptr;
+    bool built = false;
+    int levels = 0;
+};
+
+struct Slot {                               // one in-flight batch
+    double *q = nullptr, *interps = nullptr, *dists = nullptr;     // staging (host callers only)
+    int *coords = nullptr;
+    int *list = nullptr, *chosen = nullptr, *tielist = nullptr;
+    long long cap_q = 0, cap_work = 0, cap_coords = 0;
+    NdpCounters *ctr = nullptr;             // device
+    NdpCounters *ctr_host = nullptr;        // pinned
+    cudaEvent_t in_done = nullptr, searched = nullptr, out_ready = nullptr, out_done = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;   // phase timing
+    bool used = false;
+};
+
+struct ndpb_table {
+    int device = 0;
+    NdpGeom g{};
+    int nticks = 0;
+    bool has_grid = false;
+    double *ticks = nullptr, *grid = nullptr, *cells = nullptr;
+    long long grid_doubles = 0;
+    Pyramid pyr[2];                         // [0] vmask, [1] hcmask
+    Topology topo[2];
+    cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_owned = nullptr;         // the compute stream this table created (s_compute may be a caller's)
+    Slot slot[2];
+    std::mutex mu;
+    int sm_count = 148;
+    // options
+    int opt_gather = 0, opt_linear_search = 0;
+    long long opt_chunk = 1 << 22;
+    // stats of the last call
+    long long st_launches = 0, st_offgrid = 0, st_hard = 0, st_ties = 0, st_h2d = 0, st_d2h = 0;
+    double st_main_ms = 0, st_search_ms = 0, st_finish_ms = 0;
+};
+
+static int blocks_for(long long items, int per_block = NDP_BLOCK)
+{
+    long long b = (items + per_block - 1) / per_block;
+    return (int) std::max<long long>(1, std::min<long long>(b, INT_MAX));
+}
+
+static bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static size_t tick_smem(const ndpb_table *t) { return (size_t) t->nticks * sizeof(double); }
+static int ticks_in_smem(const ndpb_table *t) { return tick_smem(t) <= 40 * 1024; }
+static size_t smem_bytes(const ndpb_table *t) { return ticks_in_smem(t) ? tick_smem(t) : 0; }
+
+static int build_pyramid(ndpb_table *t, Pyramid &P, uint32_t *level0)
+{
+    const NdpGeom &g = t->g;
+    NdpPyramid &D = P.dev;
+    D.nlev = 0;
+    int dim[NDP_MAX_AXES];
+    for (int a = 0; a < g.nbasic; a++) dim[a] = g.len[a];
+    uint32_t *prev = level0;
+    for (int lev = 0; lev < NDP_MAX_LEVELS; lev++) {
+        long long nblocks = 1;
+        for (int a = g.nbasic - 1, s = 1; a >= 0; a--) { D.dim[lev][a] = dim[a]; D.stride[lev][a] = s; s *= dim[a]; nblocks *= dim[a]; }
+        if (lev == 0) D.bits[0] = level0;
+        else {
+            uint32_t *bits = nullptr;
+            CU(cudaMalloc(&bits, sizeof(uint32_t) * ((nblocks + 31) / 32)));
+            P.owned.push_back(bits);
+            PyrLevelArgs A{};
+            A.nb = g.nbasic;
+            for (int a = 0; a < g.nbasic; a++) { A.cdim[a] = D.dim[lev - 1][a]; A.cstride[a] = D.stride[lev - 1][a]; A.pdim[a] = dim[a]; }
+            A.nparent = (int) nblocks; A.cbits = prev; A.pbits = bits;
+            k_pyr_level<<<blocks_for(((nblocks + 31) / 32) * 32), NDP_BLOCK, 0, t->s_compute>>>(A);
+            CU(cudaGetLastError());
+            D.bits[lev] = bits;
+            prev = bits;
+        }
+        D.nlev = lev + 1;
+        if (nblocks == 1) break;
+        for (int a = 0; a < g.nbasic; a++) dim[a] = (dim[a] + 1) / 2;
+    }
+    // any_set: the single top block; first_clear: lowest clear bit of level 0
+    uint32_t top = 0;
+    int *d_first = nullptr;
+    int init = INT_MAX;
+    CU(cudaMalloc(&d_first, sizeof(int)));
+    CU(cudaMemcpyAsync(d_first, &init, sizeof(int), cudaMemcpyHostToDevice, t->s_compute));
+    k_first_clear<<<blocks_for((g.nverts + 31) / 32), NDP_BLOCK, 0, t->s_compute>>>(level0, g.nverts, d_first);
+    CU(cudaGetLastError());
+    int first = 0;
+    CU(cudaMemcpyAsync(&first, d_first, sizeof(int), cudaMemcpyDeviceToHost, t->s_compute));
+    CU(cudaMemcpyAsync(&top, D.bits[D.nlev - 1], sizeof(uint32_t), cudaMemcpyDeviceToHost, t->s_compute));
+    CU(cudaStreamSynchronize(t->s_compute));
+    CU(cudaFree(d_first));
+    D.first_clear = (first == INT_MAX) ? -1 : first;
+    D.any_set = (top & 1u) ? 1 : 0;
+    return NDPB_OK;
+}
+
+static void free_slot(Slot &s)
+{
+    cudaFree(s.q); cudaFree(s.interps); cudaFree(s.dists); cudaFree(s.coords);
+    cudaFree(s.list); cudaFree(s.chosen); cudaFree(s.tielist); cudaFree(s.ctr);
+    if (s.ctr_host) cudaFreeHost(s.ctr_host);
+    cudaEvent_t *ev[] = {&s.in_done, &s.searched, &s.out_ready, &s.out_done, &s.t0, &s.t1, &s.t2, &s.t3};
+    for (auto e : ev) if (*e) cudaEventDestroy(*e);
+    s = Slot{};
+}
+
+extern "C" int ndpb_table_destroy(ndpb_table *t)
+{
+    if (!t) return NDPB_OK;
+    cudaSetDevice(t->device);
+    cudaDeviceSynchronize();
+    cudaFree(t->ticks); cudaFree(t->grid); cudaFree(t->cells);
+    for (auto &P : t->pyr) {
+        for (auto p : P.owned) cudaFree(p);
+        if (P.dev.nlev) cudaFree((void *) P.dev.bits[0]);
+    }
+    for (auto &T : t->topo) { cudaFree(T.parent); cudaFree(T.depth); }
+    for (auto &s : t->slot) free_slot(s);
+    if (t->s_owned) cudaStreamDestroy(t->s_owned);
+    if (t->s_in) cudaStreamDestroy(t->s_in);
+    if (t->s_out) cudaStreamDestroy(t->s_out);
+    delete t;
+    return NDPB_OK;
+}
+
+static int maybe_build_cells(ndpb_table *t)
+{
+    const NdpGeom &g = t->g;
+    if (t->cells || t->opt_gather == 1 || g.naxes > 6) return NDPB_OK;
+    // pays when a corner vector is smaller than a 128-byte line; must fit comfortably
+    const long long bytes = (g.ncells << g.naxes) * g.vdim * (long long) sizeof(double);
+    if (t->opt_gather != 2 && g.vdim * sizeof(double) >= 128) return NDPB_OK;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes > (long long) (free_b / 2)) return NDPB_OK;
+    CU(cudaMalloc(&t->cells, bytes));
+    k_build_cells<<<t->sm_count * 16, NDP_BLOCK, 0, t->s_compute>>>(g, t->grid, t->cells);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(t->s_compute));
+    return NDPB_OK;
+}
+
+extern "C" int ndpb_table_create(const double *const *axes, const int32_t *axlen, int naxes, int nbasic,
+                                 const double *grid, int vdim, int device, ndpb_table **out)
+{
+    if (!out) return fail(NDPB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!axes || !axlen || naxes < 1 || naxes > NDP_MAX_AXES) return fail(NDPB_ERR_INVALID, "naxes must be in [1, 12]");
+    if (nbasic == 0) nbasic = naxes;
+    if (nbasic < 1 || nbasic > naxes) return fail(NDPB_ERR_INVALID, "nbasic must be in [1, naxes]");
+    if (vdim < 1) return fail(NDPB_ERR_INVALID, "vdim must be >= 1");
+    long long nverts = 1, nall = 1, ncells = 1;
+    int nticks = 0;
+    for (int a = 0; a < naxes; a++) {
+        if (axlen[a] < 2 || axlen[a] > (1 << 16)) return fail(NDPB_ERR_INVALID, "every axis needs 2..65536 ticks");
+        if (!axes[a]) return fail(NDPB_ERR_INVALID, "axis pointer is NULL");
+        nall *= axlen[a]; ncells *= axlen[a] - 1; nticks += axlen[a];
+        if (a < nbasic) nverts *= axlen[a];
+        if (nall > (1LL << 40)) return fail(NDPB_ERR_INVALID, "grid too large");
+    }
+    if (nverts >= INT_MAX - 64) return fail(NDPB_ERR_INVALID, "basic lattice must have < 2^31 vertices (as in the reference)");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(NDPB_ERR_CUDA, "no CUDA device available (libndpb200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(NDPB_ERR_INVALID, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+
+    ndpb_table *t = new ndpb_table();
+    t->device = device;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) t->sm_count = prop.multiProcessorCount;
+    NdpGeom &g = t->g;
+    g.naxes = naxes; g.nbasic = nbasic; g.vdim = vdim;
+    for (int a = 0, off = 0; a < naxes; a++) { g.len[a] = axlen[a]; g.tickoff[a] = off; off += axlen[a]; }
+    for (int a = naxes - 1; a >= 0; a--) {
+        g.vstride[a] = (a == naxes - 1) ? 1 : g.vstride[a + 1] * g.len[a + 1];
+        g.cstride[a] = (a == naxes - 1) ? 1 : g.cstride[a + 1] * (g.len[a + 1] - 1);
+    }
+    for (int a = nbasic - 1; a >= 0; a--) g.bstride[a] = (a == nbasic - 1) ? 1 : g.bstride[a + 1] * g.len[a + 1];
+    g.nverts = (int) nverts;
+    g.ncells = ncells;
+    t->nticks = nticks;
+    t->grid_doubles = nall * vdim;
+
+    auto bail = [&](int rc) { ndpb_table_destroy(t); return rc; };
+#define CUT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        fail(e_ == cudaErrorMemoryAllocation ? NDPB_ERR_NOMEM : NDPB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+        return bail(e_ == cudaErrorMemoryAllocation ? NDPB_ERR_NOMEM : NDPB_ERR_CUDA); } } while (0)
+
+    CUT(cudaStreamCreateWithFlags(&t->s_owned, cudaStreamNonBlocking));
+    t->s_compute = t->s_owned;
+    CUT(cudaStreamCreateWithFlags(&t->s_in, cudaStreamNonBlocking));
+    CUT(cudaStreamCreateWithFlags(&t->s_out, cudaStreamNonBlocking));
+
+    std::vector<double> flat(nticks);
+    for (int a = 0; a < naxes; a++) {
+        if (is_device_ptr(axes[a])) CUT(cudaMemcpy(flat.data() + g.tickoff[a], axes[a], sizeof(double) * axlen[a], cudaMemcpyDeviceToHost));
+        else memcpy(flat.data() + g.tickoff[a], axes[a], sizeof(double) * axlen[a]);
+    }
+    CUT(cudaMalloc(&t->ticks, sizeof(double) * nticks));
+    CUT(cudaMemcpy(t->ticks, flat.data(), sizeof(double) * nticks, cudaMemcpyHostToDevice));
+
+    if (grid) {
+        t->has_grid = true;
+        CUT(cudaMalloc(&t->grid, sizeof(double) * t->grid_doubles));
+        CUT(cudaMemcpy(t->grid, grid, sizeof(double) * t->grid_doubles, cudaMemcpyDefault));
+        const long long words = (nverts + 31) / 32;
+        uint32_t *vbits = nullptr, *hbits = nullptr;
+        CUT(cudaMalloc(&vbits, sizeof(uint32_t) * words));
+        CUT(cudaMalloc(&hbits, sizeof(uint32_t) * words));
+        const int nb = blocks_for(words * 32);
+        k_vmask_bits<<<nb, NDP_BLOCK, 0, t->s_compute>>>(t->grid, g.nverts, g.vstride[nbasic - 1] * vdim, vbits);
+        k_hcmask_bits<<<nb, NDP_BLOCK, 0, t->s_compute>>>(g, vbits, hbits);
+        CUT(cudaGetLastError());
+        int rc = build_pyramid(t, t->pyr[0], vbits);
+        if (rc == NDPB_OK) rc = build_pyramid(t, t->pyr[1], hbits);
+        if (rc == NDPB_OK) rc = maybe_build_cells(t);
+        if (rc != NDPB_OK) return bail(rc);
+    }
+#undef CUT
+    *out = t;
+    return NDPB_OK;
+}
+
+extern "C" int64_t ndpb_table_nverts(const ndpb_table *t) { return t ? t->g.nverts : 0; }
+
+extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t value)
+{
+    if (!t || !key) return fail(NDPB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(t->mu);
+    CU(cudaSetDevice(t->device));
+    std::string k(key);
+    if (k == "gather") {
+        if (value < 0 || value > 2) return fail(NDPB_ERR_INVALID, "gather must be 0, 1 or 2");
+        t->opt_gather = (int) value;
+        if (value == 1 && t->cells) { CU(cudaDeviceSynchronize()); CU(cudaFree(t->cells)); t->cells = nullptr; }
+        if (value != 1 && t->has_grid) return maybe_build_cells(t);
+        return NDPB_OK;
+    }
+    if (k == "linear_search") {
+        if (value < 0 || value > 2) return fail(NDPB_ERR_INVALID, "linear_search must be 0, 1 or 2");
+        t->opt_linear_search = (int) value;
+        return NDPB_OK;
+    }
+    if (k == "stream") {
+        // run the kernels on a caller-owned stream (e.g. torch's current stream) so that the
+        // caller's CUDA events bracket them; 0 restores the table's own stream
+        CU(cudaStreamSynchronize(t->s_compute));
+        t->s_compute = value ? (cudaStream_t) (uintptr_t) value : t->s_owned;
+        return NDPB_OK;
+    }
+    if (k == "chunk") {
+        if (value < 1024) return fail(NDPB_ERR_INVALID, "chunk must be >= 1024");
+        t->opt_chunk = value;
+        return NDPB_OK;
+    }
+    return fail(NDPB_ERR_INVALID, "unknown option " + k);
+}
+
+extern "C" int64_t ndpb_table_stat(const ndpb_table *t, const char *key)
+{
+    if (!t || !key) return -1;
+    std::string k(key);
+    if (k == "launches") return t->st_launches;
+    if (k == "offgrid") return t->st_offgrid;
+    if (k == "hard") return t->st_hard;
+    if (k == "ties") return t->st_ties;
+    if (k == "h2d_bytes") return t->st_h2d;
+    if (k == "d2h_bytes") return t->st_d2h;
+    if (k == "cellmajor") return t->cells ? 1 : 0;
+    if (k == "main_ns") return (int64_t) (t->st_main_ms * 1e6);
+    if (k == "search_ns") return (int64_t) (t->st_search_ms * 1e6);
+    if (k == "finish_ns") return (int64_t) (t->st_finish_ms * 1e6);
+    if (k == "tree_levels_nearest") return t->topo[0].levels;
+    if (k == "tree_levels_linear") return t->topo[1].levels;
+    return -1;
+}
+
+extern "C" int ndpb_table_masks(ndpb_table *t, int32_t *vmask, int32_t *hcmask)
+{
+    if (!t || !vmask || !hcmask) return fail(NDPB_ERR_INVALID, "NULL argument");
+    if (!t->has_grid) return fail(NDPB_ERR_STATE, "axes-only table has no masks");
+    std::lock_guard<std::mutex> lk(t->mu);
+    CU(cudaSetDevice(t->device));
+    int32_t *outs[2] = {vmask, hcmask};
+    for (int m = 0; m < 2; m++) {
+        int32_t *dst = outs[m];
+        int32_t *tmp = nullptr;
+        const bool dev = is_device_ptr(dst);
+        if (!dev) CU(cudaMalloc(&tmp, sizeof(int32_t) * t->g.nverts));
+        k_unpack_bits<<<blocks_for(t->g.nverts), NDP_BLOCK, 0, t->s_compute>>>(t->pyr[m].dev.bits[0], t->g.nverts, dev ? dst : tmp);
+        CU(cudaGetLastError());
+        if (!dev) {
+            CU(cudaMemcpyAsync(dst, tmp, sizeof(int32_t) * t->g.nverts, cudaMemcpyDeviceToHost, t->s_compute));
+            CU(cudaStreamSynchronize(t->s_compute));
+            CU(cudaFree(tmp));
+        }
+    }
+    CU(cudaStreamSynchronize(t->s_compute));
+    return NDPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kd topology (lazy, per method -- like the reference's lazy trees, ndpolator.c:218-221)
+// ---------------------------------------------------------------------------
+struct BitSet {
+    const uint32_t *bits;
+    __host__ __device__ bool operator()(int v) const { return (bits[v >> 5] >> (v & 31)) & 1u; }
+};
+
+static int ensure_topology(ndpb_table *t, int m)
+{
+    Topology &T = t->topo[m];
+    if (T.built) return NDPB_OK;
+    const NdpGeom &g = t->g;
+    cudaStream_t st = t->s_compute;
+    const int nv = g.nverts;
+    CU(cudaMalloc(&T.parent, sizeof(int) * nv));
+    CU(cudaMalloc(&T.depth, sizeof(int) * nv));
+    k_fill_int<<<t->sm_count * 8, NDP_BLOCK, 0, st>>>(T.parent, nv, -2);
+    k_fill_int<<<t->sm_count * 8, NDP_BLOCK, 0, st>>>(T.depth, nv, -1);
+
+    // ascending ids of the masked vertices
+    int *ids[2] = {nullptr, nullptr}, *ss[2] = {nullptr, nullptr}, *se[2] = {nullptr, nullptr};
+    int *flag = nullptr, *scan = nullptr, *d_count = nullptr, *d_active = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0, need = 0;
+    CU(cudaMalloc(&ids[0], sizeof(int) * (size_t) nv));
+    CU(cudaMalloc(&d_count, sizeof(int)));
+    CU(cudaMalloc(&d_active, sizeof(int)));
+    thrust::counting_iterator<int> counting(0);
+    BitSet pred{t->pyr[m].dev.bits[0]};
+    CU(cub::DeviceSelect::If(nullptr, need, counting, ids[0], d_count, nv, pred, st));
+    tmp_bytes = need;
+    CU(cudaMalloc(&tmp, tmp_bytes));
+    CU(cub::DeviceSelect::If(tmp, tmp_bytes, counting, ids[0], d_count, nv, pred, st));
+    int N = 0;
+    CU(cudaMemcpyAsync(&N, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t->pyr[m].count = N;
+
+    int levels = 0;
+    if (N > 0) {
+        CU(cudaMalloc(&ids[1], sizeof(int) * (size_t) N));
+        for (int b = 0; b < 2; b++) { CU(cudaMalloc(&ss[b], sizeof(int) * (size_t) N)); CU(cudaMalloc(&se[b], sizeof(int) * (size_t) N)); }
+        CU(cudaMalloc(&flag, sizeof(int) * ((size_t) N + 1)));
+        CU(cudaMalloc(&scan, sizeof(int) * ((size_t) N + 1)));
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, need, flag, scan, N + 1, st));
+        if (need > tmp_bytes) { CU(cudaFree(tmp)); tmp_bytes = need; CU(cudaMalloc(&tmp, tmp_bytes)); }
+        k_topo_init<<<blocks_for(N), NDP_BLOCK, 0, st>>>(N, ss[0], se[0], ids[0], T.parent, T.depth);
+        int cur = 0;
+        for (int depth = 0;; depth++) {
+            TopoArgs A{};
+            A.g = g; A.N = N; A.axis = depth % g.nbasic; A.depth = depth;
+            A.ids = ids[cur]; A.seg_start = ss[cur]; A.seg_end = se[cur];
+            A.flag = flag; A.scan = scan;
+            A.ids2 = ids[cur ^ 1]; A.seg_start2 = ss[cur ^ 1]; A.seg_end2 = se[cur ^ 1];
+            A.parent = T.parent; A.depthv = T.depth; A.active = d_active;
+            CU(cudaMemsetAsync(d_active, 0, sizeof(int), st));
+            k_topo_flags<<<blocks_for(N + 1), NDP_BLOCK, 0, st>>>(A);
+            CU(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, scan, N + 1, st));
+            k_topo_scatter<<<blocks_for(N), NDP_BLOCK, 0, st>>>(A);
+            CU(cudaGetLastError());
+            int active = 0;
+            CU(cudaMemcpyAsync(&active, d_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            cur ^= 1;
+            levels = depth + 2;
+            if (active == 0) break;
+        }
+    }
+    for (int b = 0; b < 2; b++) { cudaFree(ids[b]); cudaFree(ss[b]); cudaFree(se[b]); }
+    cudaFree(flag); cudaFree(scan); cudaFree(tmp); cudaFree(d_count); cudaFree(d_active);
+    T.levels = levels;
+    T.built = true;
+    return NDPB_OK;
+}
+
+extern "C" int ndpb_table_tree_topology(ndpb_table *t, int method, int32_t *parent, int32_t *depth)
+{
+    if (!t || !parent || !depth) return fail(NDPB_ERR_INVALID, "NULL argument");
+    if (!t->has_grid) return fail(NDPB_ERR_STATE, "axes-only table has no tree");
+    if (method != NDPB_METHOD_NEAREST && method != NDPB_METHOD_LINEAR) return fail(NDPB_ERR_INVALID, "method must be NEAREST or LINEAR");
+    std::lock_guard<std::mutex> lk(t->mu);
+    CU(cudaSetDevice(t->device));
+    const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;
+    int rc = ensure_topology(t, m);
+    if (rc != NDPB_OK) return rc;
+    CU(cudaMemcpy(parent, t->topo[m].parent, sizeof(int) * t->g.nverts, cudaMemcpyDefault));
+    CU(cudaMemcpy(depth, t->topo[m].depth, sizeof(int) * t->g.nverts, cudaMemcpyDefault));
+    return NDPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batches
+// ---------------------------------------------------------------------------
+static int ensure_slot(ndpb_table *t, Slot &s, long long nq, bool stage_q, bool stage_interps, bool stage_dists,
+                       bool stage_coords, bool work)
+{
+    const NdpGeom &g = t->g;
+    if (!s.ctr) {
+        CU(cudaMalloc(&s.ctr, sizeof(NdpCounters)));
+        CU(cudaMallocHost(&s.ctr_host, sizeof(NdpCounters)));
+        cudaEvent_t *ev[] = {&s.in_done, &s.searched, &s.out_ready, &s.out_done};
+        for (auto e : ev) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        cudaEvent_t *tv[] = {&s.t0, &s.t1, &s.t2, &s.t3};
+        for (auto e : tv) CU(cudaEventCreate(e));
+    }
+    if ((stage_q || stage_interps || stage_dists) && nq > s.cap_q) {
+        CU(cudaStreamSynchronize(t->s_compute)); CU(cudaStreamSynchronize(t->s_in)); CU(cudaStreamSynchronize(t->s_out));
+        cudaFree(s.q); cudaFree(s.interps); cudaFree(s.dists);
+        s.q = s.interps = s.dists = nullptr; s.cap_q = 0;
+        CU(cudaMalloc(&s.q, sizeof(double) * nq * g.naxes));
+        CU(cudaMalloc(&s.interps, sizeof(double) * nq * g.vdim));
+        CU(cudaMalloc(&s.dists, sizeof(double) * nq));
+        s.cap_q = nq;
+    }
+    if (stage_coords && nq > s.cap_coords) {
+        CU(cudaStreamSynchronize(t->s_compute)); CU(cudaStreamSynchronize(t->s_out));
+        cudaFree(s.coords); s.coords = nullptr; s.cap_coords = 0;
+        CU(cudaMalloc(&s.coords, sizeof(int) * nq * g.naxes));
+        s.cap_coords = nq;
+    }
+    if (work && nq > s.cap_work) {
+        CU(cudaStreamSynchronize(t->s_compute));
+        cudaFree(s.list); cudaFree(s.chosen); cudaFree(s.tielist);
+        s.list = s.chosen = s.tielist = nullptr; s.cap_work = 0;
+        CU(cudaMalloc(&s.list, sizeof(int) * nq));
+        CU(cudaMalloc(&s.chosen, sizeof(int) * nq));
+        CU(cudaMalloc(&s.tielist, sizeof(int) * nq));
+        s.cap_work = nq;
+    }
+    return NDPB_OK;
+}
+
+template <int N, bool CM>
+static int launch_main_g(ndpb_table *t, const MainArgs &A, int G, int blocks, size_t smem, cudaStream_t st)
+{
+    switch (G) {
+    case 1: k_main<N, 1, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 2: k_main<N, 2, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 4: k_main<N, 4, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 8: k_main<N, 8, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 16: k_main<N, 16, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    default: k_main<N, 32, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    }
+    CU(cudaGetLastError());
+    t->st_launches++;
+    return NDPB_OK;
+}
+
+template <bool CM>
+static int launch_main_n(ndpb_table *t, const MainArgs &A, int G, int blocks, size_t smem, cudaStream_t st)
+{
+    switch (t->g.naxes) {
+    case 1: return launch_main_g<1, CM>(t, A, G, blocks, smem, st);
+    case 2: return launch_main_g<2, CM>(t, A, G, blocks, smem, st);
+    case 3: return launch_main_g<3, CM>(t, A, G, blocks, smem, st);
+    case 4: return launch_main_g<4, CM>(t, A, G, blocks, smem, st);
+    case 5: return launch_main_g<5, CM>(t, A, G, blocks, smem, st);
+    case 6: return launch_main_g<6, CM>(t, A, G, blocks, smem, st);
+    default: return launch_main_g<0, false>(t, A, G, blocks, smem, st);
+    }
+}
+
+static int launch_main(ndpb_table *t, const MainArgs &A, cudaStream_t st)
+{
+    const NdpGeom &g = t->g;
+    int G = 1;
+    while (G < g.vdim && G < 32) G <<= 1;
+    const long long groups_per_block = NDP_BLOCK / G;
+    const int blocks = (int) std::min<long long>((A.n + groups_per_block - 1) / groups_per_block, (long long) t->sm_count * 8);
+    const size_t smem = smem_bytes(t);
+    return A.cells ? launch_main_n<true>(t, A, G, blocks, smem, st) : launch_main_n<false>(t, A, G, blocks, smem, st);
+}
+
+template <bool CM>
+static int launch_finish_n(ndpb_table *t, const FinishArgs &A, cudaStream_t st)
+{
+    const int blocks = t->sm_count * 8;
+    const size_t smem = smem_bytes(t);
+    switch (t->g.naxes) {
+    case 1: k_finish<1, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 2: k_finish<2, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 3: k_finish<3, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 4: k_finish<4, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 5: k_finish<5, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 6: k_finish<6, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    default: k_finish<0, false><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    }
+    CU(cudaGetLastError());
+    t->st_launches++;
+    return NDPB_OK;
+}
+
+static int launch_finish(ndpb_table *t, const FinishArgs &A, cudaStream_t st)
+{
+    return A.cells ? launch_finish_n<true>(t, A, st) : launch_finish_n<false>(t, A, st);
+}
+
+static bool use_brute(const ndpb_table *t, int search)
+{
+    if (search != NDPB_SEARCH_LINEAR) return false;
+    if (t->opt_linear_search == 1) return true;
+    if (t->opt_linear_search == 2) return false;
+    return t->g.nverts <= 4096;      // the literal scan only where it is cheap; identical results either way
+}
+
+static int launch_search(ndpb_table *t, SearchArgs &A, long long upper, cudaStream_t st)
+{
+    const int m = A.method == NDPB_METHOD_LINEAR ? 1 : 0;
+    A.g = t->g; A.P = t->pyr[m].dev;
+    A.have_topo = t->topo[m].built ? 1 : 0;
+    A.topo.parent = t->topo[m].parent; A.topo.depth = t->topo[m].depth;
+    A.ticks = t->ticks; A.nticks = t->nticks; A.ticks_in_smem = ticks_in_smem(t);
+    const size_t smem = smem_bytes(t);
+    if (use_brute(t, A.search) && !A.sublist) {
+        const int blocks = (int) std::min<long long>((upper * 32 + NDP_BLOCK - 1) / NDP_BLOCK, (long long) t->sm_count * 8);
+        k_search_brute<<<std::max(blocks, 1), NDP_BLOCK, smem, st>>>(A);
+    } else {
+        const int blocks = (int) std::min<long long>((upper + NDP_BLOCK - 1) / NDP_BLOCK, (long long) t->sm_count * 8);
+        k_search<<<std::max(blocks, 1), NDP_BLOCK, smem, st>>>(A);
+    }
+    CU(cudaGetLastError());
+    t->st_launches++;
+    return NDPB_OK;
+}
+
+enum Task { TASK_NDPOLATE, TASK_NEAREST, TASK_DISTANCE };
+
+// Enqueues everything that needs no host decision for one batch resident on the device.
+static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, long long n, int method, int search,
+                         double *interps, double *dists, int *coords)
+{
+    cudaStream_t st = t->s_compute;
+    CU(cudaMemsetAsync(s.ctr, 0, sizeof(NdpCounters), st));
+    CU(cudaEventRecord(s.t0, st));
+    if (task == TASK_NDPOLATE) {
+        MainArgs M{};
+        M.g = t->g; M.ticks = t->ticks; M.nticks = t->nticks; M.ticks_in_smem = ticks_in_smem(t);
+        M.grid = t->grid; M.cells = t->cells; M.q = q; M.n = n;
+        M.interps = interps; M.dists = dists; M.method = method; M.offlist = s.list; M.ctr = s.ctr;
+        int rc = launch_main(t, M, st);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(s.t1, st));
+    if (task != TASK_NDPOLATE || method != NDPB_METHOD_NONE) {
+        SearchArgs S{};
+        S.q = q; S.method = method; S.search = search;
+        S.list = (task == TASK_NDPOLATE) ? s.list : nullptr;
+        S.sublist = nullptr;
+        S.count = (task == TASK_NDPOLATE) ? &s.ctr->n_off : nullptr;
+        S.count_host = n;
+        S.chosen = s.chosen; S.dists = dists; S.coords = coords; S.tielist = s.tielist; S.ctr = s.ctr;
+        int rc = launch_search(t, S, n, st);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(s.t2, st));
+    if (task == TASK_NDPOLATE && method != NDPB_METHOD_NONE) {
+        FinishArgs F{};
+        F.g = t->g; F.ticks = t->ticks; F.nticks = t->nticks; F.ticks_in_smem = ticks_in_smem(t);
+        F.grid = t->grid; F.cells = t->cells; F.q = q; F.method = method;
+        F.list = s.list; F.sublist = nullptr; F.count = &s.ctr->n_off; F.chosen = s.chosen; F.interps = interps;
+        int rc = launch_finish(t, F, st);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(s.t3, st));
+    CU(cudaMemcpyAsync(s.ctr_host, s.ctr, sizeof(NdpCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(s.searched, st));
+    s.used = true;
+    return NDPB_OK;
+}
+
+// Waits for the batch, settles kd ties through the topology if any turned up.
+static int batch_complete(ndpb_table *t, Slot &s, Task task, const double *q, long long n, int method, int search,
+                          double *interps, double *dists, int *coords)
+{
+    cudaStream_t st = t->s_compute;
+    CU(cudaEventSynchronize(s.searched));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.t0, s.t1) == cudaSuccess) t->st_main_ms += ms;
+    if (cudaEventElapsedTime(&ms, s.t1, s.t2) == cudaSuccess) t->st_search_ms += ms;
+    if (cudaEventElapsedTime(&ms, s.t2, s.t3) == cudaSuccess) t->st_finish_ms += ms;
+    const NdpCounters c = *s.ctr_host;
+    t->st_offgrid += (task == TASK_NDPOLATE) ? c.n_off : (method == NDPB_METHOD_NONE ? 0 : n);
+    t->st_hard += c.n_hard;
+    if (c.n_tie > 0) {
+        const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;
+        int rc = ensure_topology(t, m);
+        if (rc) return rc;
+        SearchArgs S{};
+        S.q = q; S.method = method; S.search = search;
+        S.list = (task == TASK_NDPOLATE) ? s.list : nullptr;
+        S.sublist = s.tielist; S.count = &s.ctr->n_tie; S.count_host = 0;
+        S.chosen = s.chosen; S.dists = dists; S.coords = coords; S.tielist = s.tielist; S.ctr = s.ctr;
+        rc = launch_search(t, S, c.n_tie, st);
+        if (rc) return rc;
+        if (task == TASK_NDPOLATE) {
+            FinishArgs F{};
+            F.g = t->g; F.ticks = t->ticks; F.nticks = t->nticks; F.ticks_in_smem = ticks_in_smem(t);
+            F.grid = t->grid; F.cells = t->cells; F.q = q; F.method = method;
+            F.list = s.list; F.sublist = s.tielist; F.count = &s.ctr->n_tie; F.chosen = s.chosen; F.interps = interps;
+            rc = launch_finish(t, F, st);
+            if (rc) return rc;
+        }
+        t->st_ties += c.n_tie;
+    }
+    CU(cudaEventRecord(s.out_ready, st));
+    return NDPB_OK;
+}
+
+static void reset_stats(ndpb_table *t)
+{
+    t->st_launches = t->st_offgrid = t->st_hard = t->st_ties = t->st_h2d = t->st_d2h = 0;
+    t->st_main_ms = t->st_search_ms = t->st_finish_ms = 0;
+}
+
+// Drives one API call: device-resident callers run as one batch per 2^30 queries;
+// host callers are cut into chunks whose H2D copy, kernels and D2H copy overlap
+// across two slots and three streams.
+static int run_call(ndpb_table *t, Task task, const double *q, long long n, int method, int search,
+                    double *interps, double *dists, int *coords)
+{
+    const NdpGeom &g = t->g;
+    reset_stats(t);
+    if (n == 0) return NDPB_OK;
+    const bool q_dev = is_device_ptr(q);
+    const bool i_dev = !interps || is_device_ptr(interps);
+    const bool d_dev = !dists || is_device_ptr(dists);
+    const bool c_dev = !coords || is_device_ptr(coords);
+    const bool all_dev = q_dev && i_dev && d_dev && c_dev;
+    const long long chunk = all_dev ? (1LL << 30) : t->opt_chunk;
+    const long long nchunks = (n + chunk - 1) / chunk;
+    const bool need_dists = true;     // the search always writes distances
+
+    auto stage_in = [&](long long c) -> int {
+        Slot &s = t->slot[c & 1];
+        const long long lo = c * chunk, cnt = std::min(chunk, n - lo);
+        int rc = ensure_slot(t, s, cnt, !q_dev || !i_dev || !d_dev, false, false, coords && !c_dev, true);
+        if (rc) return rc;
+        if (!q_dev) {
+            if (s.used) CU(cudaStreamWaitEvent(t->s_in, s.out_done, 0));   // slot's previous results are out
+            CU(cudaMemcpyAsync(s.q, q + lo * g.naxes, sizeof(double) * cnt * g.naxes, cudaMemcpyHostToDevice, t->s_in));
+            CU(cudaEventRecord(s.in_done, t->s_in));
+            t->st_h2d += sizeof(double) * cnt * g.naxes;
+        }
+        return NDPB_OK;
+    };
+
+    int rc = stage_in(0);
+    if (rc) return rc;
+    for (long long c = 0; c < nchunks; c++) {
+        Slot &s = t->slot[c & 1];
+        const long long lo = c * chunk, cnt = std::min(chunk, n - lo);
+        const double *qd = q_dev ? q + lo * g.naxes : s.q;
+        double *id = !interps ? nullptr : (i_dev ? interps + lo * g.vdim : s.interps);
+        double *dd = (dists && d_dev) ? dists + lo : s.dists;
+        int *cd = !coords ? nullptr : (c_dev ? coords + lo * g.naxes : s.coords);
+        if (!dd) { rc = ensure_slot(t, s, cnt, true, false, false, false, true); if (rc) return rc; dd = s.dists; }
+        if (!q_dev) CU(cudaStreamWaitEvent(t->s_compute, s.in_done, 0));
+        if (s.used) CU(cudaStreamWaitEvent(t->s_compute, s.out_done, 0));
+        rc = batch_enqueue(t, s, task, qd, cnt, method, search, id, dd, cd);
+        if (rc) return rc;
+        if (c + 1 < nchunks) { rc = stage_in(c + 1); if (rc) return rc; }
+        rc = batch_complete(t, s, task, qd, cnt, method, search, id, dd, cd);
+        if (rc) return rc;
+        CU(cudaStreamWaitEvent(t->s_out, s.out_ready, 0));
+        if (interps && !i_dev) {
+            CU(cudaMemcpyAsync(interps + lo * g.vdim, s.interps, sizeof(double) * cnt * g.vdim, cudaMemcpyDeviceToHost, t->s_out));
+            t->st_d2h += sizeof(double) * cnt * g.vdim;
+        }
+        if (dists && !d_dev && need_dists) {
+            CU(cudaMemcpyAsync(dists + lo, s.dists, sizeof(double) * cnt, cudaMemcpyDeviceToHost, t->s_out));
+            t->st_d2h += sizeof(double) * cnt;
+        }
+        if (coords && !c_dev) {
+            CU(cudaMemcpyAsync(coords + lo * g.naxes, s.coords, sizeof(int) * cnt * g.naxes, cudaMemcpyDeviceToHost, t->s_out));
+            t->st_d2h += sizeof(int) * cnt * g.naxes;
+        }
+        CU(cudaEventRecord(s.out_done, t->s_out));
+    }
+    CU(cudaStreamSynchronize(t->s_compute));
+    CU(cudaStreamSynchronize(t->s_out));
+    return NDPB_OK;
+}
+
+static int check_call(ndpb_table *t, const void *q, long long n, bool needs_grid)
+{
+    if (!t) return fail(NDPB_ERR_INVALID, "table is NULL");
+    if (n < 0) return fail(NDPB_ERR_INVALID, "negative query count");
+    if (n > 0 && !q) return fail(NDPB_ERR_INVALID, "query_pts is NULL");
+    if (needs_grid && !t->has_grid) return fail(NDPB_ERR_STATE, "this call needs a table created with a grid");
+    return NDPB_OK;
+}
+
+extern "C" int ndpb_ndpolate(ndpb_table *t, const double *query_pts, int64_t n, int method, int search,
+                             double *interps, double *dists)
+{
+    int rc = check_call(t, query_pts, n, true);
+    if (rc) return rc;
+    if (method < NDPB_METHOD_NONE || method > NDPB_METHOD_LINEAR) return fail(NDPB_ERR_INVALID, "invalid extrapolation method");
+    if (search < NDPB_SEARCH_KDTREE || search > NDPB_SEARCH_LINEAR) return fail(NDPB_ERR_INVALID, "invalid search algorithm");
+    if (n > 0 && (!interps || !dists)) return fail(NDPB_ERR_INVALID, "output pointer is NULL");
+    std::lock_guard<std::mutex> lk(t->mu);
+    CU(cudaSetDevice(t->device));
+    return run_call(t, TASK_NDPOLATE, query_pts, n, method, search, interps, dists, nullptr);
+}
+
+extern "C" int ndpb_find_nearest(ndpb_table *t, const double *query_pts, int64_t n, int method, int search,
+                                 int32_t *coords, double *dist)
+{
+    int rc = check_call(t, query_pts, n, true);
+    if (rc) return rc;
+    if (method != NDPB_METHOD_NEAREST && method != NDPB_METHOD_LINEAR) return fail(NDPB_ERR_INVALID, "method must be NEAREST or LINEAR");
+    if (search < NDPB_SEARCH_KDTREE || search > NDPB_SEARCH_LINEAR) return fail(NDPB_ERR_INVALID, "invalid search algorithm");
+    if (n > 0 && (!coords || !dist)) return fail(NDPB_ERR_INVALID, "output pointer is NULL");
+    std::lock_guard<std::mutex> lk(t->mu);
+    CU(cudaSetDevice(t->device));
+    return run_call(t, TASK_NEAREST, query_pts, n, method, search, nullptr, dist, coords);
+}
+
+extern "C" int ndpb_distance(ndpb_table *t, const double *query_pts, int64_t n, double *dists)
+{
+    int rc = check_call(t, query_pts, n, true);
+    if (rc) return rc;
+    if (n > 0 && !dists) return fail(NDPB_ERR_INVALID, "output pointer is NULL");
+    std::lock_guard<std::mutex> lk(t->mu);
+    CU(cudaSetDevice(t->device));
+    return run_call(t, TASK_DISTANCE, query_pts, n, NDPB_METHOD_LINEAR, NDPB_SEARCH_KDTREE, nullptr, dists, nullptr);
+}
+
+// taps: simple synchronous staging (they are parity instruments, not the hot path)
+template <class T>
+struct Staged {
+    T *dev = nullptr; T *user = nullptr; size_t count = 0; bool own = false;
+    int in(const T *p, size_t n) {
+        user = const_cast<T *>(p); count = n;
+        if (is_device_ptr(p) || n == 0) { dev = user; return NDPB_OK; }
+        own = true;
+        CU(cudaMalloc(&dev, sizeof(T) * n));
+        CU(cudaMemcpy(dev, p, sizeof(T) * n, cudaMemcpyHostToDevice));
+        return NDPB_OK;
+    }
+    int out(T *p, size_t n) {
+        user = p; count = n;
+        if (is_device_ptr(p) || n == 0) { dev = p; return NDPB_OK; }
+        own = true;
+        CU(cudaMalloc(&dev, sizeof(T) * n));
+        return NDPB_OK;
+    }
+    int back() {
+        if (own) CU(cudaMemcpy(user, dev, sizeof(T) * count, cudaMemcpyDeviceToHost));
+        return NDPB_OK;
+    }
+    ~Staged() { if (own) cudaFree(dev); }
+};
+
+extern "C" int ndpb_find(ndpb_table *t, const double *query_pts, int64_t n,
+                         int32_t *indices, int32_t *flags, double *normed)
+{
+    int rc = check_call(t, query_pts, n, false);
+    if (rc) return rc;
+    if (n > 0 && (!indices || !flags || !normed)) return fail(NDPB_ERR_INVALID, "output pointer is NULL");
+    std::lock_guard<std::mutex> lk(t->mu);
+    CU(cudaSetDevice(t->device));
+    reset_stats(t);
+    if (n == 0) return NDPB_OK;
+    const size_t e = (size_t) n * t->g.naxes;
+    Staged<double> q, nrm; Staged<int32_t> idx, flg;
+    if ((rc = q.in(query_pts, e)) || (rc = idx.out(indices, e)) || (rc = flg.out(flags, e)) || (rc = nrm.out(normed, e))) return rc;
+    ImportArgs A{};
+    A.g = t->g; A.ticks = t->ticks; A.nticks = t->nticks; A.ticks_in_smem = ticks_in_smem(t);
+    A.q = q.dev; A.n = n; A.indices = idx.dev; A.flags = flg.dev; A.normed = nrm.dev;
+    const int blocks = (int) std::min<long long>(((long long) e + NDP_BLOCK - 1) / NDP_BLOCK, (long long) t->sm_count * 16);
+    k_import<<<blocks, NDP_BLOCK, smem_bytes(t), t->s_compute>>>(A);
+    CU(cudaGetLastError());
+    t->st_launches++;
+    CU(cudaStreamSynchronize(t->s_compute));
+    if ((rc = idx.back()) || (rc = flg.back()) || (rc = nrm.back())) return rc;
+    return NDPB_OK;
+}
+
+extern "C" int ndpb_hypercubes(ndpb_table *t, const double *normed, const int32_t *indices, const int32_t *flags,
+                               int64_t n, int32_t *dim, int32_t *fdhc, double *v)
+{
+    int rc = check_call(t, normed, n, true);
+    if (rc) return rc;
+    if (n > 0 && (!indices || !flags || !dim || !fdhc || !v)) return fail(NDPB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(t->mu);
+    CU(cudaSetDevice(t->device));
+    reset_stats(t);
+    if (n == 0) return NDPB_OK;
+    const size_t e = (size_t) n * t->g.naxes;
+    const size_t slot = ((size_t) 1 << t->g.naxes) * t->g.vdim;
+    Staged<double> nrm, vv; Staged<int32_t> idx, flg, dm, fd;
+    if ((rc = nrm.in(normed, e)) || (rc = idx.in(indices, e)) || (rc = flg.in(flags, e)) ||
+        (rc = dm.out(dim, n)) || (rc = fd.out(fdhc, n)) || (rc = vv.out(v, (size_t) n * slot))) return rc;
+    HypercubeArgs A{};
+    A.g = t->g; A.grid = t->grid; A.normed = nrm.dev; A.indices = idx.dev; A.flags = flg.dev; A.n = n;
+    A.dim = dm.dev; A.fdhc = fd.dev; A.v = vv.dev;
+    k_hypercubes<<<blocks_for(n), NDP_BLOCK, 0, t->s_compute>>>(A);
+    CU(cudaGetLastError());
+    t->st_launches++;
+    CU(cudaStreamSynchronize(t->s_compute));
+    if ((rc = dm.back()) || (rc = fd.back()) || (rc = vv.back())) return rc;
+    return NDPB_OK;
+}

@@ -1,0 +1,585 @@
+// ndp_core.cuh -- per-query arithmetic of the ndpolate hot path, written once as
+// __host__ __device__ inline functions.  The CUDA kernels in ndp_kernels.cuh are
+// the product; tests/hostsim/ compiles the very same functions for the host so
+// that the logic can be diffed against the oracle in the CPU-only container
+// before any GPU time is spent.  (That host build is test scaffolding: it is not
+// part of libndpb200.so and the product never falls back to it.)
+//
+// Numerics contract (BASELINE.json north_star): fp64 everywhere, compiled with
+// -fmad=false so that every a+b*c keeps the two roundings of the reference's
+// x86-64 build; sums run in the reference's order.  Citations are to the
+// reference tree (src/ndpolator.c unless another file is named).
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define NDP_HD __host__ __device__ __forceinline__
+#else
+#define NDP_HD inline
+struct double2 { double x, y; };
+#endif
+
+#define NDP_MAX_AXES 12
+#define NDP_MAX_LEVELS 18      // occupancy pyramid: ceil(log2(65536)) + 2
+
+// extrapolation methods / search algorithms / flags: src/ndpolator.h:28-63
+#define NDP_M_NONE 0
+#define NDP_M_NEAREST 1
+#define NDP_M_LINEAR 2
+#define NDP_S_KDTREE 0
+#define NDP_S_LINEAR 1
+#define NDP_F_ON_VERTEX 1
+#define NDP_F_OOB 2
+
+// search "mode" = which metric picks the winner and how ties are broken
+#define NDP_MODE_KD_NEAREST 0   // kd_nearest over vmask vertices           (:223-254, kdtree.c:345-457)
+#define NDP_MODE_KD_LINEAR 1    // kd_nearest over hcmask cell centres       (:126-127, :255-258)
+#define NDP_MODE_LS_NEAREST 2   // full scan, all-axes vertex distance       (:279-329, :300-309)
+#define NDP_MODE_LS_LINEAR 3    // full scan, ndp_distance to the cell       (:310-313)
+
+NDP_HD int ndp_mode_of(int method, int search)
+{
+    return (search == NDP_S_KDTREE ? 0 : 2) + (method == NDP_M_LINEAR ? 1 : 0);
+}
+
+// Table geometry, passed to kernels by value.
+struct NdpGeom {
+    int naxes, nbasic, vdim;
+    int len[NDP_MAX_AXES];            // ticks per axis
+    int tickoff[NDP_MAX_AXES];        // start of axis a in the concatenated tick array
+    long long vstride[NDP_MAX_AXES];  // vertices per +1 on axis a, all axes (ndp_types.c:59-65 `cplen`)
+    long long cstride[NDP_MAX_AXES];  // cells per +1 on axis a in the (len-1)^n cell lattice
+    int bstride[NDP_MAX_AXES];        // same as vstride but within the basic-only lattice
+    int nverts;                       // basic lattice size (ndp_types.c:174-176); < 2^31 like the reference's int
+    long long ncells;
+};
+
+// Bit-packed occupancy pyramid over the basic lattice.  Level 0 = one bit per
+// basic vertex (vmask or hcmask); level L = one bit per 2^L-wide block, set when
+// any vertex inside is set; the last level is a single block.
+struct NdpPyramid {
+    int nlev;
+    int dim[NDP_MAX_LEVELS][NDP_MAX_AXES];
+    int stride[NDP_MAX_LEVELS][NDP_MAX_AXES];
+    const uint32_t *bits[NDP_MAX_LEVELS];
+    int first_clear;                  // lowest vertex id whose level-0 bit is clear, or -1
+    int any_set;                      // 0 when the mask is empty
+};
+
+// Shape of the reference's insertion-ordered kd-tree (ndp_kdtree_create, :114-136),
+// per basic vertex id: parent vertex (-1 root, -2 absent) and depth.
+struct NdpTopo {
+    const int *parent;
+    const int *depth;
+};
+
+NDP_HD bool ndp_bit(const uint32_t *bits, int i)
+{
+    return (bits[i >> 5] >> (i & 31)) & 1u;
+}
+
+// ---------------------------------------------------------------------------
+// A1: per-axis index search (find_first_geq_than, :21-45; normalisation :379-381)
+// ---------------------------------------------------------------------------
+NDP_HD void ndp_import_axis(const double *tick, int len, double x, int &index, int &flag, double &normed)
+{
+    const double rtol = 1e-6;                   // :358
+    int lo = 1, hi = len - 1;
+    while (lo != hi) {                          // :24-33 -- note the absolute "+ rtol"
+        int mid = lo + ((hi - lo) >> 1);
+        if (x + rtol > tick[mid]) lo = mid + 1; else hi = mid;
+    }
+    int f = (x < tick[0] || x > tick[len - 1]) ? NDP_F_OOB : 0;    // :35
+    double t = (x - tick[lo - 1]) / (tick[lo] - tick[lo - 1]);     // :37 and :381 compute the same quotient
+    if (fabs(t) < rtol || (lo == len - 1 && fabs(t - 1) < rtol)) f |= NDP_F_ON_VERTEX;   // :37-39
+    index = lo; flag = f; normed = t;
+}
+
+// One lerp of c_ndpolate (:91): three roundings; -fmad=false keeps them apart.
+NDP_HD double ndp_lerp(double lo, double hi, double x)
+{
+    double diff = hi - lo;
+    double step = diff * x;
+    return lo + step;
+}
+
+// ---------------------------------------------------------------------------
+// A2 + A3 on one cell, one component.
+//
+// Corner j of the cell whose superior corner is `sup` has bit (n-1-a) <-> axis a
+// (axis 0 = most significant, :480 / :601).  Pinned axes (ON_VERTEX, :474-478)
+// select one side instead of interpolating; `sel` says which.  Corners that the
+// reference would not have gathered (the other side of a pinned axis) neither
+// count for the NaN test (:491) nor influence the result.
+//
+// LOAD(fv) fills fv[0 .. 2^N) with the corner values.  N > 0: axes known at compile
+// time, the whole cell lives in registers.  Returns the reduced value; nan_used
+// reports whether any *used* corner was NaN.
+// ---------------------------------------------------------------------------
+template <int N, class Load>
+NDP_HD double ndp_cell_reduce(Load load, const double *x, unsigned pinmask, unsigned selbits, bool &nan_used)
+{
+    double fv[1 << N];
+    load(fv);
+
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < (1 << N); j++) {
+        bool used = (((unsigned) j ^ selbits) & pinmask) == 0;
+        bad |= used && (fv[j] != fv[j]);
+    }
+    nan_used = bad;
+
+#pragma unroll
+    for (int a = 0; a < N; a++) {
+        const int h = 1 << (N - 1 - a);
+        const bool pinned = (pinmask >> (N - 1 - a)) & 1u;
+        const bool upper = (selbits >> (N - 1 - a)) & 1u;
+        const double xa = x[a];
+        // constant trip count so that the front end unrolls fully and fv[] stays in registers
+#pragma unroll
+        for (int j = 0; j < (N ? (1 << (N - 1)) : 1); j++) {
+            if (j < h) {
+                double l = ndp_lerp(fv[j], fv[j + h], xa);
+                double s = upper ? fv[j + h] : fv[j];
+                fv[j] = pinned ? s : l;
+            }
+        }
+    }
+    return fv[0];
+}
+
+// Runtime-n version (any n <= NDP_MAX_AXES): walks only the used corners in
+// "axis 0 fastest" order and folds them with a carry chain, which performs
+// exactly the lerps of c_ndpolate (:83-96) in an order that respects every data
+// dependence, with O(n) state.  free_ax[0..d) lists the non-pinned axes in
+// ascending order; FETCHV(bits) gets the corner whose free axis i is at the
+// upper side iff bit i of `bits` is set.
+template <class FetchV>
+NDP_HD double ndp_cell_reduce_rt(int d, FetchV fetchv, const double *xfree, bool &nan_used)
+{
+    double acc[NDP_MAX_AXES];
+    bool bad = false;
+    double val = 0.0;
+    for (unsigned c = 0; c < (1u << d); c++) {
+        val = fetchv(c);
+        bad |= (val != val);
+        int level = 0;
+        while ((c >> level) & 1u) {      // partner at this level is complete: combine (lower, upper)
+            val = ndp_lerp(acc[level], val, xfree[level]);
+            level++;
+        }
+        if (level < d) acc[level] = val;
+    }
+    nan_used = bad;
+    return val;
+}
+
+// ---------------------------------------------------------------------------
+// A5/A6: selection metric of the nearest search
+// ---------------------------------------------------------------------------
+
+// max(0, min(len-1, round(qc))) of :241, evaluated in double like the C macros.
+NDP_HD int ndp_assoc_coord(double qc, int len)
+{
+    double r = round(qc);
+    double hi = (double) (len - 1);
+    double m = hi < r ? hi : r;
+    double c = 0.0 > m ? 0.0 : m;
+    return (int) c;
+}
+
+// Per-axis contribution of a block of lattice coordinates [lo, hi] on a basic
+// axis.  For lo == hi this is the exact per-axis term of the reference metric;
+// for lo < hi it is the smallest term any coordinate inside can produce,
+// evaluated with the same roundings, so block sums never exceed vertex sums
+// (fl(a+b) is monotone in both arguments).
+NDP_HD double ndp_axis_term(int mode, double q, int lo, int hi)
+{
+    double d;
+    if (mode == NDP_MODE_KD_LINEAR) {            // cell centres c-0.5 (:126-127); kdtree.c:379-381, :745-759
+        double plo = (double) lo - 0.5, phi = (double) hi - 0.5;
+        if (q < plo) d = plo - q; else if (q > phi) d = phi - q; else d = 0.0;
+    } else if (mode == NDP_MODE_LS_LINEAR) {     // ndp_distance, :158-176: cell [c-1, c]
+        double clo = (double) lo - 1.0, chi = (double) hi;
+        if (q < clo) d = clo - q; else if (q > chi) d = q - chi; else d = 0.0;
+    } else {                                     // vertex at integer position (:245-254, :300-309; kdtree.c:379-381)
+        double plo = (double) lo, phi = (double) hi;
+        if (q < plo) d = plo - q; else if (q > phi) d = phi - q; else d = 0.0;
+    }
+    return d * d;
+}
+
+struct NdpQuery {                 // one imported query in index space
+    double qc[NDP_MAX_AXES];      // idx + normed - 1.0 (:226, :250)
+    int acoord[NDP_MAX_AXES];     // rounded/clamped tick of associated axes (:240-242)
+};
+
+// Sum of the associated-axis terms that the full-scan metrics append (:179-183, :304-308).
+NDP_HD double ndp_add_assoc(const NdpGeom &g, int mode, const NdpQuery &Q, double acc)
+{
+    if (mode >= NDP_MODE_LS_NEAREST)
+        for (int a = g.nbasic; a < g.naxes; a++) {
+            double diff = Q.qc[a] - (double) Q.acoord[a];
+            acc += diff * diff;
+        }
+    return acc;
+}
+
+NDP_HD double ndp_metric_vertex(const NdpGeom &g, int mode, const NdpQuery &Q, const int *c)
+{
+    double acc = 0.0;
+    for (int a = 0; a < g.nbasic; a++) acc += ndp_axis_term(mode, Q.qc[a], c[a], c[a]);
+    return ndp_add_assoc(g, mode, Q, acc);
+}
+
+// Reported squared distance once the winner is known (:245-258).
+NDP_HD double ndp_reported_dist(const NdpGeom &g, int method, const NdpQuery &Q, const int *coords)
+{
+    double acc = 0.0;
+    if (method == NDP_M_NEAREST) {
+        for (int a = 0; a < g.naxes; a++) {
+            double diff = Q.qc[a] - (double) coords[a];
+            acc += diff * diff;
+        }
+    } else {
+        for (int a = 0; a < g.nbasic; a++) acc += ndp_axis_term(NDP_MODE_LS_LINEAR, Q.qc[a], coords[a], coords[a]);
+        for (int a = g.nbasic; a < g.naxes; a++) {
+            double diff = Q.qc[a] - (double) coords[a];
+            acc += diff * diff;
+        }
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------
+// Tie resolution for the kd modes.
+//
+// kd_nearest (kdtree.c:404-457) seeds the best guess with the root and replaces
+// it only on a strictly smaller distance (:383); kd_nearest_i visits, at every
+// node, the nearer child's subtree, then the node, then (if not pruned) the
+// farther child's subtree.  A subtree holding a vertex at the minimum distance
+// cannot be pruned before that distance has been reached, so among several
+// vertices at exactly the minimum distance the reference returns the one that
+// comes first in that traversal order, except that the root beats everything.
+// For two candidates the order is decided at their lowest common ancestor.
+// ---------------------------------------------------------------------------
+NDP_HD double ndp_tree_pos(const NdpGeom &g, int mode, int v, int ax)
+{
+    double p = (double) ((v / g.bstride[ax]) % g.len[ax]);
+    return (mode == NDP_MODE_KD_LINEAR) ? p - 0.5 : p;
+}
+
+// true when vertex A precedes vertex B (A != B) in the reference's traversal for query Q
+NDP_HD bool ndp_tree_beats(const NdpGeom &g, int mode, const NdpTopo &T, const NdpQuery &Q, int A, int B)
+{
+    int a = A, b = B, ca = -1, cb = -1;          // ca/cb: child of the meeting node on A's / B's side
+    int da = T.depth[a], db = T.depth[b];
+    while (da > db) { ca = a; a = T.parent[a]; da--; }
+    while (db > da) { cb = b; b = T.parent[b]; db--; }
+    while (a != b) { ca = a; a = T.parent[a]; cb = b; b = T.parent[b]; da--; }
+    const int C = a;                             // lowest common ancestor, depth da
+    const int ax = da % g.nbasic;                // split axis cycles with depth (kdtree.c:189)
+    const double cpos = ndp_tree_pos(g, mode, C, ax);
+    const bool near_is_lo = (Q.qc[ax] - cpos) <= 0;          // kdtree.c:354-355
+    if (C == A) {                                // A is an ancestor of B
+        if (da == 0) return true;                // the root is the initial guess
+        bool b_is_lo = ndp_tree_pos(g, mode, cb, ax) < cpos; // kdtree.c:190
+        return !(b_is_lo == near_is_lo);         // B wins only from A's nearer subtree
+    }
+    if (C == B) {
+        if (da == 0) return false;
+        bool a_is_lo = ndp_tree_pos(g, mode, ca, ax) < cpos;
+        return a_is_lo == near_is_lo;
+    }
+    bool a_is_lo = ndp_tree_pos(g, mode, ca, ax) < cpos;
+    return a_is_lo == near_is_lo;
+}
+
+// ---------------------------------------------------------------------------
+// Exact nearest search on the lattice.
+//
+// Every candidate of the reference's search sits on the integer basic lattice,
+// so instead of walking its (unbalanced, 100s of levels deep) pointer tree we
+//  (1) try the lattice point the query rounds to and prove it the unique
+//      minimiser by checking its 2*nbasic axis neighbours (per-axis convexity +
+//      monotone rounding make that sufficient), and otherwise
+//  (2) run a branch-and-bound descent over the occupancy pyramid with an
+//      explicit per-thread stack, nearest child first, pruning blocks whose
+//      lower bound exceeds the best distance (ties are kept and resolved by the
+//      reference's own rule: tree order for the kd modes, lowest index for the
+//      full scan).
+// Distances are the reference's own expressions, so the winner is bit-exact.
+// ---------------------------------------------------------------------------
+
+#define NDP_SEARCH_OK 0
+#define NDP_SEARCH_TIE 1      // kd mode tie met without topology: caller must redo with NdpTopo
+#define NDP_SEARCH_EMPTY 2    // mask has no set bit
+
+struct NdpHit {
+    int vertex;      // winning basic vertex id
+    double dsel;     // its selection metric
+    int status;
+    int hard;        // 1 when step (2) ran
+};
+
+NDP_HD bool ndp_search_fast(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q, NdpHit &hit)
+{
+    const bool cells = (mode == NDP_MODE_KD_LINEAR || mode == NDP_MODE_LS_LINEAR);
+    int c[NDP_MAX_AXES];
+    int flat = 0;
+    for (int a = 0; a < g.nbasic; a++) {
+        const double lo = cells ? 1.0 : 0.0, hi = (double) (g.len[a] - 1);
+        double p = cells ? floor(Q.qc[a]) + 1.0 : rint(Q.qc[a]);
+        p = p < lo ? lo : (p > hi ? hi : p);     // NaN falls through; the neighbour test below then fails
+        c[a] = (int) p;
+        if (!(c[a] >= (int) lo && c[a] <= (int) hi)) return false;
+        flat += c[a] * g.bstride[a];
+    }
+    if (!ndp_bit(P.bits[0], flat)) return false;
+    const double d0 = ndp_metric_vertex(g, mode, Q, c);
+    if (!(d0 == d0)) return false;
+    for (int a = 0; a < g.nbasic; a++) {
+        const int keep = c[a];
+        for (int s = -1; s <= 1; s += 2) {
+            int t = keep + s;
+            if (t < (cells ? 1 : 0) || t > g.len[a] - 1) continue;
+            c[a] = t;
+            double d = ndp_metric_vertex(g, mode, Q, c);
+            c[a] = keep;
+            if (!(d > d0)) return false;
+        }
+    }
+    hit.vertex = flat; hit.dsel = d0; hit.status = NDP_SEARCH_OK; hit.hard = 0;
+    return true;
+}
+
+NDP_HD void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
+                            const NdpTopo *topo, NdpHit &hit)
+{
+    const int nb = g.nbasic;
+    const unsigned nchild = 1u << nb;
+    const int top = P.nlev - 1;
+    const bool kd = mode < NDP_MODE_LS_NEAREST;
+    // children are ordered by which half the query leans to; for cell modes lean on q + 0.5
+    const double lean = (mode == NDP_MODE_KD_NEAREST || mode == NDP_MODE_LS_NEAREST) ? 0.0 : 0.5;
+
+    int bc[NDP_MAX_LEVELS][NDP_MAX_AXES];     // block coordinates along the current path
+    unsigned next[NDP_MAX_LEVELS];            // next child ordinal to try at each level
+
+    int best = -1;
+    double bestd = 0.0;
+    bool tie = false;
+
+    hit.hard = 1;
+    if (!P.any_set) { hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_EMPTY; return; }
+
+    int lev = top;
+    for (int a = 0; a < nb; a++) bc[top][a] = 0;
+    next[top] = 0;
+    if (top == 0) {          // single-vertex lattice cannot happen (every axis has >= 2 ticks), kept for safety
+        hit.vertex = 0; hit.dsel = 0.0; hit.status = NDP_SEARCH_OK; return;
+    }
+
+    for (;;) {
+        if (next[lev] == nchild) {
+            if (lev == top) break;
+            lev++;
+            continue;
+        }
+        const unsigned k = next[lev]++;
+        const int cl = lev - 1;               // child level
+        int cb[NDP_MAX_AXES];
+        int flat = 0;
+        bool inside = true;
+        double bound = 0.0;
+        for (int a = 0; a < nb; a++) {
+            const int mid = ((2 * bc[lev][a] + 1) << cl);          // first coordinate of the upper child
+            const unsigned nearbit = (Q.qc[a] + lean >= (double) mid) ? 1u : 0u;
+            const int b = 2 * bc[lev][a] + (int) (((k >> a) & 1u) ^ nearbit);
+            if (b >= P.dim[cl][a]) { inside = false; break; }
+            cb[a] = b;
+            flat += b * P.stride[cl][a];
+            int lo = b << cl;
+            int hi = ((b + 1) << cl) - 1;
+            if (hi > g.len[a] - 1) hi = g.len[a] - 1;
+            bound += ndp_axis_term(mode, Q.qc[a], lo, hi);
+        }
+        if (!inside) continue;
+        if (!ndp_bit(P.bits[cl], flat)) continue;
+        bound = ndp_add_assoc(g, mode, Q, bound);
+        if (best >= 0 && bound > bestd) continue;     // equal bounds are explored: ties matter
+        if (cl == 0) {
+            // a level-0 block is one vertex and its bound is the reference's distance expression
+            if (best < 0 || bound < bestd) { best = flat; bestd = bound; tie = false; }
+            else if (bound == bestd) {
+                if (!kd) { if (flat < best) best = flat; }               // _compare_indexed_dists, :101-112
+                else if (topo) { if (ndp_tree_beats(g, mode, *topo, Q, flat, best)) best = flat; }
+                else tie = true;
+            }
+            continue;
+        }
+        lev = cl;
+        for (int a = 0; a < nb; a++) bc[lev][a] = cb[a];
+        next[lev] = 0;
+    }
+    hit.vertex = best;
+    hit.dsel = bestd;
+    hit.status = tie ? NDP_SEARCH_TIE : NDP_SEARCH_OK;
+}
+
+// The full scan scores masked-out vertices 1e10 (:283-286), so beyond 1e5 cells
+// from every valid vertex the lowest masked-out id wins; an empty mask yields
+// vertex 0 (all scores equal, lowest id first).
+NDP_HD void ndp_scan_sentinel(const NdpPyramid &P, int mode, NdpHit &hit)
+{
+    if (mode < NDP_MODE_LS_NEAREST) return;
+    const double sentinel = 1e10;
+    if (hit.status == NDP_SEARCH_EMPTY) { hit.vertex = 0; hit.dsel = sentinel; hit.status = NDP_SEARCH_OK; return; }
+    if (P.first_clear >= 0 && (sentinel < hit.dsel || (sentinel == hit.dsel && P.first_clear < hit.vertex))) {
+        hit.vertex = P.first_clear; hit.dsel = sentinel;
+    }
+}
+
+// Decodes a basic vertex id into coords[0..nbasic) (:235-237) and appends the
+// associated ticks.
+NDP_HD void ndp_coords_of(const NdpGeom &g, const NdpQuery &Q, int vertex, int *coords)
+{
+    for (int a = 0; a < g.nbasic; a++) coords[a] = (vertex / g.bstride[a]) % g.len[a];
+    for (int a = g.nbasic; a < g.naxes; a++) coords[a] = Q.acoord[a];
+}
+
+// Builds the index-space query from the import products.
+NDP_HD void ndp_make_query(const NdpGeom &g, const int *idx, const double *nrm, NdpQuery &Q)
+{
+    for (int a = 0; a < g.naxes; a++) {
+        Q.qc[a] = (double) idx[a] + nrm[a] - 1.0;
+        Q.acoord[a] = (a >= g.nbasic) ? ndp_assoc_coord(Q.qc[a], g.len[a]) : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Per-query glue shared by the kernels (and by the test-only host build)
+// ---------------------------------------------------------------------------
+
+// N > 0: number of axes fixed at compile time; N == 0: read it from the geometry.
+template <int N>
+NDP_HD void ndp_import_query(const NdpGeom &g, const double *ticks, const double *qrow,
+                             int *idx, int *flg, double *nrm)
+{
+    const int n = N ? N : g.naxes;
+#pragma unroll
+    for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
+        if (a < n) ndp_import_axis(ticks + g.tickoff[a], g.len[a], qrow[a], idx[a], flg[a], nrm[a]);
+}
+
+// Reduced value of component k of the cell whose superior corner is sup[] (:472-498
+// gather + :78-99 reduction).  CM selects the cell-major copy of the grid
+// (2^n * vdim contiguous doubles per cell, `cells`), else the original strided
+// layout (`grid`).  V1 asserts vdim == 1 at compile time (128-bit pair loads).
+// pinmask/selbits use bit (n-1-a) for axis a.
+template <int N, bool CM, bool V1>
+NDP_HD double ndp_eval_cell(const NdpGeom &g, const double *__restrict__ grid, const double *__restrict__ cells,
+                            const int *sup, const double *x, unsigned pinmask, unsigned selbits, int k, bool &nan_used)
+{
+    const int V = V1 ? 1 : g.vdim;
+    if (N > 0) {
+        constexpr int NN = N ? N : 1;
+        if (CM) {
+            long long cell = 0;
+#pragma unroll
+            for (int a = 0; a < NN; a++) cell += (long long) (sup[a] - 1) * g.cstride[a];
+            const double *base = cells + (cell << NN) * V + k;
+            if (V1) {
+                const double2 *b2 = reinterpret_cast<const double2 *>(base);
+                return ndp_cell_reduce<NN>([&](double *fv) {
+#pragma unroll
+                    for (int j = 0; j < (1 << NN) / 2; j++) { double2 p = b2[j]; fv[2 * j] = p.x; fv[2 * j + 1] = p.y; }
+                }, x, pinmask, selbits, nan_used);
+            }
+            return ndp_cell_reduce<NN>([&](double *fv) {
+#pragma unroll
+                for (int j = 0; j < (1 << NN); j++) fv[j] = base[(long long) j * V];
+            }, x, pinmask, selbits, nan_used);
+        }
+        long long origin = 0;
+#pragma unroll
+        for (int a = 0; a < NN; a++) origin += (long long) (sup[a] - 1) * g.vstride[a];
+        const double *base = grid + origin * V + k;
+        return ndp_cell_reduce<NN>([&](double *fv) {
+#pragma unroll
+            for (int j = 0; j < (1 << NN); j++) {
+                long long off = 0;
+#pragma unroll
+                for (int a = 0; a < NN; a++) if ((j >> (NN - 1 - a)) & 1) off += g.vstride[a];
+                fv[j] = base[off * V];
+            }
+        }, x, pinmask, selbits, nan_used);
+    }
+    // runtime n: used corners only, carry-chain reduction, original layout
+    const int n = g.naxes;
+    long long fixed = 0;
+    long long fstride[NDP_MAX_AXES];
+    double xfree[NDP_MAX_AXES];
+    int d = 0;
+    for (int a = 0; a < n; a++) {
+        const bool pinned = (pinmask >> (n - 1 - a)) & 1u;
+        const bool upper = (selbits >> (n - 1 - a)) & 1u;
+        if (pinned) fixed += (long long) (upper ? sup[a] : sup[a] - 1) * g.vstride[a];
+        else { fixed += (long long) (sup[a] - 1) * g.vstride[a]; fstride[d] = g.vstride[a]; xfree[d] = x[a]; d++; }
+    }
+    const double *base = grid + fixed * V + k;
+    return ndp_cell_reduce_rt(d, [&](unsigned c) {
+        long long off = 0;
+        for (int i = 0; i < d; i++) if ((c >> i) & 1u) off += fstride[i];
+        return base[off * V];
+    }, xfree, nan_used);
+}
+
+// Classification of an imported query (:438-460): out-of-bounds, pinned axes and
+// which side each pinned axis selects (:476).
+template <int N>
+NDP_HD bool ndp_classify(const NdpGeom &g, const int *flg, const double *nrm, unsigned &pinmask, unsigned &selbits)
+{
+    const int n = N ? N : g.naxes;
+    bool oob = false;
+    pinmask = 0; selbits = 0;
+#pragma unroll
+    for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
+        if (a < n) {
+            oob |= (flg[a] & NDP_F_OOB) != 0;
+            if (flg[a] & NDP_F_ON_VERTEX) {
+                pinmask |= 1u << (n - 1 - a);
+                if (nrm[a] > 0.5) selbits |= 1u << (n - 1 - a);
+            }
+        }
+    return oob;
+}
+
+// Off-grid finish for component k once the winner `coords` is known.
+//   NEAREST (:556-567): the vertex' own value.
+//   LINEAR  (:569-635): full-dimensional cell below coords (clamped at 0, :601),
+//                       query shifted into that cell's unit coordinates (:621-622).
+template <int N, bool CM, bool V1>
+NDP_HD double ndp_finish_component(const NdpGeom &g, const double *__restrict__ grid, const double *__restrict__ cells,
+                                   int method, const int *idx, const double *nrm, const int *coords, int k)
+{
+    const int n = N ? N : g.naxes;
+    if (method == NDP_M_NEAREST) {
+        long long v = 0;
+        for (int a = 0; a < n; a++) v += (long long) coords[a] * g.vstride[a];
+        return grid[v * (V1 ? 1 : g.vdim) + k];
+    }
+    int sup[NDP_MAX_AXES];
+    double x[NDP_MAX_AXES];
+#pragma unroll
+    for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
+        if (a < n) {
+            sup[a] = coords[a] > 1 ? coords[a] : 1;
+            x[a] = nrm[a] + (double) (idx[a] - coords[a]);
+        }
+    bool unused;
+    return ndp_eval_cell<N, CM, V1>(g, grid, cells, sup, x, 0u, 0u, k, unused);
+}

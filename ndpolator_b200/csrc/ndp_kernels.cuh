@@ -1,0 +1,352 @@
+// ndp_kernels.cuh -- sm_100a kernels of the ndpolate hot path.
+//
+//   k_import        per-axis index search tap            (ndp_query_pts_import, src/ndpolator.c:354-414)
+//   k_hypercubes    hypercube assembly tap               (ndp_find_hypercubes, :416-508)
+//   k_main          import + gather + reduce, fused      (:354-414 + :416-508 + :78-99 + :547-554, :648-667)
+//                   -> interps/dists for points in a fully defined hypercube,
+//                      compacted list of the rest
+//   k_search        exact nearest on the lattice         (ndp_find_nearest, :188-352; kdtree.c:345-457)
+//   k_search_brute  warp-cooperative full scan           (:279-329)
+//   k_finish        nearest copy / linear extrapolation  (:556-635)
+//
+// All kernels are grid-stride over their work list and read list lengths from
+// device counters, so the host never synchronises between them.
+#pragma once
+
+#include <cuda_runtime.h>
+#include "ndp_core.cuh"
+
+#define NDP_BLOCK 256
+
+struct NdpCounters {      // one per in-flight batch, zeroed before k_main
+    int n_off;            // queries not in a fully defined hypercube (search needed)
+    int n_tie;            // kd-mode ties met without topology
+    int n_hard;           // queries that needed the pyramid descent
+    int n_tie_resolved;   // ties settled through the kd topology
+};
+
+// ---------------------------------------------------------------------------
+// axis staging: all ticks of all axes in shared memory when they fit
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ const double *ndp_stage_ticks(const double *ticks, int nticks, bool in_smem, double *smem)
+{
+    if (!in_smem) return ticks;
+    for (int i = threadIdx.x; i < nticks; i += blockDim.x) smem[i] = ticks[i];
+    __syncthreads();
+    return smem;
+}
+
+// ---------------------------------------------------------------------------
+// k_import: indices / flags / normed for every (query, axis)
+// ---------------------------------------------------------------------------
+struct ImportArgs {
+    NdpGeom g;
+    const double *ticks; int nticks; int ticks_in_smem;
+    const double *q; long long n;
+    int *indices; int *flags; double *normed;
+};
+
+__global__ void __launch_bounds__(NDP_BLOCK) k_import(const __grid_constant__ ImportArgs A)
+{
+    extern __shared__ double s_ticks[];
+    const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
+    const int n = A.g.naxes;
+    const long long total = A.n * n;
+    // one thread per (query, axis) element: fully coalesced loads and stores
+    for (long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long) gridDim.x * blockDim.x) {
+        const int a = (int) (e % n);
+        int idx, flg; double nrm;
+        ndp_import_axis(tk + A.g.tickoff[a], A.g.len[a], A.q[e], idx, flg, nrm);
+        A.indices[e] = idx; A.flags[e] = flg; A.normed[e] = nrm;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_hypercubes: the tap behind cndpolator.hypercubes
+// ---------------------------------------------------------------------------
+struct HypercubeArgs {
+    NdpGeom g;
+    const double *grid;
+    const double *normed; const int *indices; const int *flags; long long n;
+    int *dim; int *fdhc; double *v;
+};
+
+__global__ void __launch_bounds__(NDP_BLOCK) k_hypercubes(const __grid_constant__ HypercubeArgs A)
+{
+    const NdpGeom &g = A.g;
+    const int n = g.naxes, V = g.vdim;
+    const long long slot = ((long long) 1 << n) * V;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (long long) gridDim.x * blockDim.x) {
+        const int *idx = A.indices + i * n;
+        const int *flg = A.flags + i * n;
+        const double *nrm = A.normed + i * n;
+        int full = 1, d = n;
+        for (int a = 0; a < n; a++) {
+            if (flg[a] & NDP_F_OOB) full = 0;
+            if (flg[a] & NDP_F_ON_VERTEX) d--;
+        }
+        double *out = A.v + i * slot;
+        for (int j = 0; j < (1 << d); j++) {
+            long long vert = 0;
+            int l = 0;
+            for (int a = 0; a < n; a++) {
+                int c;
+                if (flg[a] & NDP_F_ON_VERTEX) c = nrm[a] > 0.5 ? idx[a] : idx[a] - 1;
+                else {
+                    int bit = (j >> (d - l - 1)) & 1;
+                    c = idx[a] - 1 + bit;
+                    if (c < bit) c = bit;
+                    l++;
+                }
+                vert += g.vstride[a] * c;
+            }
+            const double *src = A.grid + vert * V;
+            if (src[0] != src[0]) full = 0;
+            for (int k = 0; k < V; k++) out[(long long) j * V + k] = src[k];
+        }
+        A.dim[i] = d;
+        A.fdhc[i] = full;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_main
+// ---------------------------------------------------------------------------
+struct MainArgs {
+    NdpGeom g;
+    const double *ticks; int nticks; int ticks_in_smem;
+    const double *grid;       // original layout
+    const double *cells;      // cell-major copy or nullptr
+    const double *q; long long n;
+    double *interps; double *dists;
+    int method;
+    int *offlist;             // ids of queries that need the search (method != NONE)
+    NdpCounters *ctr;
+};
+
+// N: compile-time axis count (0 = runtime).  G: lanes cooperating on one query,
+// each owning components k = lane, lane+G, ... (G = 1 for scalar tables).
+template <int N, int G, bool CM>
+__global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_main(const __grid_constant__ MainArgs A)
+{
+    extern __shared__ double s_ticks[];
+    const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
+    const NdpGeom &g = A.g;
+    const int n = N ? N : g.naxes;
+    const int V = (G == 1) ? 1 : g.vdim;              // G == 1 is only launched for scalar tables
+    const int lig = threadIdx.x % G;                  // lane in group
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(unsigned) (G - 1)));
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    const long long per_pass = (long long) gridDim.x * (NDP_BLOCK / G);
+    const long long rounds = (A.n + per_pass - 1) / per_pass;
+    for (long long r = 0; r < rounds; r++) {
+        const long long i = r * per_pass + (long long) blockIdx.x * (NDP_BLOCK / G) + threadIdx.x / G;
+        const bool live = i < A.n;
+        bool need_search = false;
+
+        if (live) {
+            int idx[N ? N : NDP_MAX_AXES], flg[N ? N : NDP_MAX_AXES];
+            double nrm[N ? N : NDP_MAX_AXES];
+            ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
+            unsigned pinmask, selbits;
+            const bool oob = ndp_classify<N>(g, flg, nrm, pinmask, selbits);
+
+            bool fdhc = !oob;
+            if (!oob) {
+                // component 0 decides whether the hypercube is fully defined (:491)
+                for (int k0 = 0; k0 < V && fdhc; k0 += G) {
+                    const int k = k0 + lig;
+                    bool bad = false;
+                    double val = 0.0;
+                    if (k < V) val = ndp_eval_cell<N, CM, G == 1>(g, A.grid, A.cells, idx, nrm, pinmask, selbits, k, bad);
+                    if (k0 == 0) {
+                        if (G > 1) bad = __shfl_sync(gmask, (int) bad, lane & ~(unsigned) (G - 1)) != 0;
+                        if (bad) { fdhc = false; break; }
+                    }
+                    if (k < V) A.interps[i * V + k] = val;
+                }
+            }
+            if (fdhc) {
+                if (lig == 0) A.dists[i] = 0.0;
+            } else if (A.method == NDP_M_NONE) {
+                for (int k = lig; k < V; k += G) A.interps[i * V + k] = qnan;     // :551-554
+                if (lig == 0) A.dists[i] = 0.0;
+            } else {
+                need_search = (lig == 0);
+            }
+        }
+
+        // warp-aggregated append to the off-grid list
+        const unsigned votes = __ballot_sync(0xffffffffu, need_search);
+        if (votes) {
+            int base = 0;
+            const int leader = __ffs(votes) - 1;
+            if ((int) lane == leader) base = atomicAdd(&A.ctr->n_off, __popc(votes));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need_search) A.offlist[base + __popc(votes & ((1u << lane) - 1u))] = (int) i;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_search / k_search_brute
+// ---------------------------------------------------------------------------
+struct SearchArgs {
+    NdpGeom g;
+    NdpPyramid P;
+    NdpTopo topo; int have_topo;
+    const double *ticks; int nticks; int ticks_in_smem;
+    const double *q;
+    int method, search;
+    const int *list;        // query id per work item, or nullptr (work item t = query t)
+    const int *sublist;     // positions into list to (re)do, or nullptr
+    const int *count;       // device count of work items (of sublist when given), or nullptr
+    long long count_host;   // used when count == nullptr
+    int *chosen;            // winning basic vertex per work item
+    double *dists;          // per query id
+    int *coords;            // optional (n x naxes) tap, per query id
+    int *tielist;           // positions whose kd tie could not be settled yet
+    NdpCounters *ctr;
+};
+
+__device__ __forceinline__ void ndp_publish(const SearchArgs &A, const NdpQuery &Q, long long t, long long i, NdpHit hit)
+{
+    const NdpGeom &g = A.g;
+    const int mode = ndp_mode_of(A.method, A.search);
+    int coords[NDP_MAX_AXES];
+    double dist;
+    if (hit.status == NDP_SEARCH_EMPTY) {
+        // empty kd-tree: the reference falls through to the scan (:273-275), which scores every vertex 1e10
+        hit.vertex = 0; hit.dsel = 1e10; hit.status = NDP_SEARCH_OK;
+        ndp_coords_of(g, Q, 0, coords);
+        dist = 1e10;
+    } else {
+        ndp_coords_of(g, Q, hit.vertex, coords);
+        dist = (mode >= NDP_MODE_LS_NEAREST) ? hit.dsel : ndp_reported_dist(g, A.method, Q, coords);
+    }
+    A.chosen[t] = hit.vertex;
+    A.dists[i] = dist;
+    if (A.coords) for (int a = 0; a < g.naxes; a++) A.coords[i * g.naxes + a] = coords[a];
+}
+
+__global__ void __launch_bounds__(NDP_BLOCK) k_search(const __grid_constant__ SearchArgs A)
+{
+    extern __shared__ double s_ticks[];
+    const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
+    const NdpGeom &g = A.g;
+    const int n = g.naxes;
+    const int mode = ndp_mode_of(A.method, A.search);
+    const long long total = A.count ? (long long) *A.count : A.count_host;
+    for (long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long) gridDim.x * blockDim.x) {
+        const long long t = A.sublist ? A.sublist[s] : s;
+        const long long i = A.list ? A.list[t] : t;
+        int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES];
+        double nrm[NDP_MAX_AXES];
+        ndp_import_query<0>(g, tk, A.q + i * n, idx, flg, nrm);
+        NdpQuery Q;
+        ndp_make_query(g, idx, nrm, Q);
+
+        NdpHit hit;
+        if (!ndp_search_fast(g, A.P, mode, Q, hit)) {
+            ndp_search_hard(g, A.P, mode, Q, A.have_topo ? &A.topo : nullptr, hit);
+            atomicAdd(&A.ctr->n_hard, 1);
+            if (hit.status == NDP_SEARCH_TIE) {
+                // provisional (valid) vertex so that k_finish stays in bounds; redone once the topology exists
+                A.chosen[t] = hit.vertex;
+                A.tielist[atomicAdd(&A.ctr->n_tie, 1)] = (int) t;
+                continue;
+            }
+            if (A.sublist) atomicAdd(&A.ctr->n_tie_resolved, 1);
+        }
+        ndp_scan_sentinel(A.P, mode, hit);
+        ndp_publish(A, Q, t, i, hit);
+    }
+}
+
+// One warp per query: lanes stride over every basic vertex exactly as the
+// reference's scan does (:279-324), each keeping its (distance, id) minimum, then
+// a shuffle arg-min with the reference's tie rule (:101-112).  For small lattices.
+__global__ void __launch_bounds__(NDP_BLOCK) k_search_brute(const __grid_constant__ SearchArgs A)
+{
+    extern __shared__ double s_ticks[];
+    const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
+    const NdpGeom &g = A.g;
+    const int n = g.naxes;
+    const int mode = ndp_mode_of(A.method, A.search);
+    const unsigned lane = threadIdx.x & 31;
+    const long long total = A.count ? (long long) *A.count : A.count_host;
+    const long long warps = ((long long) gridDim.x * blockDim.x) >> 5;
+    for (long long t = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < total; t += warps) {
+        const long long i = A.list ? A.list[t] : t;
+        int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES];
+        double nrm[NDP_MAX_AXES];
+        ndp_import_query<0>(g, tk, A.q + i * n, idx, flg, nrm);
+        NdpQuery Q;
+        ndp_make_query(g, idx, nrm, Q);
+
+        int best = -1;
+        double bestd = 0.0;
+        for (int v = (int) lane; v < g.nverts; v += 32) {
+            double d;
+            if (!ndp_bit(A.P.bits[0], v)) d = 1e10;                     // :283-286
+            else {
+                int c[NDP_MAX_AXES];
+                for (int a = 0; a < g.nbasic; a++) c[a] = (v / g.bstride[a]) % g.len[a];
+                d = ndp_metric_vertex(g, mode, Q, c);
+            }
+            if (best < 0 || d < bestd) { best = v; bestd = d; }         // ascending v per lane: first wins ties
+        }
+        for (int off = 16; off; off >>= 1) {
+            const int ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const double od = __shfl_xor_sync(0xffffffffu, bestd, off);
+            if (ob >= 0 && (best < 0 || od < bestd || (od == bestd && ob < best))) { best = ob; bestd = od; }
+        }
+        if (lane == 0) {
+            NdpHit hit; hit.vertex = best; hit.dsel = bestd; hit.status = NDP_SEARCH_OK; hit.hard = 0;
+            ndp_publish(A, Q, t, i, hit);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_finish
+// ---------------------------------------------------------------------------
+struct FinishArgs {
+    NdpGeom g;
+    const double *ticks; int nticks; int ticks_in_smem;
+    const double *grid; const double *cells;
+    const double *q;
+    int method;
+    const int *list;        // query id per work item
+    const int *sublist;     // positions into list to redo (after tie resolution), or nullptr
+    const int *count;       // device count of work items (of sublist when given)
+    const int *chosen;
+    double *interps;
+};
+
+template <int N, bool CM>
+__global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __grid_constant__ FinishArgs A)
+{
+    extern __shared__ double s_ticks[];
+    const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
+    const NdpGeom &g = A.g;
+    const int n = N ? N : g.naxes;
+    const int V = g.vdim;
+    const long long total = *A.count;
+    for (long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long) gridDim.x * blockDim.x) {
+        const long long t = A.sublist ? A.sublist[s] : s;
+        const long long i = A.list[t];
+        int idx[N ? N : NDP_MAX_AXES], flg[N ? N : NDP_MAX_AXES];
+        double nrm[N ? N : NDP_MAX_AXES];
+        ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
+        int coords[NDP_MAX_AXES];
+        const int vertex = A.chosen[t];
+        for (int a = 0; a < g.nbasic; a++) coords[a] = (vertex / g.bstride[a]) % g.len[a];
+        for (int a = g.nbasic; a < n; a++)
+            coords[a] = ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
+        for (int k = 0; k < V; k++)
+            A.interps[i * V + k] = ndp_finish_component<N, CM, false>(g, A.grid, A.cells, A.method, idx, nrm, coords, k);
+    }
+}

@@ -1,0 +1,184 @@
+// ndp_table.cuh -- register-time kernels: vertex / hypercube masks
+// (reference src/ndp_types.c:174-258), the occupancy pyramid the nearest search
+// descends, the cell-major copy of the grid, and the level-synchronous rebuild of
+// the reference's insertion-ordered kd-tree shape (src/ndpolator.c:114-136,
+// external/kdtree/kdtree.c:167-209) used to settle exact distance ties.
+#pragma once
+
+#include <cuda_runtime.h>
+#include "ndp_core.cuh"
+
+// vmask[v] = component 0 of the basic vertex (associated indices 0) is not NaN
+// (ndp_types.c:179-184).  One warp packs 32 vertices into one word.
+__global__ void k_vmask_bits(const double *__restrict__ grid, int nverts, long long doubles_per_vertex, uint32_t *bits)
+{
+    const long long v = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (v < nverts) { double x = grid[v * doubles_per_vertex]; ok = (x == x); }
+    const unsigned word = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && v < nverts) bits[v >> 5] = word;
+}
+
+// hcmask[v] = v is the superior corner of a cell whose 2^nbasic corners are all
+// defined (ndp_types.c:201-258).
+__global__ void k_hcmask_bits(const __grid_constant__ NdpGeom g, const uint32_t *__restrict__ vbits, uint32_t *bits)
+{
+    const long long v = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (v < g.nverts && ndp_bit(vbits, (int) v)) {
+        ok = true;
+        for (int a = 0; a < g.nbasic && ok; a++)
+            if (((int) v / g.bstride[a]) % g.len[a] == 0) ok = false;
+        for (int corner = 0; corner < (1 << g.nbasic) && ok; corner++) {
+            int w = (int) v;
+            for (int a = 0; a < g.nbasic; a++)
+                if (!((corner >> a) & 1)) w -= g.bstride[a];
+            if (!ndp_bit(vbits, w)) ok = false;
+        }
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && v < g.nverts) bits[v >> 5] = word;
+}
+
+struct PyrLevelArgs {
+    int nb;
+    int cdim[NDP_MAX_AXES], cstride[NDP_MAX_AXES];   // child level
+    int pdim[NDP_MAX_AXES];                           // parent level
+    int nparent;
+    const uint32_t *cbits;
+    uint32_t *pbits;
+};
+
+__global__ void k_pyr_level(const __grid_constant__ PyrLevelArgs A)
+{
+    const long long p = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    bool any = false;
+    if (p < A.nparent) {
+        int pc[NDP_MAX_AXES];
+        int rem = (int) p;
+        for (int a = A.nb - 1; a >= 0; a--) { pc[a] = rem % A.pdim[a]; rem /= A.pdim[a]; }
+        for (int k = 0; k < (1 << A.nb) && !any; k++) {
+            int flat = 0;
+            bool inside = true;
+            for (int a = 0; a < A.nb; a++) {
+                int c = 2 * pc[a] + ((k >> a) & 1);
+                if (c >= A.cdim[a]) { inside = false; break; }
+                flat += c * A.cstride[a];
+            }
+            if (inside && ndp_bit(A.cbits, flat)) any = true;
+        }
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31) == 0 && p < A.nparent) A.pbits[p >> 5] = word;
+}
+
+// lowest vertex id whose bit is clear (for the 1e10 sentinel of the full scan); *out preset to INT_MAX
+__global__ void k_first_clear(const uint32_t *__restrict__ bits, int nverts, int *out)
+{
+    const long long w = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const int nwords = (nverts + 31) >> 5;
+    if (w >= nwords) return;
+    uint32_t word = ~bits[w];
+    if (w == nwords - 1 && (nverts & 31)) word &= (1u << (nverts & 31)) - 1u;
+    if (word) atomicMin(out, (int) (w * 32 + (__ffs(word) - 1)));
+}
+
+__global__ void k_unpack_bits(const uint32_t *__restrict__ bits, int n, int32_t *out)
+{
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ndp_bit(bits, (int) i) ? 1 : 0;
+}
+
+// Cell-major copy: for every cell (superior corner c, all axes) the 2^n corner
+// vectors in the reference's corner order (axis 0 = most significant bit),
+// contiguous: cells[(cell * 2^n + j) * vdim + k].  One in-grid query then reads
+// one contiguous, aligned burst instead of 2^(n-1) scattered sectors.
+__global__ void k_build_cells(const __grid_constant__ NdpGeom g, const double *__restrict__ grid, double *__restrict__ cells)
+{
+    const int n = g.naxes, V = g.vdim;
+    const long long total = g.ncells << n;
+    for (long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long) gridDim.x * blockDim.x) {
+        const int j = (int) (e & ((1LL << n) - 1));
+        long long cell = e >> n;
+        long long vert = 0;
+        for (int a = n - 1; a >= 0; a--) {
+            const int cd = g.len[a] - 1;
+            const int c = (int) (cell % cd);          // inferior corner on axis a
+            cell /= cd;
+            vert += (long long) (c + ((j >> (n - 1 - a)) & 1)) * g.vstride[a];
+        }
+        for (int k = 0; k < V; k++) cells[e * V + k] = grid[vert * V + k];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kd-tree shape, level-synchronous.
+//
+// The reference inserts the masked vertices in ascending id (ndpolator.c:119-131)
+// with the split axis cycling by depth (kdtree.c:189-193).  Hence every subtree
+// holds a set of vertices whose smallest id is the subtree's root, and the rest
+// split by (coordinate < root coordinate) on axis depth % nbasic.  Keeping each
+// subtree as a contiguous, id-ascending segment, one round per tree level turns
+// every segment head into a node and stably partitions the remainder into the
+// two child segments; all segments of a level are processed at once.
+// ---------------------------------------------------------------------------
+struct TopoArgs {
+    NdpGeom g;
+    int N;               // vertices in the tree
+    int axis;            // split axis of this level = depth % nbasic
+    int depth;
+    const int *ids; const int *seg_start; const int *seg_end;
+    int *flag;           // N + 1 entries (last = 0)
+    const int *scan;     // exclusive scan of flag, N + 1 entries
+    int *ids2; int *seg_start2; int *seg_end2;
+    int *parent; int *depthv;
+    int *active;         // number of vertices still waiting to become a node
+};
+
+__global__ void k_topo_flags(const __grid_constant__ TopoArgs A)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > A.N) return;
+    int f = 0;
+    if (i < A.N) {
+        const int s = A.seg_start[i];
+        if (s >= 0 && i != s) {
+            const int st = A.g.bstride[A.axis], ln = A.g.len[A.axis];
+            f = ((A.ids[i] / st) % ln) < ((A.ids[s] / st) % ln);      // kdtree.c:190
+        }
+    }
+    A.flag[i] = f;
+}
+
+__global__ void k_topo_scatter(const __grid_constant__ TopoArgs A)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.N) return;
+    const int s = A.seg_start[i];
+    if (s < 0 || i == s) {             // already a node, or becomes one now
+        A.ids2[i] = A.ids[i]; A.seg_start2[i] = -1; A.seg_end2[i] = -1;
+        return;
+    }
+    const int e = A.seg_end[i];
+    const int nl = A.scan[e] - A.scan[s + 1];
+    const int lrank = A.scan[i] - A.scan[s + 1];
+    int np, ns, ne;
+    if (A.flag[i]) { ns = s + 1; ne = s + 1 + nl; np = ns + lrank; }
+    else { ns = s + 1 + nl; ne = e; np = ns + (i - (s + 1) - lrank); }
+    A.ids2[np] = A.ids[i]; A.seg_start2[np] = ns; A.seg_end2[np] = ne;
+    if (np == ns) { A.parent[A.ids[i]] = A.ids[s]; A.depthv[A.ids[i]] = A.depth + 1; }
+    else atomicAdd(A.active, 1);       // still inside a segment after this round
+}
+
+__global__ void k_fill_int(int *p, long long n, int value)
+{
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) p[i] = value;
+}
+
+__global__ void k_topo_init(int N, int *seg_start, int *seg_end, const int *ids, int *parent, int *depthv)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    seg_start[i] = 0; seg_end[i] = N;
+    if (i == 0) { parent[ids[0]] = -1; depthv[ids[0]] = 0; }
+}

@@ -1,0 +1,277 @@
+// hostsim.cpp -- TEST SCAFFOLDING, NOT A PRODUCT PATH.
+//
+// Compiles ndpolator_b200/csrc/ndp_core.cuh (the __host__ __device__ per-query
+// logic the CUDA kernels are thin wrappers around) for the host, and drives it
+// with plain loops that mirror the kernels' control flow (k_main -> k_search ->
+// tie pass -> k_finish, and the level-synchronous kd-topology rounds).  Its only
+// purpose is to let `pytest -m "not gpu"` diff the device logic against the
+// oracle in the GPU-less build container before GPU minutes are spent.
+// libndpb200.so does not contain, link or load this file, and the Python package
+// never imports it: with no GPU the product fails loudly instead.
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include <numeric>
+
+#include "../../ndpolator_b200/csrc/ndp_core.cuh"
+
+struct HsPyr { NdpPyramid dev; std::vector<std::vector<uint32_t>> levels; };
+
+struct HsTable {
+    NdpGeom g;
+    std::vector<double> ticks, grid, cells;
+    HsPyr pyr[2];
+    std::vector<int> parent[2], depth[2];
+    bool topo_built[2] = {false, false};
+    long long n_hard = 0, n_tie = 0, n_off = 0;
+};
+
+static void set_bit(std::vector<uint32_t> &b, long long i) { b[i >> 5] |= 1u << (i & 31); }
+
+static void build_pyr(HsTable *t, HsPyr &P, std::vector<uint32_t> level0)
+{
+    const NdpGeom &g = t->g;
+    NdpPyramid &D = P.dev;
+    int dim[NDP_MAX_AXES];
+    for (int a = 0; a < g.nbasic; a++) dim[a] = g.len[a];
+    P.levels.clear();
+    P.levels.push_back(std::move(level0));
+    for (int lev = 0; lev < NDP_MAX_LEVELS; lev++) {
+        long long nblocks = 1;
+        for (int a = g.nbasic - 1, s = 1; a >= 0; a--) { D.dim[lev][a] = dim[a]; D.stride[lev][a] = s; s *= dim[a]; nblocks *= dim[a]; }
+        if (lev > 0) {
+            std::vector<uint32_t> bits((nblocks + 31) / 32, 0u);
+            const std::vector<uint32_t> &child = P.levels[lev - 1];
+            for (long long p = 0; p < nblocks; p++) {
+                int pc[NDP_MAX_AXES]; long long rem = p;
+                for (int a = g.nbasic - 1; a >= 0; a--) { pc[a] = rem % dim[a]; rem /= dim[a]; }
+                bool any = false;
+                for (int k = 0; k < (1 << g.nbasic) && !any; k++) {
+                    int flat = 0; bool inside = true;
+                    for (int a = 0; a < g.nbasic; a++) {
+                        int c = 2 * pc[a] + ((k >> a) & 1);
+                        if (c >= D.dim[lev - 1][a]) { inside = false; break; }
+                        flat += c * D.stride[lev - 1][a];
+                    }
+                    if (inside && ndp_bit(child.data(), flat)) any = true;
+                }
+                if (any) set_bit(bits, p);
+            }
+            P.levels.push_back(std::move(bits));
+        }
+        D.nlev = lev + 1;
+        if (nblocks == 1) break;
+        for (int a = 0; a < g.nbasic; a++) dim[a] = (dim[a] + 1) / 2;
+    }
+    for (int l = 0; l < D.nlev; l++) D.bits[l] = P.levels[l].data();
+    D.first_clear = -1;
+    for (int v = 0; v < g.nverts; v++) if (!ndp_bit(D.bits[0], v)) { D.first_clear = v; break; }
+    D.any_set = ndp_bit(D.bits[D.nlev - 1], 0) ? 1 : 0;
+}
+
+extern "C" void *hs_create(int naxes, int nbasic, const int *axlen, const double *ticks, int vdim, const double *grid, int with_cells)
+{
+    HsTable *t = new HsTable();
+    NdpGeom &g = t->g;
+    std::memset(&g, 0, sizeof g);
+    g.naxes = naxes; g.nbasic = nbasic; g.vdim = vdim;
+    int nt = 0; long long nall = 1, ncells = 1, nverts = 1;
+    for (int a = 0; a < naxes; a++) { g.len[a] = axlen[a]; g.tickoff[a] = nt; nt += axlen[a]; nall *= axlen[a]; ncells *= axlen[a] - 1; if (a < nbasic) nverts *= axlen[a]; }
+    for (int a = naxes - 1; a >= 0; a--) {
+        g.vstride[a] = (a == naxes - 1) ? 1 : g.vstride[a + 1] * g.len[a + 1];
+        g.cstride[a] = (a == naxes - 1) ? 1 : g.cstride[a + 1] * (g.len[a + 1] - 1);
+    }
+    for (int a = nbasic - 1; a >= 0; a--) g.bstride[a] = (a == nbasic - 1) ? 1 : g.bstride[a + 1] * g.len[a + 1];
+    g.nverts = (int) nverts; g.ncells = ncells;
+    t->ticks.assign(ticks, ticks + nt);
+    if (!grid) return t;
+    t->grid.assign(grid, grid + nall * vdim);
+    // masks: mirrors k_vmask_bits / k_hcmask_bits
+    std::vector<uint32_t> vb((nverts + 31) / 32, 0u), hb((nverts + 31) / 32, 0u);
+    const long long dpv = g.vstride[nbasic - 1] * vdim;
+    for (long long v = 0; v < nverts; v++) { double x = grid[v * dpv]; if (x == x) set_bit(vb, v); }
+    for (long long v = 0; v < nverts; v++) {
+        if (!ndp_bit(vb.data(), (int) v)) continue;
+        bool ok = true;
+        for (int a = 0; a < nbasic && ok; a++) if (((int) v / g.bstride[a]) % g.len[a] == 0) ok = false;
+        for (int corner = 0; corner < (1 << nbasic) && ok; corner++) {
+            int w = (int) v;
+            for (int a = 0; a < nbasic; a++) if (!((corner >> a) & 1)) w -= g.bstride[a];
+            if (!ndp_bit(vb.data(), w)) ok = false;
+        }
+        if (ok) set_bit(hb, v);
+    }
+    build_pyr(t, t->pyr[0], vb);
+    build_pyr(t, t->pyr[1], hb);
+    if (with_cells && naxes <= 6) {          // mirrors k_build_cells
+        const int n = naxes, V = vdim;
+        t->cells.resize((size_t) (ncells << n) * V);
+        for (long long e = 0; e < (ncells << n); e++) {
+            const int j = (int) (e & ((1LL << n) - 1));
+            long long cell = e >> n, vert = 0;
+            for (int a = n - 1; a >= 0; a--) {
+                const int cd = g.len[a] - 1; const int c = (int) (cell % cd); cell /= cd;
+                vert += (long long) (c + ((j >> (n - 1 - a)) & 1)) * g.vstride[a];
+            }
+            for (int k = 0; k < V; k++) t->cells[e * V + k] = grid[vert * V + k];
+        }
+    }
+    return t;
+}
+
+extern "C" void hs_free(void *h) { delete (HsTable *) h; }
+
+extern "C" void hs_masks(void *h, int32_t *vmask, int32_t *hcmask)
+{
+    HsTable *t = (HsTable *) h;
+    for (int v = 0; v < t->g.nverts; v++) { vmask[v] = ndp_bit(t->pyr[0].dev.bits[0], v); hcmask[v] = ndp_bit(t->pyr[1].dev.bits[0], v); }
+}
+
+// mirrors ensure_topology(): k_topo_flags -> exclusive scan -> k_topo_scatter per level
+static void build_topo(HsTable *t, int m)
+{
+    if (t->topo_built[m]) return;
+    const NdpGeom &g = t->g;
+    std::vector<int> &parent = t->parent[m], &depthv = t->depth[m];
+    parent.assign(g.nverts, -2); depthv.assign(g.nverts, -1);
+    std::vector<int> ids;
+    for (int v = 0; v < g.nverts; v++) if (ndp_bit(t->pyr[m].dev.bits[0], v)) ids.push_back(v);
+    const int N = (int) ids.size();
+    t->topo_built[m] = true;
+    if (!N) return;
+    std::vector<int> ss(N, 0), se(N, N), ids2(N), ss2(N), se2(N), flag(N + 1), scan(N + 1);
+    parent[ids[0]] = -1; depthv[ids[0]] = 0;
+    for (int depth = 0;; depth++) {
+        const int axis = depth % g.nbasic;
+        for (int i = 0; i <= N; i++) {
+            int f = 0;
+            if (i < N) { int s = ss[i]; if (s >= 0 && i != s) { int st = g.bstride[axis], ln = g.len[axis]; f = ((ids[i] / st) % ln) < ((ids[s] / st) % ln); } }
+            flag[i] = f;
+        }
+        std::exclusive_scan(flag.begin(), flag.end(), scan.begin(), 0);
+        int active = 0;
+        for (int i = 0; i < N; i++) {
+            int s = ss[i];
+            if (s < 0 || i == s) { ids2[i] = ids[i]; ss2[i] = -1; se2[i] = -1; continue; }
+            int e = se[i], nl = scan[e] - scan[s + 1], lrank = scan[i] - scan[s + 1], np, ns, ne;
+            if (flag[i]) { ns = s + 1; ne = s + 1 + nl; np = ns + lrank; }
+            else { ns = s + 1 + nl; ne = e; np = ns + (i - (s + 1) - lrank); }
+            ids2[np] = ids[i]; ss2[np] = ns; se2[np] = ne;
+            if (np == ns) { parent[ids[i]] = ids[s]; depthv[ids[i]] = depth + 1; } else active++;
+        }
+        ids.swap(ids2); ss.swap(ss2); se.swap(se2);
+        if (!active) break;
+    }
+}
+
+extern "C" void hs_topology(void *h, int method, int32_t *parent, int32_t *depth)
+{
+    HsTable *t = (HsTable *) h;
+    const int m = method == NDP_M_LINEAR ? 1 : 0;
+    build_topo(t, m);
+    std::copy(t->parent[m].begin(), t->parent[m].end(), parent);
+    std::copy(t->depth[m].begin(), t->depth[m].end(), depth);
+}
+
+extern "C" void hs_find(void *h, long long n, const double *q, int32_t *indices, int32_t *flags, double *normed)
+{
+    HsTable *t = (HsTable *) h;
+    const NdpGeom &g = t->g;
+    for (long long e = 0; e < n * g.naxes; e++) {
+        int a = (int) (e % g.naxes), idx, flg; double nrm;
+        ndp_import_axis(t->ticks.data() + g.tickoff[a], g.len[a], q[e], idx, flg, nrm);
+        indices[e] = idx; flags[e] = flg; normed[e] = nrm;
+    }
+}
+
+// mirrors k_search + ndp_publish, with the deferred tie pass folded in
+static void search_one(HsTable *t, const double *qrow, int method, int search, int *vertex, double *dist, int *coords)
+{
+    const NdpGeom &g = t->g;
+    const int mode = ndp_mode_of(method, search), m = method == NDP_M_LINEAR ? 1 : 0;
+    int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES]; double nrm[NDP_MAX_AXES];
+    ndp_import_query<0>(g, t->ticks.data(), qrow, idx, flg, nrm);
+    NdpQuery Q; ndp_make_query(g, idx, nrm, Q);
+    NdpHit hit;
+    if (!ndp_search_fast(g, t->pyr[m].dev, mode, Q, hit)) {
+        t->n_hard++;
+        ndp_search_hard(g, t->pyr[m].dev, mode, Q, nullptr, hit);
+        if (hit.status == NDP_SEARCH_TIE) {
+            t->n_tie++;
+            build_topo(t, m);
+            NdpTopo T{t->parent[m].data(), t->depth[m].data()};
+            ndp_search_hard(g, t->pyr[m].dev, mode, Q, &T, hit);
+        }
+    }
+    ndp_scan_sentinel(t->pyr[m].dev, mode, hit);
+    if (hit.status == NDP_SEARCH_EMPTY) { hit.vertex = 0; hit.dsel = 1e10; ndp_coords_of(g, Q, 0, coords); *dist = 1e10; }
+    else { ndp_coords_of(g, Q, hit.vertex, coords); *dist = (mode >= NDP_MODE_LS_NEAREST) ? hit.dsel : ndp_reported_dist(g, method, Q, coords); }
+    *vertex = hit.vertex;
+}
+
+extern "C" void hs_find_nearest(void *h, long long n, const double *q, int method, int search, int32_t *coords, double *dist)
+{
+    HsTable *t = (HsTable *) h;
+    const int na = t->g.naxes;
+    for (long long i = 0; i < n; i++) { int v, c[NDP_MAX_AXES]; search_one(t, q + i * na, method, search, &v, &dist[i], c); for (int a = 0; a < na; a++) coords[i * na + a] = c[a]; }
+}
+
+template <int N, bool CM, bool V1>
+static void ndpolate_n(HsTable *t, long long nq, const double *q, int method, int search, double *interps, double *dists)
+{
+    const NdpGeom &g = t->g;
+    const int n = N ? N : g.naxes, V = g.vdim;
+    const double *cells = t->cells.empty() ? nullptr : t->cells.data();
+    for (long long i = 0; i < nq; i++) {
+        int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES]; double nrm[NDP_MAX_AXES];
+        ndp_import_query<N>(g, t->ticks.data(), q + i * n, idx, flg, nrm);
+        unsigned pin, sel;
+        const bool oob = ndp_classify<N>(g, flg, nrm, pin, sel);
+        bool fdhc = !oob;
+        if (!oob) {
+            for (int k = 0; k < V; k++) {
+                bool bad = false;
+                double val = ndp_eval_cell<N, CM, V1>(g, t->grid.data(), cells, idx, nrm, pin, sel, k, bad);
+                if (k == 0 && bad) { fdhc = false; break; }
+                interps[i * V + k] = val;
+            }
+        }
+        if (fdhc) { dists[i] = 0.0; continue; }
+        if (method == NDP_M_NONE) { for (int k = 0; k < V; k++) interps[i * V + k] = NAN; dists[i] = 0.0; continue; }
+        t->n_off++;
+        int vertex, coords[NDP_MAX_AXES];
+        search_one(t, q + i * n, method, search, &vertex, &dists[i], coords);
+        // mirrors k_finish: coords are re-derived from the chosen vertex
+        int c2[NDP_MAX_AXES];
+        for (int a = 0; a < g.nbasic; a++) c2[a] = (vertex / g.bstride[a]) % g.len[a];
+        for (int a = g.nbasic; a < n; a++) c2[a] = ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
+        for (int k = 0; k < V; k++)
+            interps[i * V + k] = ndp_finish_component<N, CM, false>(g, t->grid.data(), cells, method, idx, nrm, c2, k);
+    }
+}
+
+template <bool CM>
+static void ndpolate_cm(HsTable *t, long long nq, const double *q, int method, int search, double *interps, double *dists, int generic)
+{
+    const bool v1 = t->g.vdim == 1;
+#define GO(N) do { if (v1) ndpolate_n<N, CM, true>(t, nq, q, method, search, interps, dists); else ndpolate_n<N, CM, false>(t, nq, q, method, search, interps, dists); } while (0)
+    if (generic) { ndpolate_n<0, false, false>(t, nq, q, method, search, interps, dists); return; }
+    switch (t->g.naxes) {
+    case 1: GO(1); break; case 2: GO(2); break; case 3: GO(3); break;
+    case 4: GO(4); break; case 5: GO(5); break; case 6: GO(6); break;
+    default: ndpolate_n<0, false, false>(t, nq, q, method, search, interps, dists);
+    }
+#undef GO
+}
+
+// variant: 0 = strided layout, 1 = cell-major, 2 = runtime-n generic path
+extern "C" void hs_ndpolate(void *h, long long n, const double *q, int method, int search, int variant, double *interps, double *dists)
+{
+    HsTable *t = (HsTable *) h;
+    if (variant == 1 && !t->cells.empty()) ndpolate_cm<true>(t, n, q, method, search, interps, dists, 0);
+    else ndpolate_cm<false>(t, n, q, method, search, interps, dists, variant == 2);
+}
+
+extern "C" void hs_stats(void *h, long long *out) { HsTable *t = (HsTable *) h; out[0] = t->n_off; out[1] = t->n_hard; out[2] = t->n_tie; }

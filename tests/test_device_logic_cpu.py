@@ -1,0 +1,46 @@
+"""CPU: the per-query device logic (ndpolator_b200/csrc/ndp_core.cuh, the code the
+CUDA kernels wrap) compiled for the host by tests/hostsim and diffed bit for bit
+against the oracle: masks, import, the rebuilt kd topology, nearest search in all
+four modes (fast path, pyramid descent, tie resolution), and ndpolate through the
+strided, cell-major and runtime-n gather variants.  This is a development check of
+the kernel logic in the GPU-less container; the GPU parity suite is test_gpu_parity.py."""
+import shutil
+
+import numpy as np
+import pytest
+
+from cases import adversarial_queries, assert_same_bits, build_cases
+from oracle.oracle import Oracle
+
+pytestmark = pytest.mark.skipif(shutil.which('g++') is None, reason='g++ not available')
+
+
+@pytest.mark.parametrize('case', build_cases(seed=3), ids=lambda c: c[0])
+def test_device_logic_matches_oracle(case):
+    from hostsim.driver import HostSim
+    name, axes, nbasic, grid = case
+    q = adversarial_queries(axes, 700, np.random.default_rng(9))
+    O, H = Oracle('port', axes, grid, nbasic), HostSim(axes, grid, nbasic)
+    for a, b, what in zip(O.masks(), H.masks(), ('vmask', 'hcmask')):
+        assert_same_bits(a, b, what)
+    fo = O.find(q)
+    for a, b, what in zip(fo, H.find(q), ('indices', 'flags', 'normed')):
+        assert_same_bits(a, b, what)
+    for m in (1, 2):
+        po, do = O.tree_topology(m)
+        ph, dh = H.topology(m)
+        assert np.array_equal(po, ph.astype(np.int64)), f'kd parent, method {m}'
+        assert np.array_equal(do, dh), f'kd depth, method {m}'
+        for s in (0, 1):
+            a, b = O.find_nearest(*fo, m, s), H.find_nearest(q, m, s)
+            assert_same_bits(a[0], b[0], f'coords {m}/{s}')
+            assert_same_bits(a[1], b[1], f'ndist {m}/{s}')
+    for m in (0, 1, 2):
+        for s in (0, 1):
+            a = O.ndpolate(q, m, s)
+            for variant in (0, 1, 2):
+                b = H.ndpolate(q, m, s, variant)
+                assert_same_bits(a[0], b[0], f'interps {m}/{s} variant {variant}')
+                assert_same_bits(a[1], b[1], f'dists {m}/{s} variant {variant}')
+    st = H.stats()
+    assert st['hard'] > 0 and st['ties'] > 0      # the adversarial set must reach the slow paths

@@ -1,0 +1,206 @@
+"""GPU: parity of the CUDA path, called through the C ABI (ndpolator_b200.cndpolator.Table
+-> libndpb200.so), against (a) golden vectors produced by the reference itself and
+(b) the CPU oracle on fresh seeded inputs.  Bar (BASELINE.json north_star): indices,
+flags, hypercube corner ids / fdhc / dim, nearest coords (ties included) and NaN
+placement bit-exact; interps, dists, normed within 1e-13 relative -- the tests demand
+bit-exactness for those too (compiled with -fmad=false), which implies the 1e-13 bar."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import adversarial_queries, assert_same_bits, build_cases
+from oracle.oracle import Oracle
+from test_oracle_cpu import GOLDEN, check_engine_against_golden, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _table(axes, grid, nbasic, **opts):
+    from ndpolator_b200.cndpolator import Table
+    t = Table(axes, grid, nbasic)
+    for k, v in opts.items():
+        t.set_option(k, v)
+    return t
+
+
+def test_extension_is_loaded_and_gpu_present():
+    import torch
+    assert torch.cuda.is_available()
+    from ndpolator_b200 import _lib
+    assert b'sm_100a' in _lib.lib().ndpb_version()
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[4:-4] for p in GOLDEN])
+@pytest.mark.parametrize('gather', [1, 2], ids=['strided', 'cellmajor'])
+def test_cuda_matches_reference_golden(path, gather):
+    z, axes, nbasic = load_golden(path)
+    T = _table(axes, z['grid'], nbasic, gather=gather)
+    check_engine_against_golden(
+        z, T.find, lambda idx, flg, nrm: T.hypercubes_raw(nrm, idx, flg), T.ndpolate,
+        lambda q, idx, flg, nrm, m, s: T.find_nearest(q, m, s), T.distance, T.masks)
+    if gather == 2 and len(axes) <= 6 and z['grid'].shape[-1] * 8 < 128:
+        assert T.stat('cellmajor') == 1
+    T.close()
+
+
+@pytest.mark.parametrize('case', build_cases(seed=21), ids=lambda c: c[0])
+def test_cuda_matches_oracle_fresh_inputs(case):
+    name, axes, nbasic, grid = case
+    q = adversarial_queries(axes, 20000, np.random.default_rng(123))
+    O = Oracle('port', axes, grid, nbasic)
+    T = _table(axes, grid, nbasic)
+    for a, b, what in zip(O.masks(), T.masks(), ('vmask', 'hcmask')):
+        assert_same_bits(a, b, what)
+    fo = O.find(q)
+    for a, b, what in zip(fo, T.find(q), ('indices', 'flags', 'normed')):
+        assert_same_bits(a, b, what)
+    dim_o, fdhc_o, _ = O.hypercubes(*fo)
+    dim_t, fdhc_t, _ = T.hypercubes_raw(fo[2], fo[0], fo[1])
+    assert_same_bits(dim_o, dim_t, 'dim')
+    assert_same_bits(fdhc_o, fdhc_t, 'fdhc')
+    for m in (1, 2):
+        po, do = O.tree_topology(m)
+        pt, dt = T.tree_topology(m)
+        assert np.array_equal(po, pt.astype(np.int64)), f'kd parent, method {m}'
+        assert np.array_equal(do, dt), f'kd depth, method {m}'
+    ties = 0
+    for m in (0, 1, 2):
+        for s in (0, 1):
+            a, b = O.ndpolate(q, m, s), T.ndpolate(q, m, s)
+            assert_same_bits(a[0], b[0], f'interps {m}/{s}')
+            assert_same_bits(a[1], b[1], f'dists {m}/{s}')
+            ties += T.stat('ties')
+            if m:
+                a, b = O.find_nearest(*fo, m, s), T.find_nearest(q, m, s)
+                assert_same_bits(a[0], b[0], f'coords {m}/{s}')
+                assert_same_bits(a[1], b[1], f'ndist {m}/{s}')
+    assert_same_bits(O.distance(q), T.distance(q), 'distance')
+    assert T.stat('launches') > 0
+    T.close()
+
+
+def test_tie_pass_runs_before_topology_exists():
+    """Exact mid-point queries on a fresh table: the first call meets ties with no kd
+    topology yet, builds it, and resolves them like the reference's traversal."""
+    name, axes, nbasic, grid = build_cases()[1]
+    rng = np.random.default_rng(3)
+    mids = [(a[1:] + a[:-1]) / 2 for a in axes]
+    q = np.stack([rng.choice(m, 5000) for m in mids], axis=1) + np.array([7.0, 0, 0])    # outside along axis 0
+    O = Oracle('port', axes, grid, nbasic)
+    T = _table(axes, grid, nbasic)
+    a, b = O.ndpolate(q, 1, 0), T.ndpolate(q, 1, 0)
+    assert T.stat('ties') > 0
+    assert_same_bits(a[0], b[0], 'interps')
+    assert_same_bits(a[1], b[1], 'dists')
+    a, b = O.ndpolate(q, 2, 0), T.ndpolate(q, 2, 0)
+    assert_same_bits(a[0], b[0], 'interps linear')
+    T.close()
+
+
+def test_host_chunking_device_tensors_and_search_variants_agree():
+    import torch
+    name, axes, nbasic, grid = build_cases()[7]          # 5-D with a structured void
+    q = adversarial_queries(axes, 30000, np.random.default_rng(8))
+    O = Oracle('port', axes, grid, nbasic)
+    want = {(m, s): O.ndpolate(q, m, s) for m in (0, 1, 2) for s in (0, 1)}
+    T = _table(axes, grid, nbasic, chunk=4096)           # many chunks through the 2-slot pipeline
+    for (m, s), w in want.items():
+        got = T.ndpolate(q, m, s)
+        assert_same_bits(w[0], got[0], f'chunked interps {m}/{s}')
+        assert_same_bits(w[1], got[1], f'chunked dists {m}/{s}')
+    assert T.stat('h2d_bytes') == q.nbytes
+    qd = torch.as_tensor(q, device='cuda')
+    for (m, s), w in want.items():
+        gi, gd = T.ndpolate(qd, m, s)
+        assert gi.is_cuda and gd.is_cuda
+        assert_same_bits(w[0], gi.cpu().numpy(), f'device interps {m}/{s}')
+        assert_same_bits(w[1], gd.cpu().numpy(), f'device dists {m}/{s}')
+    assert T.stat('h2d_bytes') == 0
+    for impl in (1, 2):                                  # literal warp scan vs lattice descent
+        T.set_option('linear_search', impl)
+        for m in (1, 2):
+            got = T.ndpolate(q, m, 1)
+            assert_same_bits(want[(m, 1)][0], got[0], f'linear_search={impl} interps {m}')
+            assert_same_bits(want[(m, 1)][1], got[1], f'linear_search={impl} dists {m}')
+    T.close()
+
+
+@pytest.mark.parametrize('spec', [('C1', None, 200000), ('C2', 50, 200000), ('C3', 24, 60000),
+                                  ('C4', 12, 100000), ('C5', 6, 100000)], ids=lambda s: f'{s[0]}@{s[1]}')
+def test_baseline_configs_scaled_vs_oracle(spec):
+    """The BASELINE.json configurations (C1/C2 at full grid size, C3-C5 scaled so that the
+    oracle's O(N*depth) tree build finishes in seconds), every extrapolation method."""
+    from ndpolator_b200 import synth
+    name, scale, n = spec
+    w = synth.workload(name, scale, n_queries=n)
+    grid, q = w.grid(), w.queries(0, n)
+    nb = len(w.basic_axes)
+    O = Oracle('port', w.axes, grid, nb)
+    T = _table(w.axes, grid, nb)
+    for m in (0, 1, 2):
+        a, b = O.ndpolate(q, m, 0, threads=os.cpu_count() or 1), T.ndpolate(q, m, 0)
+        assert_same_bits(a[0], b[0], f'{name} interps method {m}')
+        assert_same_bits(a[1], b[1], f'{name} dists method {m}')
+    sub = q[:300]
+    for m in (1, 2):
+        a, b = O.ndpolate(sub, m, 1), T.ndpolate(sub, m, 1)
+        assert_same_bits(a[0], b[0], f'{name} interps method {m}, search linear')
+        assert_same_bits(a[1], b[1], f'{name} dists method {m}, search linear')
+    T.close()
+
+
+def test_c4_full_size_properties():
+    """BASELINE.json's headline configuration at full size (40^5 grid, 819 MB; cell-major
+    copy 23 GB): size-independent properties, plus a small sub-sample pinned to the oracle
+    through the tree-free full scan (the oracle's kd-tree for this grid takes ~15 min to build)."""
+    import torch
+    from ndpolator_b200 import synth
+    w = synth.workload('C4', None)
+    dev = 'cuda'
+    grid_d = w.grid(dev)
+    nb = len(w.basic_axes)
+    from ndpolator_b200.cndpolator import Table
+    T = Table(w.axes, grid_d, nb)
+    assert T.stat('cellmajor') == 1
+    n = 1 << 22
+    q = w.queries(0, n, dev)
+    # (1) strided and cell-major gathers agree bit for bit; NaN only where no extrapolation is possible
+    res = {}
+    for m in (0, 1, 2):
+        gi, gd = T.ndpolate(q, m, 0)
+        res[m] = (gi.clone(), gd.clone())
+    T.set_option('gather', 1)
+    for m in (0, 2):
+        gi, gd = T.ndpolate(q, m, 0)
+        assert torch.equal(gi.view(torch.int64), res[m][0].view(torch.int64))
+        assert torch.equal(gd.view(torch.int64), res[m][1].view(torch.int64))
+    T.set_option('gather', 2)
+    none_nan = torch.isnan(res[0][0][:, 0])
+    frac_in = 1.0 - none_nan.double().mean().item()
+    assert 0.45 < frac_in < 0.65                       # ~56 % of the near mix sits in a full hypercube
+    for m in (1, 2):
+        assert not torch.isnan(res[m][0]).any()
+        assert torch.equal(res[m][0][~none_nan], res[0][0][~none_nan])     # in-grid points do not depend on the method
+        assert (res[m][1][~none_nan] == 0).all() and (res[m][1] >= 0).all()
+        assert (res[m][1][none_nan] > 0).float().mean() > 0.99
+    # (2) nearest: the value returned is the grid value at the coords the search reports, kd == full scan
+    c_kd, d_kd = T.find_nearest(q[:200000], 1, 0)
+    c_ls, d_ls = T.find_nearest(q[:200000], 1, 1)
+    assert torch.equal(c_kd, c_ls) and torch.equal(d_kd.view(torch.int64), d_ls.view(torch.int64))
+    flat = (c_kd.long() * torch.tensor([40 ** 4, 40 ** 3, 40 ** 2, 40, 1], device=dev)).sum(1)
+    vals = grid_d.reshape(-1)[flat]
+    off = none_nan[:200000]
+    assert torch.equal(vals[off], res[1][0][:200000, 0][off])
+    # (3) sub-sample vs the CPU oracle (full scan: no tree build)
+    grid_h = grid_d.cpu().numpy()
+    O = Oracle('port', w.axes, grid_h, nb)
+    idx = torch.nonzero(none_nan)[:12, 0]
+    sub = q[idx].cpu().numpy()
+    a = O.ndpolate(sub, 1, 1)
+    assert_same_bits(a[0], res[1][0][idx].cpu().numpy(), 'C4 full size, nearest vs oracle scan')
+    assert_same_bits(a[1], res[1][1][idx].cpu().numpy(), 'C4 full size, nearest dists vs oracle scan')
+    inside = torch.nonzero(~none_nan)[:20000, 0]
+    a = O.ndpolate(q[inside].cpu().numpy(), 0, 0)
+    assert_same_bits(a[0], res[0][0][inside].cpu().numpy(), 'C4 full size, in-grid vs oracle')
+    T.close()
