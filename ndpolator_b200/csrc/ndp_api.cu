@@ -48,7 +48,8 @@ extern "C" const char *ndpb_version(void) { return "ndpb200 0.1.0 (sm_100a; pari
 // table
 // ---------------------------------------------------------------------------
 struct Pyramid {
-    NdpPyramid dev{};                       // device pointers inside
+    NdpPyramid dev{};                       // host copy of the descriptor (device pointers inside)
+    NdpPyramid *d_desc = nullptr;           // the same descriptor in device memory (kernels read it there)
     std::vector<uint32_t *> owned;
     int count = 0;                          // set bits at level 0
 };
@@ -62,7 +63,7 @@ struct Topology {
 struct Slot {                               // one in-flight batch
     double *q = nullptr, *interps = nullptr, *dists = nullptr;     // staging (host callers only)
     int *coords = nullptr;
-    int *list = nullptr, *chosen = nullptr, *tielist = nullptr;
+    int *list = nullptr, *chosen = nullptr, *tielist = nullptr, *hardlist = nullptr;
     long long cap_q = 0, cap_work = 0, cap_coords = 0;
     NdpCounters *ctr = nullptr;             // device
     NdpCounters *ctr_host = nullptr;        // pinned
@@ -78,7 +79,8 @@ struct ndpb_table {
     bool has_grid = false;
     double *ticks = nullptr, *grid = nullptr, *cells = nullptr;
     long long grid_doubles = 0;
-    Pyramid pyr[2];                         // [0] vmask, [1] hcmask
+    Pyramid pyr[2];                         // [0] vmask, [1] hcmask: over the whole basic lattice
+    Pyramid red[2];                         // the same masks over their variant axes only
     Topology topo[2];
     cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
     cudaStream_t s_owned = nullptr;         // the compute stream this table created (s_compute may be a caller's)
@@ -111,25 +113,29 @@ static size_t tick_smem(const ndpb_table *t) { return (size_t) t->nticks * sizeo
 static int ticks_in_smem(const ndpb_table *t) { return tick_smem(t) <= 40 * 1024; }
 static size_t smem_bytes(const ndpb_table *t) { return ticks_in_smem(t) ? tick_smem(t) : 0; }
 
-static int build_pyramid(ndpb_table *t, Pyramid &P, uint32_t *level0)
+// Builds the occupancy pyramid above `level0` (nvar axes of sizes dim0[], mapped to the basic
+// axes var_axis[]); takes ownership of level0.
+static int build_pyramid(ndpb_table *t, Pyramid &P, uint32_t *level0, int nvar, const int *var_axis, const int *dim0, bool full)
 {
     const NdpGeom &g = t->g;
     NdpPyramid &D = P.dev;
     D.nlev = 0;
+    D.nvar = nvar;
     int dim[NDP_MAX_AXES];
-    for (int a = 0; a < g.nbasic; a++) dim[a] = g.len[a];
+    for (int j = 0; j < nvar; j++) { dim[j] = dim0[j]; D.var_axis[j] = var_axis[j]; }
+    P.owned.push_back(level0);
     uint32_t *prev = level0;
     for (int lev = 0; lev < NDP_MAX_LEVELS; lev++) {
         long long nblocks = 1;
-        for (int a = g.nbasic - 1, s = 1; a >= 0; a--) { D.dim[lev][a] = dim[a]; D.stride[lev][a] = s; s *= dim[a]; nblocks *= dim[a]; }
+        for (int j = nvar - 1, s = 1; j >= 0; j--) { D.dim[lev][j] = dim[j]; D.stride[lev][j] = s; s *= dim[j]; nblocks *= dim[j]; }
         if (lev == 0) D.bits[0] = level0;
         else {
             uint32_t *bits = nullptr;
             CU(cudaMalloc(&bits, sizeof(uint32_t) * ((nblocks + 31) / 32)));
             P.owned.push_back(bits);
             PyrLevelArgs A{};
-            A.nb = g.nbasic;
-            for (int a = 0; a < g.nbasic; a++) { A.cdim[a] = D.dim[lev - 1][a]; A.cstride[a] = D.stride[lev - 1][a]; A.pdim[a] = dim[a]; }
+            A.nb = nvar;
+            for (int j = 0; j < nvar; j++) { A.cdim[j] = D.dim[lev - 1][j]; A.cstride[j] = D.stride[lev - 1][j]; A.pdim[j] = dim[j]; }
             A.nparent = (int) nblocks; A.cbits = prev; A.pbits = bits;
             k_pyr_level<<<blocks_for(((nblocks + 31) / 32) * 32), NDP_BLOCK, 0, t->s_compute>>>(A);
             CU(cudaGetLastError());
@@ -138,30 +144,62 @@ static int build_pyramid(ndpb_table *t, Pyramid &P, uint32_t *level0)
         }
         D.nlev = lev + 1;
         if (nblocks == 1) break;
-        for (int a = 0; a < g.nbasic; a++) dim[a] = (dim[a] + 1) / 2;
+        for (int j = 0; j < nvar; j++) dim[j] = (dim[j] + 1) / 2;
     }
-    // any_set: the single top block; first_clear: lowest clear bit of level 0
+    // any_set: the single top block; first_clear: lowest clear bit of level 0 (full pyramid only)
     uint32_t top = 0;
-    int *d_first = nullptr;
-    int init = INT_MAX;
-    CU(cudaMalloc(&d_first, sizeof(int)));
-    CU(cudaMemcpyAsync(d_first, &init, sizeof(int), cudaMemcpyHostToDevice, t->s_compute));
-    k_first_clear<<<blocks_for((g.nverts + 31) / 32), NDP_BLOCK, 0, t->s_compute>>>(level0, g.nverts, d_first);
-    CU(cudaGetLastError());
-    int first = 0;
-    CU(cudaMemcpyAsync(&first, d_first, sizeof(int), cudaMemcpyDeviceToHost, t->s_compute));
+    int first = INT_MAX;
+    if (full) {
+        int *d_first = nullptr;
+        CU(cudaMalloc(&d_first, sizeof(int)));
+        CU(cudaMemcpyAsync(d_first, &first, sizeof(int), cudaMemcpyHostToDevice, t->s_compute));
+        k_first_clear<<<blocks_for((g.nverts + 31) / 32), NDP_BLOCK, 0, t->s_compute>>>(level0, g.nverts, d_first);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&first, d_first, sizeof(int), cudaMemcpyDeviceToHost, t->s_compute));
+        CU(cudaStreamSynchronize(t->s_compute));
+        CU(cudaFree(d_first));
+    }
     CU(cudaMemcpyAsync(&top, D.bits[D.nlev - 1], sizeof(uint32_t), cudaMemcpyDeviceToHost, t->s_compute));
     CU(cudaStreamSynchronize(t->s_compute));
-    CU(cudaFree(d_first));
     D.first_clear = (first == INT_MAX) ? -1 : first;
     D.any_set = (top & 1u) ? 1 : 0;
+    CU(cudaMalloc(&P.d_desc, sizeof(NdpPyramid)));
+    CU(cudaMemcpy(P.d_desc, &D, sizeof(NdpPyramid), cudaMemcpyHostToDevice));
     return NDPB_OK;
+}
+
+// Finds the basic axes the mask actually depends on and builds the pyramid of the slice they span.
+static int build_reduced(ndpb_table *t, int m)
+{
+    const NdpGeom &g = t->g;
+    const uint32_t *bits = t->pyr[m].dev.bits[0];
+    const int ref = m;                          // vertex mask: coordinate 0; hypercube mask: coordinate 1
+    int *d_diff = nullptr, diff[NDP_MAX_AXES] = {0};
+    CU(cudaMalloc(&d_diff, sizeof(diff)));
+    CU(cudaMemsetAsync(d_diff, 0, sizeof(diff), t->s_compute));
+    k_mask_variance<<<blocks_for(g.nverts), NDP_BLOCK, 0, t->s_compute>>>(g, bits, ref, d_diff);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(diff, d_diff, sizeof(diff), cudaMemcpyDeviceToHost, t->s_compute));
+    CU(cudaStreamSynchronize(t->s_compute));
+    CU(cudaFree(d_diff));
+    SliceArgs A{};
+    A.g = g; A.ref = ref; A.bits = bits; A.nvar = 0;
+    long long nslice = 1;
+    for (int a = 0; a < g.nbasic; a++)
+        if (diff[a]) { A.var_axis[A.nvar] = a; A.dim[A.nvar] = g.len[a]; nslice *= g.len[a]; A.nvar++; }
+    A.nslice = (int) nslice;
+    uint32_t *level0 = nullptr;
+    CU(cudaMalloc(&level0, sizeof(uint32_t) * ((nslice + 31) / 32)));
+    A.out = level0;
+    k_mask_slice<<<blocks_for(((nslice + 31) / 32) * 32), NDP_BLOCK, 0, t->s_compute>>>(A);
+    CU(cudaGetLastError());
+    return build_pyramid(t, t->red[m], level0, A.nvar, A.var_axis, A.dim, false);
 }
 
 static void free_slot(Slot &s)
 {
     cudaFree(s.q); cudaFree(s.interps); cudaFree(s.dists); cudaFree(s.coords);
-    cudaFree(s.list); cudaFree(s.chosen); cudaFree(s.tielist); cudaFree(s.ctr);
+    cudaFree(s.list); cudaFree(s.chosen); cudaFree(s.tielist); cudaFree(s.hardlist); cudaFree(s.ctr);
     if (s.ctr_host) cudaFreeHost(s.ctr_host);
     cudaEvent_t *ev[] = {&s.in_done, &s.searched, &s.out_ready, &s.out_done, &s.t0, &s.t1, &s.t2, &s.t3};
     for (auto e : ev) if (*e) cudaEventDestroy(*e);
@@ -174,10 +212,11 @@ extern "C" int ndpb_table_destroy(ndpb_table *t)
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
     cudaFree(t->ticks); cudaFree(t->grid); cudaFree(t->cells);
-    for (auto &P : t->pyr) {
-        for (auto p : P.owned) cudaFree(p);
-        if (P.dev.nlev) cudaFree((void *) P.dev.bits[0]);
-    }
+    for (Pyramid *set : {t->pyr, t->red})
+        for (int m = 0; m < 2; m++) {
+            for (auto p : set[m].owned) cudaFree(p);
+            cudaFree(set[m].d_desc);
+        }
     for (auto &T : t->topo) { cudaFree(T.parent); cudaFree(T.depth); }
     for (auto &s : t->slot) free_slot(s);
     if (t->s_owned) cudaStreamDestroy(t->s_owned);
@@ -264,6 +303,13 @@ extern "C" int ndpb_table_create(const double *const *axes, const int32_t *axlen
         if (is_device_ptr(axes[a])) CUT(cudaMemcpy(flat.data() + g.tickoff[a], axes[a], sizeof(double) * axlen[a], cudaMemcpyDeviceToHost));
         else memcpy(flat.data() + g.tickoff[a], axes[a], sizeof(double) * axlen[a]);
     }
+    for (int a = 0; a < naxes; a++) {
+        const double *tk = flat.data() + g.tickoff[a];
+        bool ascending = true;
+        for (int i = 1; i < axlen[a]; i++) if (!(tk[i] > tk[i - 1])) ascending = false;
+        const double span = tk[axlen[a] - 1] - tk[0];
+        g.inv_step[a] = (ascending && span > 0 && span < 1e300) ? (double) (axlen[a] - 1) / span : 0.0;
+    }
     CUT(cudaMalloc(&t->ticks, sizeof(double) * nticks));
     CUT(cudaMemcpy(t->ticks, flat.data(), sizeof(double) * nticks, cudaMemcpyHostToDevice));
 
@@ -279,8 +325,12 @@ extern "C" int ndpb_table_create(const double *const *axes, const int32_t *axlen
         k_vmask_bits<<<nb, NDP_BLOCK, 0, t->s_compute>>>(t->grid, g.nverts, g.vstride[nbasic - 1] * vdim, vbits);
         k_hcmask_bits<<<nb, NDP_BLOCK, 0, t->s_compute>>>(g, vbits, hbits);
         CUT(cudaGetLastError());
-        int rc = build_pyramid(t, t->pyr[0], vbits);
-        if (rc == NDPB_OK) rc = build_pyramid(t, t->pyr[1], hbits);
+        int all_axes[NDP_MAX_AXES];
+        for (int a = 0; a < nbasic; a++) all_axes[a] = a;
+        int rc = build_pyramid(t, t->pyr[0], vbits, nbasic, all_axes, g.len, true);
+        if (rc == NDPB_OK) rc = build_pyramid(t, t->pyr[1], hbits, nbasic, all_axes, g.len, true);
+        if (rc == NDPB_OK) rc = build_reduced(t, 0);
+        if (rc == NDPB_OK) rc = build_reduced(t, 1);
         if (rc == NDPB_OK) rc = maybe_build_cells(t);
         if (rc != NDPB_OK) return bail(rc);
     }
@@ -338,6 +388,8 @@ extern "C" int64_t ndpb_table_stat(const ndpb_table *t, const char *key)
     if (k == "main_ns") return (int64_t) (t->st_main_ms * 1e6);
     if (k == "search_ns") return (int64_t) (t->st_search_ms * 1e6);
     if (k == "finish_ns") return (int64_t) (t->st_finish_ms * 1e6);
+    if (k == "variant_axes_nearest") return t->red[0].dev.nvar;
+    if (k == "variant_axes_linear") return t->red[1].dev.nvar;
     if (k == "tree_levels_nearest") return t->topo[0].levels;
     if (k == "tree_levels_linear") return t->topo[1].levels;
     return -1;
@@ -490,11 +542,12 @@ static int ensure_slot(ndpb_table *t, Slot &s, long long nq, bool stage_q, bool 
     }
     if (work && nq > s.cap_work) {
         CU(cudaStreamSynchronize(t->s_compute));
-        cudaFree(s.list); cudaFree(s.chosen); cudaFree(s.tielist);
-        s.list = s.chosen = s.tielist = nullptr; s.cap_work = 0;
+        cudaFree(s.list); cudaFree(s.chosen); cudaFree(s.tielist); cudaFree(s.hardlist);
+        s.list = s.chosen = s.tielist = s.hardlist = nullptr; s.cap_work = 0;
         CU(cudaMalloc(&s.list, sizeof(int) * nq));
         CU(cudaMalloc(&s.chosen, sizeof(int) * nq));
         CU(cudaMalloc(&s.tielist, sizeof(int) * nq));
+        CU(cudaMalloc(&s.hardlist, sizeof(int) * nq));
         s.cap_work = nq;
     }
     return NDPB_OK;
@@ -573,20 +626,25 @@ static bool use_brute(const ndpb_table *t, int search)
     return t->g.nverts <= 4096;      // the literal scan only where it is cheap; identical results either way
 }
 
-static int launch_search(ndpb_table *t, SearchArgs &A, long long upper, cudaStream_t st)
+// hard == false: pass 1 over the work list (or the literal scan); hard == true: the descent over A.sublist
+static int launch_search(ndpb_table *t, SearchArgs &A, long long upper, bool hard, cudaStream_t st)
 {
     const int m = A.method == NDPB_METHOD_LINEAR ? 1 : 0;
-    A.g = t->g; A.P = t->pyr[m].dev;
+    A.g = t->g; A.F = t->pyr[m].d_desc; A.R = t->red[m].d_desc;
     A.have_topo = t->topo[m].built ? 1 : 0;
     A.topo.parent = t->topo[m].parent; A.topo.depth = t->topo[m].depth;
     A.ticks = t->ticks; A.nticks = t->nticks; A.ticks_in_smem = ticks_in_smem(t);
     const size_t smem = smem_bytes(t);
-    if (use_brute(t, A.search) && !A.sublist) {
-        const int blocks = (int) std::min<long long>((upper * 32 + NDP_BLOCK - 1) / NDP_BLOCK, (long long) t->sm_count * 8);
+    const long long cap = (long long) t->sm_count * 8;
+    if (hard) {
+        const int blocks = (int) std::min<long long>((upper + NDP_BLOCK - 1) / NDP_BLOCK, cap);
+        k_search_hard<<<std::max(blocks, 1), NDP_BLOCK, smem, st>>>(A);
+    } else if (use_brute(t, A.search)) {
+        const int blocks = (int) std::min<long long>((upper * 32 + NDP_BLOCK - 1) / NDP_BLOCK, cap);
         k_search_brute<<<std::max(blocks, 1), NDP_BLOCK, smem, st>>>(A);
     } else {
-        const int blocks = (int) std::min<long long>((upper + NDP_BLOCK - 1) / NDP_BLOCK, (long long) t->sm_count * 8);
-        k_search<<<std::max(blocks, 1), NDP_BLOCK, smem, st>>>(A);
+        const int blocks = (int) std::min<long long>((upper + NDP_BLOCK - 1) / NDP_BLOCK, cap);
+        k_search_fast<<<std::max(blocks, 1), NDP_BLOCK, smem, st>>>(A);
     }
     CU(cudaGetLastError());
     t->st_launches++;
@@ -618,9 +676,14 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
         S.sublist = nullptr;
         S.count = (task == TASK_NDPOLATE) ? &s.ctr->n_off : nullptr;
         S.count_host = n;
-        S.chosen = s.chosen; S.dists = dists; S.coords = coords; S.tielist = s.tielist; S.ctr = s.ctr;
-        int rc = launch_search(t, S, n, st);
+        S.chosen = s.chosen; S.dists = dists; S.coords = coords; S.hardlist = s.hardlist; S.tielist = s.tielist; S.ctr = s.ctr;
+        int rc = launch_search(t, S, n, false, st);
         if (rc) return rc;
+        if (!use_brute(t, search)) {                  // pass 2: whatever pass 1 could not prove
+            S.sublist = s.hardlist; S.count = &s.ctr->n_hard;
+            rc = launch_search(t, S, n, true, st);
+            if (rc) return rc;
+        }
     }
     CU(cudaEventRecord(s.t2, st));
     if (task == TASK_NDPOLATE && method != NDPB_METHOD_NONE) {
@@ -659,8 +722,8 @@ static int batch_complete(ndpb_table *t, Slot &s, Task task, const double *q, lo
         S.q = q; S.method = method; S.search = search;
         S.list = (task == TASK_NDPOLATE) ? s.list : nullptr;
         S.sublist = s.tielist; S.count = &s.ctr->n_tie; S.count_host = 0;
-        S.chosen = s.chosen; S.dists = dists; S.coords = coords; S.tielist = s.tielist; S.ctr = s.ctr;
-        rc = launch_search(t, S, c.n_tie, st);
+        S.chosen = s.chosen; S.dists = dists; S.coords = coords; S.hardlist = s.hardlist; S.tielist = s.tielist; S.ctr = s.ctr;
+        rc = launch_search(t, S, c.n_tie, true, st);
         if (rc) return rc;
         if (task == TASK_NDPOLATE) {
             FinishArgs F{};

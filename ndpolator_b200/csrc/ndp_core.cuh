@@ -54,6 +54,7 @@ struct NdpGeom {
     int bstride[NDP_MAX_AXES];        // same as vstride but within the basic-only lattice
     int nverts;                       // basic lattice size (ndp_types.c:174-176); < 2^31 like the reference's int
     long long ncells;
+    double inv_step[NDP_MAX_AXES];    // (len-1)/(last-first): index guess for the import; 0 = always bisect
 };
 
 // Bit-packed occupancy pyramid over the basic lattice.  Level 0 = one bit per
@@ -61,10 +62,12 @@ struct NdpGeom {
 // any vertex inside is set; the last level is a single block.
 struct NdpPyramid {
     int nlev;
-    int dim[NDP_MAX_LEVELS][NDP_MAX_AXES];
+    int nvar;                         // axes this pyramid spans (all basic axes, or only the mask-variant ones)
+    int var_axis[NDP_MAX_AXES];       // pyramid axis j -> basic axis
+    int dim[NDP_MAX_LEVELS][NDP_MAX_AXES];      // indexed by pyramid axis j
     int stride[NDP_MAX_LEVELS][NDP_MAX_AXES];
     const uint32_t *bits[NDP_MAX_LEVELS];
-    int first_clear;                  // lowest vertex id whose level-0 bit is clear, or -1
+    int first_clear;                  // lowest vertex id whose level-0 bit is clear, or -1 (full pyramid only)
     int any_set;                      // 0 when the mask is empty
 };
 
@@ -97,6 +100,40 @@ NDP_HD void ndp_import_axis(const double *tick, int len, double x, int &index, i
     index = lo; flag = f; normed = t;
 }
 
+// Same result as ndp_import_axis for an ascending axis, without the dependent
+// chain of the bisection: guess the index from the mean spacing, then verify the
+// two conditions that characterise the bisection's answer on a sorted axis
+// (smallest l in [1, len-1] with tick[l] >= x + rtol, else len-1) and walk at most
+// two ticks; anything else falls back to the bisection itself.  inv_step == 0
+// (axis not ascending, or degenerate) always bisects.
+NDP_HD void ndp_import_axis_guess(const double *tick, int len, double inv_step, double x, int &index, int &flag, double &normed)
+{
+    const double rtol = 1e-6;
+    if (inv_step > 0.0) {
+        const double xr = x + rtol;
+        double gd = floor((xr - tick[0]) * inv_step) + 1.0;
+        gd = gd < 1.0 ? 1.0 : (gd > (double) (len - 1) ? (double) (len - 1) : gd);
+        int l = (gd == gd) ? (int) gd : 1;
+        bool found = false;
+#pragma unroll
+        for (int step = 0; step < 3 && !found; step++) {
+            const double tl = tick[l], tp = tick[l - 1];
+            const bool up_ok = !(xr > tl) || l == len - 1;
+            const bool lo_ok = l == 1 || xr > tp;
+            if (up_ok && lo_ok) {
+                int f = (x < tick[0] || x > tick[len - 1]) ? NDP_F_OOB : 0;
+                double t = (x - tp) / (tl - tp);
+                if (fabs(t) < rtol || (l == len - 1 && fabs(t - 1) < rtol)) f |= NDP_F_ON_VERTEX;
+                index = l; flag = f; normed = t;
+                found = true;
+            } else if (!up_ok) l++;
+            else l--;
+        }
+        if (found) return;
+    }
+    ndp_import_axis(tick, len, x, index, flag, normed);
+}
+
 // One lerp of c_ndpolate (:91): three roundings; -fmad=false keeps them apart.
 NDP_HD double ndp_lerp(double lo, double hi, double x)
 {
@@ -124,31 +161,49 @@ NDP_HD double ndp_cell_reduce(Load load, const double *x, unsigned pinmask, unsi
     double fv[1 << N];
     load(fv);
 
-    bool bad = false;
+    if (pinmask == 0) {
+        // the common case: every axis interpolates (constant trip counts so that fv[] stays in registers)
 #pragma unroll
-    for (int j = 0; j < (1 << N); j++) {
-        bool used = (((unsigned) j ^ selbits) & pinmask) == 0;
-        bad |= used && (fv[j] != fv[j]);
-    }
-    nan_used = bad;
-
+        for (int a = 0; a < N; a++) {
+            const int h = 1 << (N - 1 - a);
+            const double xa = x[a];
 #pragma unroll
-    for (int a = 0; a < N; a++) {
-        const int h = 1 << (N - 1 - a);
-        const bool pinned = (pinmask >> (N - 1 - a)) & 1u;
-        const bool upper = (selbits >> (N - 1 - a)) & 1u;
-        const double xa = x[a];
-        // constant trip count so that the front end unrolls fully and fv[] stays in registers
+            for (int j = 0; j < (N ? (1 << (N - 1)) : 1); j++)
+                if (j < h) fv[j] = ndp_lerp(fv[j], fv[j + h], xa);
+        }
+    } else {
 #pragma unroll
-        for (int j = 0; j < (N ? (1 << (N - 1)) : 1); j++) {
-            if (j < h) {
-                double l = ndp_lerp(fv[j], fv[j + h], xa);
-                double s = upper ? fv[j + h] : fv[j];
-                fv[j] = pinned ? s : l;
+        for (int a = 0; a < N; a++) {
+            const int h = 1 << (N - 1 - a);
+            const bool pinned = (pinmask >> (N - 1 - a)) & 1u;
+            const bool upper = (selbits >> (N - 1 - a)) & 1u;
+            const double xa = x[a];
+#pragma unroll
+            for (int j = 0; j < (N ? (1 << (N - 1)) : 1); j++) {
+                if (j < h) {
+                    double l = ndp_lerp(fv[j], fv[j + h], xa);
+                    double s = upper ? fv[j + h] : fv[j];
+                    fv[j] = pinned ? s : l;
+                }
             }
         }
     }
-    return fv[0];
+    const double result = fv[0];
+
+    // A NaN in any used corner reaches the result through every lerp and select, so a
+    // non-NaN result proves all used corners defined; only a NaN result needs the
+    // corner-by-corner test of :491 (it may also stem from a NaN query coordinate).
+    bool bad = false;
+    if (result != result) {
+        load(fv);
+#pragma unroll
+        for (int j = 0; j < (1 << N); j++) {
+            bool used = (((unsigned) j ^ selbits) & pinmask) == 0;
+            bad |= used && (fv[j] != fv[j]);
+        }
+    }
+    nan_used = bad;
+    return result;
 }
 
 // Runtime-n version (any n <= NDP_MAX_AXES): walks only the used corners in
@@ -356,18 +411,29 @@ NDP_HD bool ndp_search_fast(const NdpGeom &g, const NdpPyramid &P, int mode, con
     return true;
 }
 
+// Descent over pyramid P.  When P spans only some basic axes (the mask does not
+// depend on the others), fixed[] holds the coordinate of every other axis and the
+// descent runs on that slice; the metric still sums all basic axes in order.
 NDP_HD void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
-                            const NdpTopo *topo, NdpHit &hit)
+                            const int *fixed, const NdpTopo *topo, NdpHit &hit)
 {
-    const int nb = g.nbasic;
-    const unsigned nchild = 1u << nb;
+    const int nb = g.nbasic, nv = P.nvar;
+    const unsigned nchild = 1u << nv;
     const int top = P.nlev - 1;
     const bool kd = mode < NDP_MODE_LS_NEAREST;
     // children are ordered by which half the query leans to; for cell modes lean on q + 0.5
     const double lean = (mode == NDP_MODE_KD_NEAREST || mode == NDP_MODE_LS_NEAREST) ? 0.0 : 0.5;
 
-    int bc[NDP_MAX_LEVELS][NDP_MAX_AXES];     // block coordinates along the current path
+    int bc[NDP_MAX_LEVELS][NDP_MAX_AXES];     // block coordinates along the current path (pyramid axes)
     unsigned next[NDP_MAX_LEVELS];            // next child ordinal to try at each level
+    int jof[NDP_MAX_AXES];                    // basic axis -> pyramid axis, or -1
+    double fterm[NDP_MAX_AXES];               // metric term of the fixed axes
+    int base = 0;                             // vertex id contribution of the fixed axes
+
+    for (int a = 0; a < nb; a++) jof[a] = -1;
+    for (int j = 0; j < nv; j++) jof[P.var_axis[j]] = j;
+    for (int a = 0; a < nb; a++)
+        if (jof[a] < 0) { fterm[a] = ndp_axis_term(mode, Q.qc[a], fixed[a], fixed[a]); base += fixed[a] * g.bstride[a]; }
 
     int best = -1;
     double bestd = 0.0;
@@ -377,10 +443,14 @@ NDP_HD void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, con
     if (!P.any_set) { hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_EMPTY; return; }
 
     int lev = top;
-    for (int a = 0; a < nb; a++) bc[top][a] = 0;
+    for (int j = 0; j < nv; j++) bc[top][j] = 0;
     next[top] = 0;
-    if (top == 0) {          // single-vertex lattice cannot happen (every axis has >= 2 ticks), kept for safety
-        hit.vertex = 0; hit.dsel = 0.0; hit.status = NDP_SEARCH_OK; return;
+    if (top == 0) {
+        // a one-point slice (every axis is mask-invariant): that point is the only candidate
+        double d = 0.0;
+        for (int a = 0; a < nb; a++) d += fterm[a];
+        hit.vertex = base; hit.dsel = ndp_add_assoc(g, mode, Q, d); hit.status = NDP_SEARCH_OK;
+        return;
     }
 
     for (;;) {
@@ -394,40 +464,109 @@ NDP_HD void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, con
         int cb[NDP_MAX_AXES];
         int flat = 0;
         bool inside = true;
-        double bound = 0.0;
-        for (int a = 0; a < nb; a++) {
-            const int mid = ((2 * bc[lev][a] + 1) << cl);          // first coordinate of the upper child
+        for (int j = 0; j < nv; j++) {
+            const int a = P.var_axis[j];
+            const int mid = ((2 * bc[lev][j] + 1) << cl);          // first coordinate of the upper child
             const unsigned nearbit = (Q.qc[a] + lean >= (double) mid) ? 1u : 0u;
-            const int b = 2 * bc[lev][a] + (int) (((k >> a) & 1u) ^ nearbit);
-            if (b >= P.dim[cl][a]) { inside = false; break; }
-            cb[a] = b;
-            flat += b * P.stride[cl][a];
-            int lo = b << cl;
-            int hi = ((b + 1) << cl) - 1;
-            if (hi > g.len[a] - 1) hi = g.len[a] - 1;
-            bound += ndp_axis_term(mode, Q.qc[a], lo, hi);
+            const int b = 2 * bc[lev][j] + (int) (((k >> j) & 1u) ^ nearbit);
+            if (b >= P.dim[cl][j]) { inside = false; break; }
+            cb[j] = b;
+            flat += b * P.stride[cl][j];
         }
         if (!inside) continue;
         if (!ndp_bit(P.bits[cl], flat)) continue;
+        // lower bound of the block, summed in the reference's axis order; stop as soon as it is hopeless
+        double bound = 0.0;
+        bool hopeless = false;
+        for (int a = 0; a < nb; a++) {
+            const int j = jof[a];
+            if (j < 0) bound += fterm[a];
+            else {
+                int lo = cb[j] << cl;
+                int hi = ((cb[j] + 1) << cl) - 1;
+                if (hi > g.len[a] - 1) hi = g.len[a] - 1;
+                bound += ndp_axis_term(mode, Q.qc[a], lo, hi);
+            }
+            if (best >= 0 && bound > bestd) { hopeless = true; break; }   // terms are >= 0: the sum only grows
+        }
+        if (hopeless) continue;
         bound = ndp_add_assoc(g, mode, Q, bound);
         if (best >= 0 && bound > bestd) continue;     // equal bounds are explored: ties matter
         if (cl == 0) {
             // a level-0 block is one vertex and its bound is the reference's distance expression
-            if (best < 0 || bound < bestd) { best = flat; bestd = bound; tie = false; }
+            int vid = base;
+            for (int j = 0; j < nv; j++) vid += cb[j] * g.bstride[P.var_axis[j]];
+            if (best < 0 || bound < bestd) { best = vid; bestd = bound; tie = false; }
             else if (bound == bestd) {
-                if (!kd) { if (flat < best) best = flat; }               // _compare_indexed_dists, :101-112
-                else if (topo) { if (ndp_tree_beats(g, mode, *topo, Q, flat, best)) best = flat; }
+                if (!kd) { if (vid < best) best = vid; }                 // _compare_indexed_dists, :101-112
+                else if (topo) { if (ndp_tree_beats(g, mode, *topo, Q, vid, best)) best = vid; }
                 else tie = true;
             }
             continue;
         }
         lev = cl;
-        for (int a = 0; a < nb; a++) bc[lev][a] = cb[a];
+        for (int j = 0; j < nv; j++) bc[lev][j] = cb[j];
         next[lev] = 0;
     }
     hit.vertex = best;
     hit.dsel = bestd;
     hit.status = tie ? NDP_SEARCH_TIE : NDP_SEARCH_OK;
+}
+
+// The search proper.  Axes along which the mask does not vary (a property of the
+// table, found at register time; typical of atmosphere-like tables whose voids
+// depend on two of many axes) are solved in closed form: the winner takes the
+// coordinate that minimises that axis' own term, provided that minimiser is strict
+// both per axis and in the final rounded sum -- otherwise (exact half-way queries,
+// absorbed differences) the full-lattice descent decides.  R is the pyramid over
+// the variant axes only, F the full one.
+NDP_HD void ndp_search_descend(const NdpGeom &g, const NdpPyramid &F, const NdpPyramid &R, int mode,
+                               const NdpQuery &Q, const NdpTopo *topo, NdpHit &hit)
+{
+    const int nb = g.nbasic;
+    if (R.nvar < nb && R.any_set) {
+        const bool cells = (mode == NDP_MODE_KD_LINEAR || mode == NDP_MODE_LS_LINEAR);
+        const int lo = cells ? 1 : 0;
+        int fixed[NDP_MAX_AXES];
+        bool is_var[NDP_MAX_AXES];
+        bool ok = true;
+        for (int a = 0; a < nb; a++) is_var[a] = false;
+        for (int j = 0; j < R.nvar; j++) is_var[R.var_axis[j]] = true;
+        for (int a = 0; a < nb && ok; a++) {
+            if (is_var[a]) { fixed[a] = 0; continue; }
+            const double hi = (double) (g.len[a] - 1);
+            double p = cells ? floor(Q.qc[a]) + 1.0 : rint(Q.qc[a]);
+            p = p < (double) lo ? (double) lo : (p > hi ? hi : p);
+            const int c = (int) p;
+            if (!(c >= lo && c <= g.len[a] - 1)) { ok = false; break; }
+            const double t0 = ndp_axis_term(mode, Q.qc[a], c, c);
+            if (c - 1 >= lo && !(ndp_axis_term(mode, Q.qc[a], c - 1, c - 1) > t0)) ok = false;
+            if (c + 1 <= g.len[a] - 1 && !(ndp_axis_term(mode, Q.qc[a], c + 1, c + 1) > t0)) ok = false;
+            fixed[a] = c;
+        }
+        if (ok) {
+            ndp_search_hard(g, R, mode, Q, fixed, topo, hit);
+            if (hit.status != NDP_SEARCH_EMPTY && hit.vertex >= 0) {
+                // the closed-form axes must also be strict minimisers of the rounded total
+                int c[NDP_MAX_AXES];
+                for (int a = 0; a < nb; a++) c[a] = (hit.vertex / g.bstride[a]) % g.len[a];
+                for (int a = 0; a < nb && ok; a++) {
+                    if (is_var[a]) continue;
+                    const int keep = c[a];
+                    for (int s = -1; s <= 1; s += 2) {
+                        const int t = keep + s;
+                        if (t < lo || t > g.len[a] - 1) continue;
+                        c[a] = t;
+                        const double d = ndp_metric_vertex(g, mode, Q, c);
+                        c[a] = keep;
+                        if (!(d > hit.dsel)) ok = false;
+                    }
+                }
+                if (ok) return;
+            }
+        }
+    }
+    ndp_search_hard(g, F, mode, Q, nullptr, topo, hit);
 }
 
 // The full scan scores masked-out vertices 1e10 (:283-286), so beyond 1e5 cells
@@ -472,7 +611,7 @@ NDP_HD void ndp_import_query(const NdpGeom &g, const double *ticks, const double
     const int n = N ? N : g.naxes;
 #pragma unroll
     for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
-        if (a < n) ndp_import_axis(ticks + g.tickoff[a], g.len[a], qrow[a], idx[a], flg[a], nrm[a]);
+        if (a < n) ndp_import_axis_guess(ticks + g.tickoff[a], g.len[a], g.inv_step[a], qrow[a], idx[a], flg[a], nrm[a]);
 }
 
 // Reduced value of component k of the cell whose superior corner is sup[] (:472-498

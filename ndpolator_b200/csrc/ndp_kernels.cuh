@@ -5,7 +5,8 @@
 //   k_main          import + gather + reduce, fused      (:354-414 + :416-508 + :78-99 + :547-554, :648-667)
 //                   -> interps/dists for points in a fully defined hypercube,
 //                      compacted list of the rest
-//   k_search        exact nearest on the lattice         (ndp_find_nearest, :188-352; kdtree.c:345-457)
+//   k_search_fast   exact nearest on the lattice, pass 1 (ndp_find_nearest, :188-352; kdtree.c:345-457)
+//   k_search_hard   pass 2: pyramid descent for what pass 1 could not prove; also the tie pass
 //   k_search_brute  warp-cooperative full scan           (:279-329)
 //   k_finish        nearest copy / linear extrapolation  (:556-635)
 //
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_import(const __grid_constant__ Im
     for (long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long) gridDim.x * blockDim.x) {
         const int a = (int) (e % n);
         int idx, flg; double nrm;
-        ndp_import_axis(tk + A.g.tickoff[a], A.g.len[a], A.q[e], idx, flg, nrm);
+        ndp_import_axis_guess(tk + A.g.tickoff[a], A.g.len[a], A.g.inv_step[a], A.q[e], idx, flg, nrm);
         A.indices[e] = idx; A.flags[e] = flg; A.normed[e] = nrm;
     }
 }
@@ -195,18 +196,20 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_main(const __gr
 // ---------------------------------------------------------------------------
 struct SearchArgs {
     NdpGeom g;
-    NdpPyramid P;
+    const NdpPyramid *F;    // occupancy pyramid over the whole basic lattice (device memory)
+    const NdpPyramid *R;    // pyramid over the mask-variant axes only
     NdpTopo topo; int have_topo;
     const double *ticks; int nticks; int ticks_in_smem;
     const double *q;
     int method, search;
     const int *list;        // query id per work item, or nullptr (work item t = query t)
-    const int *sublist;     // positions into list to (re)do, or nullptr
-    const int *count;       // device count of work items (of sublist when given), or nullptr
+    const int *sublist;     // k_search_hard: positions into list to do (hard list or tie list)
+    const int *count;       // device count of work items, or nullptr
     long long count_host;   // used when count == nullptr
     int *chosen;            // winning basic vertex per work item
     double *dists;          // per query id
     int *coords;            // optional (n x naxes) tap, per query id
+    int *hardlist;          // positions whose fast path failed
     int *tielist;           // positions whose kd tie could not be settled yet
     NdpCounters *ctr;
 };
@@ -231,36 +234,73 @@ __device__ __forceinline__ void ndp_publish(const SearchArgs &A, const NdpQuery 
     if (A.coords) for (int a = 0; a < g.naxes; a++) A.coords[i * g.naxes + a] = coords[a];
 }
 
-__global__ void __launch_bounds__(NDP_BLOCK) k_search(const __grid_constant__ SearchArgs A)
+// Pass 1: the rounded lattice point, proven optimal by its axis neighbours.  What it
+// cannot settle goes to the hard list so that pass 2 runs with full warps.
+__global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant__ SearchArgs A)
 {
     extern __shared__ double s_ticks[];
     const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
     const NdpGeom &g = A.g;
     const int n = g.naxes;
     const int mode = ndp_mode_of(A.method, A.search);
+    const unsigned lane = threadIdx.x & 31;
     const long long total = A.count ? (long long) *A.count : A.count_host;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    const long long rounds = (total + stride - 1) / stride;
+    for (long long r = 0; r < rounds; r++) {
+        const long long t = r * stride + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        bool hard = false;
+        if (t < total) {
+            const long long i = A.list ? A.list[t] : t;
+            int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES];
+            double nrm[NDP_MAX_AXES];
+            ndp_import_query<0>(g, tk, A.q + i * n, idx, flg, nrm);
+            NdpQuery Q;
+            ndp_make_query(g, idx, nrm, Q);
+            NdpHit hit;
+            if (ndp_search_fast(g, *A.F, mode, Q, hit)) {
+                ndp_scan_sentinel(*A.F, mode, hit);
+                ndp_publish(A, Q, t, i, hit);
+            } else hard = true;
+        }
+        const unsigned votes = __ballot_sync(0xffffffffu, hard);
+        if (votes) {
+            int base = 0;
+            const int leader = __ffs(votes) - 1;
+            if ((int) lane == leader) base = atomicAdd(&A.ctr->n_hard, __popc(votes));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (hard) A.hardlist[base + __popc(votes & ((1u << lane) - 1u))] = (int) t;
+        }
+    }
+}
+
+// Pass 2 (and the tie pass): pyramid descent with an explicit per-thread stack.
+__global__ void __launch_bounds__(NDP_BLOCK) k_search_hard(const __grid_constant__ SearchArgs A)
+{
+    extern __shared__ double s_ticks[];
+    const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
+    const NdpGeom &g = A.g;
+    const int n = g.naxes;
+    const int mode = ndp_mode_of(A.method, A.search);
+    const long long total = *A.count;
     for (long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long) gridDim.x * blockDim.x) {
-        const long long t = A.sublist ? A.sublist[s] : s;
+        const long long t = A.sublist[s];
         const long long i = A.list ? A.list[t] : t;
         int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES];
         double nrm[NDP_MAX_AXES];
         ndp_import_query<0>(g, tk, A.q + i * n, idx, flg, nrm);
         NdpQuery Q;
         ndp_make_query(g, idx, nrm, Q);
-
         NdpHit hit;
-        if (!ndp_search_fast(g, A.P, mode, Q, hit)) {
-            ndp_search_hard(g, A.P, mode, Q, A.have_topo ? &A.topo : nullptr, hit);
-            atomicAdd(&A.ctr->n_hard, 1);
-            if (hit.status == NDP_SEARCH_TIE) {
-                // provisional (valid) vertex so that k_finish stays in bounds; redone once the topology exists
-                A.chosen[t] = hit.vertex;
-                A.tielist[atomicAdd(&A.ctr->n_tie, 1)] = (int) t;
-                continue;
-            }
-            if (A.sublist) atomicAdd(&A.ctr->n_tie_resolved, 1);
+        ndp_search_descend(g, *A.F, *A.R, mode, Q, A.have_topo ? &A.topo : nullptr, hit);
+        if (hit.status == NDP_SEARCH_TIE) {
+            // provisional (valid) vertex so that k_finish stays in bounds; redone once the topology exists
+            A.chosen[t] = hit.vertex;
+            A.tielist[atomicAdd(&A.ctr->n_tie, 1)] = (int) t;
+            continue;
         }
-        ndp_scan_sentinel(A.P, mode, hit);
+        if (A.have_topo && A.sublist == A.tielist) atomicAdd(&A.ctr->n_tie_resolved, 1);
+        ndp_scan_sentinel(*A.F, mode, hit);
         ndp_publish(A, Q, t, i, hit);
     }
 }
@@ -290,7 +330,7 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_brute(const __grid_constan
         double bestd = 0.0;
         for (int v = (int) lane; v < g.nverts; v += 32) {
             double d;
-            if (!ndp_bit(A.P.bits[0], v)) d = 1e10;                     // :283-286
+            if (!ndp_bit(A.F->bits[0], v)) d = 1e10;                     // :283-286
             else {
                 int c[NDP_MAX_AXES];
                 for (int a = 0; a < g.nbasic; a++) c[a] = (v / g.bstride[a]) % g.len[a];

@@ -72,6 +72,50 @@ __global__ void k_pyr_level(const __grid_constant__ PyrLevelArgs A)
     if ((threadIdx.x & 31) == 0 && p < A.nparent) A.pbits[p >> 5] = word;
 }
 
+// Does the mask depend on axis a?  differs[a] is raised when some vertex disagrees with the
+// vertex that has the reference coordinate `ref` on axis a (0 for the vertex mask; 1 for the
+// hypercube mask, whose coordinate-0 entries are clear by construction and never searched).
+__global__ void k_mask_variance(const __grid_constant__ NdpGeom g, const uint32_t *__restrict__ bits, int ref, int *differs)
+{
+    const long long v = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= g.nverts) return;
+    const bool mine = ndp_bit(bits, (int) v);
+    for (int a = 0; a < g.nbasic; a++) {
+        const int c = ((int) v / g.bstride[a]) % g.len[a];
+        if (c < ref || c == ref) continue;
+        const int w = (int) v - (c - ref) * g.bstride[a];
+        if (ndp_bit(bits, w) != mine) differs[a] = 1;
+    }
+}
+
+struct SliceArgs {
+    NdpGeom g;
+    int nvar; int var_axis[NDP_MAX_AXES]; int dim[NDP_MAX_AXES];
+    int ref; int nslice;
+    const uint32_t *bits; uint32_t *out;
+};
+
+// level 0 of the reduced pyramid: the mask restricted to the slice where every invariant axis = ref
+__global__ void k_mask_slice(const __grid_constant__ SliceArgs A)
+{
+    const long long p = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    bool on = false;
+    if (p < A.nslice) {
+        int rem = (int) p, v = 0;
+        bool isvar[NDP_MAX_AXES];
+        for (int a = 0; a < A.g.nbasic; a++) isvar[a] = false;
+        for (int j = A.nvar - 1; j >= 0; j--) {
+            const int c = rem % A.dim[j]; rem /= A.dim[j];
+            v += c * A.g.bstride[A.var_axis[j]];
+            isvar[A.var_axis[j]] = true;
+        }
+        for (int a = 0; a < A.g.nbasic; a++) if (!isvar[a]) v += A.ref * A.g.bstride[a];
+        on = ndp_bit(A.bits, v);
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0 && p < A.nslice) A.out[p >> 5] = word;
+}
+
 // lowest vertex id whose bit is clear (for the 1e10 sentinel of the full scan); *out preset to INT_MAX
 __global__ void k_first_clear(const uint32_t *__restrict__ bits, int nverts, int *out)
 {

@@ -22,7 +22,7 @@ struct HsPyr { NdpPyramid dev; std::vector<std::vector<uint32_t>> levels; };
 struct HsTable {
     NdpGeom g;
     std::vector<double> ticks, grid, cells;
-    HsPyr pyr[2];
+    HsPyr pyr[2], red[2];
     std::vector<int> parent[2], depth[2];
     bool topo_built[2] = {false, false};
     long long n_hard = 0, n_tie = 0, n_off = 0;
@@ -30,30 +30,31 @@ struct HsTable {
 
 static void set_bit(std::vector<uint32_t> &b, long long i) { b[i >> 5] |= 1u << (i & 31); }
 
-static void build_pyr(HsTable *t, HsPyr &P, std::vector<uint32_t> level0)
+static void build_pyr(HsTable *t, HsPyr &P, std::vector<uint32_t> level0, int nvar, const int *var_axis, const int *dim0, bool full)
 {
     const NdpGeom &g = t->g;
     NdpPyramid &D = P.dev;
     int dim[NDP_MAX_AXES];
-    for (int a = 0; a < g.nbasic; a++) dim[a] = g.len[a];
+    D.nvar = nvar;
+    for (int j = 0; j < nvar; j++) { dim[j] = dim0[j]; D.var_axis[j] = var_axis[j]; }
     P.levels.clear();
     P.levels.push_back(std::move(level0));
     for (int lev = 0; lev < NDP_MAX_LEVELS; lev++) {
         long long nblocks = 1;
-        for (int a = g.nbasic - 1, s = 1; a >= 0; a--) { D.dim[lev][a] = dim[a]; D.stride[lev][a] = s; s *= dim[a]; nblocks *= dim[a]; }
+        for (int j = nvar - 1, s = 1; j >= 0; j--) { D.dim[lev][j] = dim[j]; D.stride[lev][j] = s; s *= dim[j]; nblocks *= dim[j]; }
         if (lev > 0) {
             std::vector<uint32_t> bits((nblocks + 31) / 32, 0u);
             const std::vector<uint32_t> &child = P.levels[lev - 1];
             for (long long p = 0; p < nblocks; p++) {
                 int pc[NDP_MAX_AXES]; long long rem = p;
-                for (int a = g.nbasic - 1; a >= 0; a--) { pc[a] = rem % dim[a]; rem /= dim[a]; }
+                for (int j = nvar - 1; j >= 0; j--) { pc[j] = rem % dim[j]; rem /= dim[j]; }
                 bool any = false;
-                for (int k = 0; k < (1 << g.nbasic) && !any; k++) {
+                for (int k = 0; k < (1 << nvar) && !any; k++) {
                     int flat = 0; bool inside = true;
-                    for (int a = 0; a < g.nbasic; a++) {
-                        int c = 2 * pc[a] + ((k >> a) & 1);
-                        if (c >= D.dim[lev - 1][a]) { inside = false; break; }
-                        flat += c * D.stride[lev - 1][a];
+                    for (int j = 0; j < nvar; j++) {
+                        int c = 2 * pc[j] + ((k >> j) & 1);
+                        if (c >= D.dim[lev - 1][j]) { inside = false; break; }
+                        flat += c * D.stride[lev - 1][j];
                     }
                     if (inside && ndp_bit(child.data(), flat)) any = true;
                 }
@@ -63,12 +64,40 @@ static void build_pyr(HsTable *t, HsPyr &P, std::vector<uint32_t> level0)
         }
         D.nlev = lev + 1;
         if (nblocks == 1) break;
-        for (int a = 0; a < g.nbasic; a++) dim[a] = (dim[a] + 1) / 2;
+        for (int j = 0; j < nvar; j++) dim[j] = (dim[j] + 1) / 2;
     }
     for (int l = 0; l < D.nlev; l++) D.bits[l] = P.levels[l].data();
     D.first_clear = -1;
-    for (int v = 0; v < g.nverts; v++) if (!ndp_bit(D.bits[0], v)) { D.first_clear = v; break; }
+    if (full) for (int v = 0; v < g.nverts; v++) if (!ndp_bit(D.bits[0], v)) { D.first_clear = v; break; }
     D.any_set = ndp_bit(D.bits[D.nlev - 1], 0) ? 1 : 0;
+}
+
+// mirrors k_mask_variance + k_mask_slice + build_reduced()
+static void build_red(HsTable *t, int m)
+{
+    const NdpGeom &g = t->g;
+    const uint32_t *bits = t->pyr[m].dev.bits[0];
+    const int ref = m;
+    int differs[NDP_MAX_AXES] = {0};
+    for (int v = 0; v < g.nverts; v++) {
+        const bool mine = ndp_bit(bits, v);
+        for (int a = 0; a < g.nbasic; a++) {
+            const int c = (v / g.bstride[a]) % g.len[a];
+            if (c <= ref) continue;
+            if (ndp_bit(bits, v - (c - ref) * g.bstride[a]) != mine) differs[a] = 1;
+        }
+    }
+    int nvar = 0, var_axis[NDP_MAX_AXES], dim[NDP_MAX_AXES];
+    long long nslice = 1;
+    for (int a = 0; a < g.nbasic; a++) if (differs[a]) { var_axis[nvar] = a; dim[nvar] = g.len[a]; nslice *= g.len[a]; nvar++; }
+    std::vector<uint32_t> level0((nslice + 31) / 32, 0u);
+    for (long long p = 0; p < nslice; p++) {
+        long long rem = p; int v = 0; bool isvar[NDP_MAX_AXES] = {false};
+        for (int j = nvar - 1; j >= 0; j--) { int c = rem % dim[j]; rem /= dim[j]; v += c * g.bstride[var_axis[j]]; isvar[var_axis[j]] = true; }
+        for (int a = 0; a < g.nbasic; a++) if (!isvar[a]) v += ref * g.bstride[a];
+        if (ndp_bit(bits, v)) set_bit(level0, p);
+    }
+    build_pyr(t, t->red[m], level0, nvar, var_axis, dim, false);
 }
 
 extern "C" void *hs_create(int naxes, int nbasic, const int *axlen, const double *ticks, int vdim, const double *grid, int with_cells)
@@ -86,6 +115,13 @@ extern "C" void *hs_create(int naxes, int nbasic, const int *axlen, const double
     for (int a = nbasic - 1; a >= 0; a--) g.bstride[a] = (a == nbasic - 1) ? 1 : g.bstride[a + 1] * g.len[a + 1];
     g.nverts = (int) nverts; g.ncells = ncells;
     t->ticks.assign(ticks, ticks + nt);
+    for (int a = 0; a < naxes; a++) {       // mirrors ndpb_table_create
+        const double *tk = ticks + g.tickoff[a];
+        bool ascending = true;
+        for (int i = 1; i < axlen[a]; i++) if (!(tk[i] > tk[i - 1])) ascending = false;
+        const double span = tk[axlen[a] - 1] - tk[0];
+        g.inv_step[a] = (ascending && span > 0 && span < 1e300) ? (double) (axlen[a] - 1) / span : 0.0;
+    }
     if (!grid) return t;
     t->grid.assign(grid, grid + nall * vdim);
     // masks: mirrors k_vmask_bits / k_hcmask_bits
@@ -103,8 +139,12 @@ extern "C" void *hs_create(int naxes, int nbasic, const int *axlen, const double
         }
         if (ok) set_bit(hb, v);
     }
-    build_pyr(t, t->pyr[0], vb);
-    build_pyr(t, t->pyr[1], hb);
+    int all_axes[NDP_MAX_AXES];
+    for (int a = 0; a < nbasic; a++) all_axes[a] = a;
+    build_pyr(t, t->pyr[0], vb, nbasic, all_axes, g.len, true);
+    build_pyr(t, t->pyr[1], hb, nbasic, all_axes, g.len, true);
+    build_red(t, 0);
+    build_red(t, 1);
     if (with_cells && naxes <= 6) {          // mirrors k_build_cells
         const int n = naxes, V = vdim;
         t->cells.resize((size_t) (ncells << n) * V);
@@ -181,7 +221,7 @@ extern "C" void hs_find(void *h, long long n, const double *q, int32_t *indices,
     const NdpGeom &g = t->g;
     for (long long e = 0; e < n * g.naxes; e++) {
         int a = (int) (e % g.naxes), idx, flg; double nrm;
-        ndp_import_axis(t->ticks.data() + g.tickoff[a], g.len[a], q[e], idx, flg, nrm);
+        ndp_import_axis_guess(t->ticks.data() + g.tickoff[a], g.len[a], g.inv_step[a], q[e], idx, flg, nrm);
         indices[e] = idx; flags[e] = flg; normed[e] = nrm;
     }
 }
@@ -197,12 +237,12 @@ static void search_one(HsTable *t, const double *qrow, int method, int search, i
     NdpHit hit;
     if (!ndp_search_fast(g, t->pyr[m].dev, mode, Q, hit)) {
         t->n_hard++;
-        ndp_search_hard(g, t->pyr[m].dev, mode, Q, nullptr, hit);
+        ndp_search_descend(g, t->pyr[m].dev, t->red[m].dev, mode, Q, nullptr, hit);
         if (hit.status == NDP_SEARCH_TIE) {
             t->n_tie++;
             build_topo(t, m);
             NdpTopo T{t->parent[m].data(), t->depth[m].data()};
-            ndp_search_hard(g, t->pyr[m].dev, mode, Q, &T, hit);
+            ndp_search_descend(g, t->pyr[m].dev, t->red[m].dev, mode, Q, &T, hit);
         }
     }
     ndp_scan_sentinel(t->pyr[m].dev, mode, hit);
@@ -273,5 +313,7 @@ extern "C" void hs_ndpolate(void *h, long long n, const double *q, int method, i
     if (variant == 1 && !t->cells.empty()) ndpolate_cm<true>(t, n, q, method, search, interps, dists, 0);
     else ndpolate_cm<false>(t, n, q, method, search, interps, dists, variant == 2);
 }
+
+extern "C" void hs_variant_axes(void *h, int *out) { HsTable *t = (HsTable *) h; out[0] = t->red[0].dev.nvar; out[1] = t->red[1].dev.nvar; }
 
 extern "C" void hs_stats(void *h, long long *out) { HsTable *t = (HsTable *) h; out[0] = t->n_off; out[1] = t->n_hard; out[2] = t->n_tie; }
