@@ -88,7 +88,7 @@ struct ndpb_table {
     std::mutex mu;
     int sm_count = 148;
     // options
-    int opt_gather = 0, opt_linear_search = 0;
+    int opt_gather = 0, opt_linear_search = 0, opt_staged = 0;
     long long opt_chunk = 1 << 22;
     // stats of the last call
     long long st_launches = 0, st_offgrid = 0, st_hard = 0, st_ties = 0, st_h2d = 0, st_d2h = 0;
@@ -309,7 +309,10 @@ extern "C" int ndpb_table_create(const double *const *axes, const int32_t *axlen
         for (int i = 1; i < axlen[a]; i++) if (!(tk[i] > tk[i - 1])) ascending = false;
         const double span = tk[axlen[a] - 1] - tk[0];
         g.inv_step[a] = (ascending && span > 0 && span < 1e300) ? (double) (axlen[a] - 1) / span : 0.0;
+        g.first[a] = tk[0]; g.last[a] = tk[axlen[a] - 1];
     }
+    g.small = (nall < (1LL << 31) - 64) ? 1 : 0;
+    for (int a = 0; a < naxes; a++) { g.vstride32[a] = g.small ? (int) g.vstride[a] : 0; g.cstride32[a] = g.small ? (int) g.cstride[a] : 0; }
     CUT(cudaMalloc(&t->ticks, sizeof(double) * nticks));
     CUT(cudaMemcpy(t->ticks, flat.data(), sizeof(double) * nticks, cudaMemcpyHostToDevice));
 
@@ -364,6 +367,11 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
         // caller's CUDA events bracket them; 0 restores the table's own stream
         CU(cudaStreamSynchronize(t->s_compute));
         t->s_compute = value ? (cudaStream_t) (uintptr_t) value : t->s_owned;
+        return NDPB_OK;
+    }
+    if (k == "staged") {
+        if (value < 0 || value > 1) return fail(NDPB_ERR_INVALID, "staged must be 0 (auto) or 1 (off)");
+        t->opt_staged = (int) value;
         return NDPB_OK;
     }
     if (k == "chunk") {
@@ -618,6 +626,51 @@ static int launch_finish(ndpb_table *t, const FinishArgs &A, cudaStream_t st)
     return A.cells ? launch_finish_n<true>(t, A, st) : launch_finish_n<false>(t, A, st);
 }
 
+// The bulk-copy staged gather serves scalar tables with a cell-major copy, 2..6 axes.
+static bool staged_ok(const ndpb_table *t)
+{
+    return t->opt_staged == 0 && t->cells && t->g.vdim == 1 && t->g.naxes >= 2 && t->g.naxes <= 6 &&
+           (size_t) t->nticks * sizeof(double) <= 16 * 1024;
+}
+
+static size_t staged_smem(const ndpb_table *t)
+{
+    const size_t ticks = ((size_t) t->nticks * 8 + 127) & ~(size_t) 127;
+    const size_t slot = ((size_t) 8 << t->g.naxes) + 16;
+    return ticks + 128 + (size_t) NDP_STAGED_WARPS * NDP_STAGED_STAGES * 32 * slot;
+}
+
+template <int N, int MODE>
+static int launch_staged_nm(ndpb_table *t, const StagedArgs &A, long long items, cudaStream_t st)
+{
+    const size_t smem = staged_smem(t);
+    static thread_local int configured_device = -1;
+    CU(cudaFuncSetAttribute(k_gather_staged<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    (void) configured_device;
+    int per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather_staged<N, MODE>, NDP_STAGED_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long tiles = (items + 31) / 32;
+    const long long want = (tiles + NDP_STAGED_WARPS - 1) / NDP_STAGED_WARPS;
+    const int blocks = (int) std::max<long long>(1, std::min<long long>(want, (long long) t->sm_count * per_sm));
+    k_gather_staged<N, MODE><<<blocks, NDP_STAGED_WARPS * 32, smem, st>>>(A);
+    CU(cudaGetLastError());
+    t->st_launches++;
+    return NDPB_OK;
+}
+
+template <int MODE>
+static int launch_staged(ndpb_table *t, const StagedArgs &A, long long items, cudaStream_t st)
+{
+    switch (t->g.naxes) {
+    case 2: return launch_staged_nm<2, MODE>(t, A, items, st);
+    case 3: return launch_staged_nm<3, MODE>(t, A, items, st);
+    case 4: return launch_staged_nm<4, MODE>(t, A, items, st);
+    case 5: return launch_staged_nm<5, MODE>(t, A, items, st);
+    default: return launch_staged_nm<6, MODE>(t, A, items, st);
+    }
+}
+
 static bool use_brute(const ndpb_table *t, int search)
 {
     if (search != NDPB_SEARCH_LINEAR) return false;
@@ -644,7 +697,16 @@ static int launch_search(ndpb_table *t, SearchArgs &A, long long upper, bool har
         k_search_brute<<<std::max(blocks, 1), NDP_BLOCK, smem, st>>>(A);
     } else {
         const int blocks = (int) std::min<long long>((upper + NDP_BLOCK - 1) / NDP_BLOCK, cap);
-        k_search_fast<<<std::max(blocks, 1), NDP_BLOCK, smem, st>>>(A);
+        const int nbk = std::max(blocks, 1);
+        switch (t->g.naxes) {
+        case 1: k_search_fast<1><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
+        case 2: k_search_fast<2><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
+        case 3: k_search_fast<3><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
+        case 4: k_search_fast<4><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
+        case 5: k_search_fast<5><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
+        case 6: k_search_fast<6><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
+        default: k_search_fast<0><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
+        }
     }
     CU(cudaGetLastError());
     t->st_launches++;
@@ -660,7 +722,13 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
     cudaStream_t st = t->s_compute;
     CU(cudaMemsetAsync(s.ctr, 0, sizeof(NdpCounters), st));
     CU(cudaEventRecord(s.t0, st));
-    if (task == TASK_NDPOLATE) {
+    StagedArgs G{};
+    G.g = t->g; G.ticks = t->ticks; G.nticks = t->nticks; G.cells = t->cells; G.q = q; G.n = n;
+    G.interps = interps; G.dists = dists; G.method = method; G.offlist = s.list; G.chosen = s.chosen; G.ctr = s.ctr;
+    if (task == TASK_NDPOLATE && staged_ok(t)) {
+        int rc = launch_staged<0>(t, G, n, st);
+        if (rc) return rc;
+    } else if (task == TASK_NDPOLATE) {
         MainArgs M{};
         M.g = t->g; M.ticks = t->ticks; M.nticks = t->nticks; M.ticks_in_smem = ticks_in_smem(t);
         M.grid = t->grid; M.cells = t->cells; M.q = q; M.n = n;
@@ -686,7 +754,10 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
         }
     }
     CU(cudaEventRecord(s.t2, st));
-    if (task == TASK_NDPOLATE && method != NDPB_METHOD_NONE) {
+    if (task == TASK_NDPOLATE && method == NDPB_METHOD_LINEAR && staged_ok(t)) {
+        int rc = launch_staged<1>(t, G, n, st);      // item count is read from the device counter; n bounds the grid
+        if (rc) return rc;
+    } else if (task == TASK_NDPOLATE && method != NDPB_METHOD_NONE) {
         FinishArgs F{};
         F.g = t->g; F.ticks = t->ticks; F.nticks = t->nticks; F.ticks_in_smem = ticks_in_smem(t);
         F.grid = t->grid; F.cells = t->cells; F.q = q; F.method = method;

@@ -55,6 +55,11 @@ struct NdpGeom {
     int nverts;                       // basic lattice size (ndp_types.c:174-176); < 2^31 like the reference's int
     long long ncells;
     double inv_step[NDP_MAX_AXES];    // (len-1)/(last-first): index guess for the import; 0 = always bisect
+    double first[NDP_MAX_AXES];       // tick[0] and tick[len-1] of every axis (constant-bank copies)
+    double last[NDP_MAX_AXES];
+    int vstride32[NDP_MAX_AXES];      // 32-bit copies of vstride / cstride, valid when small != 0
+    int cstride32[NDP_MAX_AXES];
+    int small;                        // every vertex and cell index fits in 31 bits
 };
 
 // Bit-packed occupancy pyramid over the basic lattice.  Level 0 = one bit per
@@ -106,30 +111,28 @@ NDP_HD void ndp_import_axis(const double *tick, int len, double x, int &index, i
 // (smallest l in [1, len-1] with tick[l] >= x + rtol, else len-1) and walk at most
 // two ticks; anything else falls back to the bisection itself.  inv_step == 0
 // (axis not ascending, or degenerate) always bisects.
-NDP_HD void ndp_import_axis_guess(const double *tick, int len, double inv_step, double x, int &index, int &flag, double &normed)
+NDP_HD void ndp_import_axis_guess(const double *tick, int len, double inv_step, double first, double last,
+                                  double x, int &index, int &flag, double &normed)
 {
     const double rtol = 1e-6;
     if (inv_step > 0.0) {
         const double xr = x + rtol;
-        double gd = floor((xr - tick[0]) * inv_step) + 1.0;
-        gd = gd < 1.0 ? 1.0 : (gd > (double) (len - 1) ? (double) (len - 1) : gd);
-        int l = (gd == gd) ? (int) gd : 1;
-        bool found = false;
-#pragma unroll
-        for (int step = 0; step < 3 && !found; step++) {
-            const double tl = tick[l], tp = tick[l - 1];
-            const bool up_ok = !(xr > tl) || l == len - 1;
-            const bool lo_ok = l == 1 || xr > tp;
-            if (up_ok && lo_ok) {
-                int f = (x < tick[0] || x > tick[len - 1]) ? NDP_F_OOB : 0;
-                double t = (x - tp) / (tl - tp);
-                if (fabs(t) < rtol || (l == len - 1 && fabs(t - 1) < rtol)) f |= NDP_F_ON_VERTEX;
-                index = l; flag = f; normed = t;
-                found = true;
-            } else if (!up_ok) l++;
-            else l--;
+        double gd = floor((xr - first) * inv_step) + 1.0;
+        gd = fmin(fmax(gd, 1.0), (double) (len - 1));          // a NaN guess becomes 1, like the bisection's answer
+        int l = (int) gd;
+        double tl = tick[l], tp = tick[l - 1];
+        // one corrective tick either way (the guess from the mean spacing is at most one off on near-uniform axes)
+        const bool up = (xr > tl) && (l < len - 1);
+        const bool dn = !up && !(xr > tp) && (l > 1);
+        if (up || dn) { l += up ? 1 : -1; tl = tick[l]; tp = tick[l - 1]; }
+        const bool ok = (!(xr > tl) || l == len - 1) && (l == 1 || xr > tp);
+        if (ok) {
+            int f = (x < first || x > last) ? NDP_F_OOB : 0;
+            const double t = (x - tp) / (tl - tp);
+            if (fabs(t) < rtol || (l == len - 1 && fabs(t - 1) < rtol)) f |= NDP_F_ON_VERTEX;
+            index = l; flag = f; normed = t;
+            return;
         }
-        if (found) return;
     }
     ndp_import_axis(tick, len, x, index, flag, normed);
 }
@@ -369,6 +372,9 @@ NDP_HD bool ndp_tree_beats(const NdpGeom &g, int mode, const NdpTopo &T, const N
 // Distances are the reference's own expressions, so the winner is bit-exact.
 // ---------------------------------------------------------------------------
 
+#ifndef NDP_RING_BUDGET
+#define NDP_RING_BUDGET 300    // lattice points the shell search may touch before the pyramid descent takes over
+#endif
 #define NDP_SEARCH_OK 0
 #define NDP_SEARCH_TIE 1      // kd mode tie met without topology: caller must redo with NdpTopo
 #define NDP_SEARCH_EMPTY 2    // mask has no set bit
@@ -380,33 +386,63 @@ struct NdpHit {
     int hard;        // 1 when step (2) ran
 };
 
+// N > 0: number of axes known at compile time (everything stays in registers).
+template <int N>
 NDP_HD bool ndp_search_fast(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q, NdpHit &hit)
 {
+    constexpr int M = N ? N : NDP_MAX_AXES;
+    const int nb = g.nbasic;
     const bool cells = (mode == NDP_MODE_KD_LINEAR || mode == NDP_MODE_LS_LINEAR);
-    int c[NDP_MAX_AXES];
+    const int lo = cells ? 1 : 0;
+    int c[M];
     int flat = 0;
-    for (int a = 0; a < g.nbasic; a++) {
-        const double lo = cells ? 1.0 : 0.0, hi = (double) (g.len[a] - 1);
-        double p = cells ? floor(Q.qc[a]) + 1.0 : rint(Q.qc[a]);
-        p = p < lo ? lo : (p > hi ? hi : p);     // NaN falls through; the neighbour test below then fails
-        c[a] = (int) p;
-        if (!(c[a] >= (int) lo && c[a] <= (int) hi)) return false;
-        flat += c[a] * g.bstride[a];
-    }
-    if (!ndp_bit(P.bits[0], flat)) return false;
-    const double d0 = ndp_metric_vertex(g, mode, Q, c);
-    if (!(d0 == d0)) return false;
-    for (int a = 0; a < g.nbasic; a++) {
-        const int keep = c[a];
-        for (int s = -1; s <= 1; s += 2) {
-            int t = keep + s;
-            if (t < (cells ? 1 : 0) || t > g.len[a] - 1) continue;
-            c[a] = t;
-            double d = ndp_metric_vertex(g, mode, Q, c);
-            c[a] = keep;
-            if (!(d > d0)) return false;
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < M; a++)
+        if (a < nb) {
+            const double hi = (double) (g.len[a] - 1);
+            double p = cells ? floor(Q.qc[a]) + 1.0 : rint(Q.qc[a]);
+            p = p < (double) lo ? (double) lo : (p > hi ? hi : p);     // NaN falls through and is rejected below
+            c[a] = (int) p;
+            ok &= (c[a] >= lo && c[a] <= g.len[a] - 1);
+            flat += c[a] * g.bstride[a];
         }
-    }
+    if (!ok) return false;
+    if (!ndp_bit(P.bits[0], flat)) return false;
+
+    // per-axis terms of the candidate and of its two axis neighbours, each computed once
+    double t0[M], tm[M], tp[M];
+    bool hm[M], hp[M];
+    double d0 = 0.0;
+#pragma unroll
+    for (int a = 0; a < M; a++)
+        if (a < nb) {
+            t0[a] = ndp_axis_term(mode, Q.qc[a], c[a], c[a]);
+            hm[a] = c[a] - 1 >= lo;
+            hp[a] = c[a] + 1 <= g.len[a] - 1;
+            tm[a] = hm[a] ? ndp_axis_term(mode, Q.qc[a], c[a] - 1, c[a] - 1) : 0.0;
+            tp[a] = hp[a] ? ndp_axis_term(mode, Q.qc[a], c[a] + 1, c[a] + 1) : 0.0;
+            d0 += t0[a];
+        }
+    d0 = ndp_add_assoc(g, mode, Q, d0);
+    if (!(d0 == d0)) return false;
+
+    // a neighbour's metric shares the candidate's ordered prefix sum up to its axis
+    double prefix = 0.0;
+#pragma unroll
+    for (int a = 0; a < M; a++)
+        if (a < nb) {
+            double sm = prefix + tm[a], sp = prefix + tp[a];
+#pragma unroll
+            for (int b = a + 1; b < M; b++)
+                if (b < nb) { sm += t0[b]; sp += t0[b]; }
+            sm = ndp_add_assoc(g, mode, Q, sm);
+            sp = ndp_add_assoc(g, mode, Q, sp);
+            if (hm[a] && !(sm > d0)) ok = false;
+            if (hp[a] && !(sp > d0)) ok = false;
+            prefix += t0[a];
+        }
+    if (!ok) return false;
     hit.vertex = flat; hit.dsel = d0; hit.status = NDP_SEARCH_OK; hit.hard = 0;
     return true;
 }
@@ -415,7 +451,7 @@ NDP_HD bool ndp_search_fast(const NdpGeom &g, const NdpPyramid &P, int mode, con
 // depend on the others), fixed[] holds the coordinate of every other axis and the
 // descent runs on that slice; the metric still sums all basic axes in order.
 NDP_HD void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
-                            const int *fixed, const NdpTopo *topo, NdpHit &hit)
+                            const int *fixed, const NdpTopo *topo, NdpHit &hit, bool seeded = false)
 {
     const int nb = g.nbasic, nv = P.nvar;
     const unsigned nchild = 1u << nv;
@@ -435,9 +471,10 @@ NDP_HD void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, con
     for (int a = 0; a < nb; a++)
         if (jof[a] < 0) { fterm[a] = ndp_axis_term(mode, Q.qc[a], fixed[a], fixed[a]); base += fixed[a] * g.bstride[a]; }
 
-    int best = -1;
-    double bestd = 0.0;
-    bool tie = false;
+    // a seed (from the ring search) is an upper bound that lets the descent prune from the first block on
+    int best = seeded ? hit.vertex : -1;
+    double bestd = seeded ? hit.dsel : 0.0;
+    bool tie = seeded && hit.status == NDP_SEARCH_TIE;
 
     hit.hard = 1;
     if (!P.any_set) { hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_EMPTY; return; }
@@ -497,7 +534,7 @@ NDP_HD void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, con
             int vid = base;
             for (int j = 0; j < nv; j++) vid += cb[j] * g.bstride[P.var_axis[j]];
             if (best < 0 || bound < bestd) { best = vid; bestd = bound; tie = false; }
-            else if (bound == bestd) {
+            else if (bound == bestd && vid != best) {
                 if (!kd) { if (vid < best) best = vid; }                 // _compare_indexed_dists, :101-112
                 else if (topo) { if (ndp_tree_beats(g, mode, *topo, Q, vid, best)) best = vid; }
                 else tie = true;
@@ -511,6 +548,117 @@ NDP_HD void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, con
     hit.vertex = best;
     hit.dsel = bestd;
     hit.status = tie ? NDP_SEARCH_TIE : NDP_SEARCH_OK;
+}
+
+// Expanding-shell search around the lattice point p0 the query rounds to, over the
+// axes pyramid P spans (level 0 of P is the mask itself).  Shell R holds the points
+// at Chebyshev distance R from p0.  After shell R, every unscanned point differs
+// from p0 by more than R on some axis, so by per-axis convexity its metric is at
+// least LB_R = min over (axis, side) of the ordered sum with that axis' term
+// evaluated R+1 ticks away and every other axis at its own minimum; the best point
+// so far is final once it is strictly below LB_R (a tie with LB_R keeps going).
+// Returns true when proven; otherwise leaves the best so far in `hit` as a seed
+// (hit.vertex < 0: nothing found yet) after about `budget` points.
+NDP_HD bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
+                            const int *fixed, const NdpTopo *topo, int budget, NdpHit &hit)
+{
+    const int nb = g.nbasic, nv = P.nvar;
+    const bool cells = (mode == NDP_MODE_KD_LINEAR || mode == NDP_MODE_LS_LINEAR);
+    const bool kd = mode < NDP_MODE_LS_NEAREST;
+    const int lo = cells ? 1 : 0;
+    int jof[NDP_MAX_AXES], p0[NDP_MAX_AXES];
+    double tmin[NDP_MAX_AXES];        // per basic axis: the smallest term any admissible coordinate can give
+    int base = 0;
+
+    hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_OK; hit.hard = 1;
+    for (int a = 0; a < nb; a++) jof[a] = -1;
+    for (int j = 0; j < nv; j++) jof[P.var_axis[j]] = j;
+    for (int a = 0; a < nb; a++) {
+        if (jof[a] < 0) { tmin[a] = ndp_axis_term(mode, Q.qc[a], fixed[a], fixed[a]); base += fixed[a] * g.bstride[a]; continue; }
+        const double hi = (double) (g.len[a] - 1);
+        double p = cells ? floor(Q.qc[a]) + 1.0 : rint(Q.qc[a]);
+        p = p < (double) lo ? (double) lo : (p > hi ? hi : p);
+        const int c = (int) p;
+        if (!(c >= lo && c <= g.len[a] - 1)) return false;
+        const double t0 = ndp_axis_term(mode, Q.qc[a], c, c);
+        // p0 must be the per-axis minimiser for the shell bound to hold
+        if (c - 1 >= lo && ndp_axis_term(mode, Q.qc[a], c - 1, c - 1) < t0) return false;
+        if (c + 1 <= g.len[a] - 1 && ndp_axis_term(mode, Q.qc[a], c + 1, c + 1) < t0) return false;
+        if (!(t0 == t0)) return false;
+        p0[jof[a]] = c; tmin[a] = t0;
+    }
+
+    int best = -1;
+    double bestd = 0.0;
+    bool tie = false;
+    int scanned = 0;
+    for (int R = 0;; R++) {
+        // --- scan shell R: odometer over [-R, R]^nv, keeping offsets with Chebyshev norm R
+        int off[NDP_MAX_AXES];
+        for (int j = 0; j < nv; j++) off[j] = -R;
+        for (;;) {
+            int cheb = 0, flat = 0, vid = base;
+            bool inside = true;
+            for (int j = 0; j < nv; j++) {
+                const int o = off[j] < 0 ? -off[j] : off[j];
+                if (o > cheb) cheb = o;
+                const int a = P.var_axis[j];
+                const int c = p0[j] + off[j];
+                if (c < lo || c > g.len[a] - 1) inside = false;
+                flat += c * P.stride[0][j];
+                vid += c * g.bstride[a];
+            }
+            if (cheb == R && inside) {
+                scanned++;
+                if (ndp_bit(P.bits[0], flat)) {
+                    double d = 0.0;
+                    for (int a = 0; a < nb; a++) {
+                        const int j = jof[a];
+                        d += (j < 0) ? tmin[a] : ndp_axis_term(mode, Q.qc[a], p0[j] + off[j], p0[j] + off[j]);
+                    }
+                    d = ndp_add_assoc(g, mode, Q, d);
+                    if (best < 0 || d < bestd) { best = vid; bestd = d; tie = false; }
+                    else if (d == bestd && vid != best) {
+                        if (!kd) { if (vid < best) best = vid; }
+                        else if (topo) { if (ndp_tree_beats(g, mode, *topo, Q, vid, best)) best = vid; }
+                        else tie = true;
+                    }
+                }
+            }
+            // next offset; interior points (norm < R) are skipped by jumping the last axis
+            int j = nv - 1;
+            if (nv > 0 && R > 0) {
+                // when all leading offsets are strictly inside, the last axis only takes -R and +R
+                bool lead_inside = true;
+                for (int jj = 0; jj < nv - 1; jj++) { const int o = off[jj] < 0 ? -off[jj] : off[jj]; if (o == R) lead_inside = false; }
+                if (lead_inside && off[j] == -R) { off[j] = R; continue; }
+            }
+            while (j >= 0) { if (++off[j] <= R) break; off[j] = -R; j--; }
+            if (j < 0) break;
+        }
+        // --- lower bound for everything beyond shell R
+        bool any_beyond = false;
+        double lb = 0.0;
+        for (int j = 0; j < nv; j++) {
+            const int a = P.var_axis[j];
+            for (int sgn = -1; sgn <= 1; sgn += 2) {
+                const int c = p0[j] + sgn * (R + 1);
+                if (c < lo || c > g.len[a] - 1) continue;
+                double d = 0.0;
+                for (int b = 0; b < nb; b++) d += (b == a) ? ndp_axis_term(mode, Q.qc[a], c, c) : tmin[b];
+                d = ndp_add_assoc(g, mode, Q, d);
+                if (!any_beyond || d < lb) lb = d;
+                any_beyond = true;
+            }
+        }
+        hit.vertex = best; hit.dsel = bestd; hit.status = tie ? NDP_SEARCH_TIE : NDP_SEARCH_OK;
+        if (!any_beyond) {                       // the whole slice has been scanned
+            if (best < 0) hit.status = NDP_SEARCH_EMPTY;
+            return true;
+        }
+        if (best >= 0 && bestd < lb) return true;
+        if (scanned >= budget) return false;
+    }
 }
 
 // The search proper.  Axes along which the mask does not vary (a property of the
@@ -545,7 +693,8 @@ NDP_HD void ndp_search_descend(const NdpGeom &g, const NdpPyramid &F, const NdpP
             fixed[a] = c;
         }
         if (ok) {
-            ndp_search_hard(g, R, mode, Q, fixed, topo, hit);
+            if (!ndp_search_ring(g, R, mode, Q, fixed, topo, NDP_RING_BUDGET, hit))
+                ndp_search_hard(g, R, mode, Q, fixed, topo, hit, hit.vertex >= 0);
             if (hit.status != NDP_SEARCH_EMPTY && hit.vertex >= 0) {
                 // the closed-form axes must also be strict minimisers of the rounded total
                 int c[NDP_MAX_AXES];
@@ -566,7 +715,9 @@ NDP_HD void ndp_search_descend(const NdpGeom &g, const NdpPyramid &F, const NdpP
             }
         }
     }
-    ndp_search_hard(g, F, mode, Q, nullptr, topo, hit);
+    if (!F.any_set) { hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_EMPTY; hit.hard = 1; return; }
+    if (!ndp_search_ring(g, F, mode, Q, nullptr, topo, NDP_RING_BUDGET, hit))
+        ndp_search_hard(g, F, mode, Q, nullptr, topo, hit, hit.vertex >= 0);
 }
 
 // The full scan scores masked-out vertices 1e10 (:283-286), so beyond 1e5 cells
@@ -611,7 +762,8 @@ NDP_HD void ndp_import_query(const NdpGeom &g, const double *ticks, const double
     const int n = N ? N : g.naxes;
 #pragma unroll
     for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
-        if (a < n) ndp_import_axis_guess(ticks + g.tickoff[a], g.len[a], g.inv_step[a], qrow[a], idx[a], flg[a], nrm[a]);
+        if (a < n) ndp_import_axis_guess(ticks + g.tickoff[a], g.len[a], g.inv_step[a], g.first[a], g.last[a],
+                                         qrow[a], idx[a], flg[a], nrm[a]);
 }
 
 // Reduced value of component k of the cell whose superior corner is sup[] (:472-498
@@ -628,8 +780,15 @@ NDP_HD double ndp_eval_cell(const NdpGeom &g, const double *__restrict__ grid, c
         constexpr int NN = N ? N : 1;
         if (CM) {
             long long cell = 0;
+            if (g.small) {
+                int c32 = 0;
 #pragma unroll
-            for (int a = 0; a < NN; a++) cell += (long long) (sup[a] - 1) * g.cstride[a];
+                for (int a = 0; a < NN; a++) c32 += (sup[a] - 1) * g.cstride32[a];
+                cell = c32;
+            } else {
+#pragma unroll
+                for (int a = 0; a < NN; a++) cell += (long long) (sup[a] - 1) * g.cstride[a];
+            }
             const double *base = cells + (cell << NN) * V + k;
             if (V1) {
                 const double2 *b2 = reinterpret_cast<const double2 *>(base);

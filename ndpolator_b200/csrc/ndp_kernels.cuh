@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_import(const __grid_constant__ Im
     for (long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long) gridDim.x * blockDim.x) {
         const int a = (int) (e % n);
         int idx, flg; double nrm;
-        ndp_import_axis_guess(tk + A.g.tickoff[a], A.g.len[a], A.g.inv_step[a], A.q[e], idx, flg, nrm);
+        ndp_import_axis_guess(tk + A.g.tickoff[a], A.g.len[a], A.g.inv_step[a], A.g.first[a], A.g.last[a], A.q[e], idx, flg, nrm);
         A.indices[e] = idx; A.flags[e] = flg; A.normed[e] = nrm;
     }
 }
@@ -236,12 +236,13 @@ __device__ __forceinline__ void ndp_publish(const SearchArgs &A, const NdpQuery 
 
 // Pass 1: the rounded lattice point, proven optimal by its axis neighbours.  What it
 // cannot settle goes to the hard list so that pass 2 runs with full warps.
+template <int N>
 __global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant__ SearchArgs A)
 {
     extern __shared__ double s_ticks[];
     const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
     const NdpGeom &g = A.g;
-    const int n = g.naxes;
+    const int n = N ? N : g.naxes;
     const int mode = ndp_mode_of(A.method, A.search);
     const unsigned lane = threadIdx.x & 31;
     const long long total = A.count ? (long long) *A.count : A.count_host;
@@ -252,13 +253,13 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant
         bool hard = false;
         if (t < total) {
             const long long i = A.list ? A.list[t] : t;
-            int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES];
-            double nrm[NDP_MAX_AXES];
-            ndp_import_query<0>(g, tk, A.q + i * n, idx, flg, nrm);
+            int idx[N ? N : NDP_MAX_AXES], flg[N ? N : NDP_MAX_AXES];
+            double nrm[N ? N : NDP_MAX_AXES];
+            ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
             NdpQuery Q;
             ndp_make_query(g, idx, nrm, Q);
             NdpHit hit;
-            if (ndp_search_fast(g, *A.F, mode, Q, hit)) {
+            if (ndp_search_fast<N>(g, *A.F, mode, Q, hit)) {
                 ndp_scan_sentinel(*A.F, mode, hit);
                 ndp_publish(A, Q, t, i, hit);
             } else hard = true;
@@ -388,5 +389,199 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __
             coords[a] = ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
         for (int k = 0; k < V; k++)
             A.interps[i * V + k] = ndp_finish_component<N, CM, false>(g, A.grid, A.cells, A.method, idx, nrm, coords, k);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Staged gather (scalar tables, cell-major layout): k_gather_staged
+//
+// The cell of a query is one contiguous (8 << N)-byte block, so instead of
+// holding 2^N load destinations in registers while DRAM answers, every lane hands
+// its block to the bulk-copy engine (cp.async.bulk -> shared memory, completion
+// counted on an mbarrier) and goes on to import the NEXT tile's queries; the
+// reduction of a tile runs one iteration later out of shared memory.  Each warp
+// owns a private two-stage ring (its own slots and mbarriers), so there is no
+// block-wide synchronisation in the loop and memory-level parallelism no longer
+// depends on occupancy.  Slots are padded by 16 bytes so that the 128-bit
+// shared loads of a quarter-warp fall into distinct bank groups.
+//
+// MODE 0: the k_main work (import + classify + gather + reduce + off-grid list)
+// MODE 1: the k_finish work for LINEAR extrapolation (cell below the found corner)
+// ---------------------------------------------------------------------------
+#define NDP_STAGED_WARPS 4
+#define NDP_STAGED_STAGES 2
+
+__device__ __forceinline__ unsigned ndp_smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ndp_mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ndp_mbar_arrive(unsigned bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ndp_mbar_arrive_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ndp_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ndp_mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+struct StagedArgs {
+    NdpGeom g;
+    const double *ticks; int nticks;
+    const double *cells;
+    const double *q; long long n;      // MODE 0: number of queries; MODE 1: unused
+    double *interps; double *dists;
+    int method;
+    int *offlist;                      // MODE 0: out; MODE 1: in (query id per work item)
+    const int *chosen;                 // MODE 1: winning vertex per work item
+    NdpCounters *ctr;
+};
+
+template <int N>
+struct NdpStagedItem {                 // what a lane keeps between issuing a tile and reducing it
+    long long i;                       // query id (-1: lane idle)
+    double x[N];                       // interpolation weights
+    unsigned pinmask, selbits;
+    bool issued;                       // a bulk copy is in flight for this lane
+};
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gather_staged(const __grid_constant__ StagedArgs A)
+{
+    constexpr unsigned CELL_BYTES = 8u << N;
+    constexpr unsigned SLOT = CELL_BYTES + 16u;
+    extern __shared__ __align__(128) unsigned char ndp_smem[];
+    const NdpGeom &g = A.g;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // shared layout: ticks | mbarriers | slots
+    double *s_ticks = reinterpret_cast<double *>(ndp_smem);
+    const unsigned ticks_bytes = ((unsigned) A.nticks * 8u + 127u) & ~127u;
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(ndp_smem + ticks_bytes);
+    unsigned char *s_slots = ndp_smem + ticks_bytes + 128u;
+
+    for (int i = threadIdx.x; i < A.nticks; i += blockDim.x) s_ticks[i] = A.ticks[i];
+    if (lane == 0)
+        for (int st = 0; st < NDP_STAGED_STAGES; st++) ndp_mbar_init(ndp_smem_u32(&s_bar[warp * NDP_STAGED_STAGES + st]), 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    unsigned bar[NDP_STAGED_STAGES], slot[NDP_STAGED_STAGES];
+    const unsigned char *slot_ptr[NDP_STAGED_STAGES];
+#pragma unroll
+    for (int st = 0; st < NDP_STAGED_STAGES; st++) {
+        bar[st] = ndp_smem_u32(&s_bar[warp * NDP_STAGED_STAGES + st]);
+        slot_ptr[st] = s_slots + ((size_t) (warp * NDP_STAGED_STAGES + st) * 32 + lane) * SLOT;
+        slot[st] = ndp_smem_u32(slot_ptr[st]);
+    }
+
+    const long long total = (MODE == 0) ? A.n : (long long) A.ctr->n_off;
+    const long long ntiles = (total + 31) / 32;
+    const long long tile_stride = (long long) gridDim.x * NDP_STAGED_WARPS;
+    const long long tile0 = (long long) blockIdx.x * NDP_STAGED_WARPS + warp;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    // issue: import the lane's query of `tile`, start its bulk copy into stage st
+    auto produce = [&](long long tile, int st, NdpStagedItem<N> &it) {
+        const long long w = tile * 32 + lane;
+        it.i = -1; it.issued = false; it.pinmask = 0; it.selbits = 0;
+        long long cell = 0;
+        if (w < total) {
+            const long long i = (MODE == 0) ? w : (long long) A.offlist[w];
+            it.i = i;
+            int idx[N], flg[N];
+            double nrm[N];
+            ndp_import_query<N>(g, s_ticks, A.q + i * N, idx, flg, nrm);
+            if (MODE == 0) {
+                const bool oob = ndp_classify<N>(g, flg, nrm, it.pinmask, it.selbits);
+                it.issued = !oob;
+#pragma unroll
+                for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; cell += (long long) (idx[a] - 1) * g.cstride[a]; }
+            } else {
+                const int vertex = A.chosen[w];
+                it.issued = true;
+#pragma unroll
+                for (int a = 0; a < N; a++) {
+                    const int c = (a < g.nbasic) ? (vertex / g.bstride[a]) % g.len[a]
+                                                 : ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
+                    const int sup = c > 1 ? c : 1;                      // :601
+                    it.x[a] = nrm[a] + (double) (idx[a] - c);           // :621-622
+                    cell += (long long) (sup - 1) * g.cstride[a];
+                }
+            }
+        }
+        if (it.issued) {
+            ndp_mbar_arrive_expect_tx(bar[st], CELL_BYTES);
+            ndp_bulk_g2s(slot[st], A.cells + (cell << N), CELL_BYTES, bar[st]);
+        } else {
+            ndp_mbar_arrive(bar[st]);
+        }
+    };
+
+    // reduce: wait for the tile's copies, interpolate out of shared memory, write results
+    auto consume = [&](int st, unsigned parity, const NdpStagedItem<N> &it) {
+        ndp_mbar_wait(bar[st], parity);
+        bool need_search = false;
+        if (it.i >= 0) {
+            bool fdhc = false;
+            if (it.issued) {
+                const double2 *b2 = reinterpret_cast<const double2 *>(slot_ptr[st]);
+                bool bad = false;
+                const double val = ndp_cell_reduce<N>([&](double *fv) {
+#pragma unroll
+                    for (int j = 0; j < (1 << N) / 2; j++) { double2 p = b2[j]; fv[2 * j] = p.x; fv[2 * j + 1] = p.y; }
+                }, it.x, it.pinmask, it.selbits, bad);
+                fdhc = !bad;
+                if (MODE == 1 || fdhc) A.interps[it.i] = val;
+            }
+            if (MODE == 0) {
+                if (fdhc) A.dists[it.i] = 0.0;
+                else if (A.method == NDP_M_NONE) { A.interps[it.i] = qnan; A.dists[it.i] = 0.0; }
+                else need_search = true;
+            }
+        }
+        if (MODE == 0) {
+            const unsigned votes = __ballot_sync(0xffffffffu, need_search);
+            if (votes) {
+                int base = 0;
+                const int leader = __ffs(votes) - 1;
+                if ((int) lane == leader) base = atomicAdd(&A.ctr->n_off, __popc(votes));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (need_search) A.offlist[base + __popc(votes & ((1u << lane) - 1u))] = (int) it.i;
+            }
+        }
+    };
+
+    // N == 1 has an 8-byte cell, below the 16-byte granule of the bulk copy: not launched for N == 1
+    NdpStagedItem<N> item[NDP_STAGED_STAGES];
+    unsigned parity[NDP_STAGED_STAGES] = {0, 0};
+    if (tile0 < ntiles) produce(tile0, 0, item[0]);
+    int st = 0;
+    for (long long tile = tile0; tile < ntiles; tile += tile_stride) {
+        const long long next = tile + tile_stride;
+        if (st == 0) {
+            if (next < ntiles) produce(next, 1, item[1]);
+            consume(0, parity[0], item[0]);
+            parity[0] ^= 1u;
+        } else {
+            if (next < ntiles) produce(next, 0, item[0]);
+            consume(1, parity[1], item[1]);
+            parity[1] ^= 1u;
+        }
+        st ^= 1;
     }
 }

@@ -121,7 +121,10 @@ extern "C" void *hs_create(int naxes, int nbasic, const int *axlen, const double
         for (int i = 1; i < axlen[a]; i++) if (!(tk[i] > tk[i - 1])) ascending = false;
         const double span = tk[axlen[a] - 1] - tk[0];
         g.inv_step[a] = (ascending && span > 0 && span < 1e300) ? (double) (axlen[a] - 1) / span : 0.0;
+        g.first[a] = tk[0]; g.last[a] = tk[axlen[a] - 1];
     }
+    g.small = (nall < (1LL << 31) - 64) ? 1 : 0;
+    for (int a = 0; a < naxes; a++) { g.vstride32[a] = g.small ? (int) g.vstride[a] : 0; g.cstride32[a] = g.small ? (int) g.cstride[a] : 0; }
     if (!grid) return t;
     t->grid.assign(grid, grid + nall * vdim);
     // masks: mirrors k_vmask_bits / k_hcmask_bits
@@ -221,13 +224,14 @@ extern "C" void hs_find(void *h, long long n, const double *q, int32_t *indices,
     const NdpGeom &g = t->g;
     for (long long e = 0; e < n * g.naxes; e++) {
         int a = (int) (e % g.naxes), idx, flg; double nrm;
-        ndp_import_axis_guess(t->ticks.data() + g.tickoff[a], g.len[a], g.inv_step[a], q[e], idx, flg, nrm);
+        ndp_import_axis_guess(t->ticks.data() + g.tickoff[a], g.len[a], g.inv_step[a], g.first[a], g.last[a], q[e], idx, flg, nrm);
         indices[e] = idx; flags[e] = flg; normed[e] = nrm;
     }
 }
 
 // mirrors k_search + ndp_publish, with the deferred tie pass folded in
-static void search_one(HsTable *t, const double *qrow, int method, int search, int *vertex, double *dist, int *coords)
+template <int N>
+static void search_one_n(HsTable *t, const double *qrow, int method, int search, int *vertex, double *dist, int *coords)
 {
     const NdpGeom &g = t->g;
     const int mode = ndp_mode_of(method, search), m = method == NDP_M_LINEAR ? 1 : 0;
@@ -235,7 +239,7 @@ static void search_one(HsTable *t, const double *qrow, int method, int search, i
     ndp_import_query<0>(g, t->ticks.data(), qrow, idx, flg, nrm);
     NdpQuery Q; ndp_make_query(g, idx, nrm, Q);
     NdpHit hit;
-    if (!ndp_search_fast(g, t->pyr[m].dev, mode, Q, hit)) {
+    if (!ndp_search_fast<N>(g, t->pyr[m].dev, mode, Q, hit)) {
         t->n_hard++;
         ndp_search_descend(g, t->pyr[m].dev, t->red[m].dev, mode, Q, nullptr, hit);
         if (hit.status == NDP_SEARCH_TIE) {
@@ -249,6 +253,19 @@ static void search_one(HsTable *t, const double *qrow, int method, int search, i
     if (hit.status == NDP_SEARCH_EMPTY) { hit.vertex = 0; hit.dsel = 1e10; ndp_coords_of(g, Q, 0, coords); *dist = 1e10; }
     else { ndp_coords_of(g, Q, hit.vertex, coords); *dist = (mode >= NDP_MODE_LS_NEAREST) ? hit.dsel : ndp_reported_dist(g, method, Q, coords); }
     *vertex = hit.vertex;
+}
+
+static void search_one(HsTable *t, const double *qrow, int method, int search, int *vertex, double *dist, int *coords)
+{
+    switch (t->g.naxes) {      // mirrors the dispatch of k_search_fast<N>
+    case 1: search_one_n<1>(t, qrow, method, search, vertex, dist, coords); break;
+    case 2: search_one_n<2>(t, qrow, method, search, vertex, dist, coords); break;
+    case 3: search_one_n<3>(t, qrow, method, search, vertex, dist, coords); break;
+    case 4: search_one_n<4>(t, qrow, method, search, vertex, dist, coords); break;
+    case 5: search_one_n<5>(t, qrow, method, search, vertex, dist, coords); break;
+    case 6: search_one_n<6>(t, qrow, method, search, vertex, dist, coords); break;
+    default: search_one_n<0>(t, qrow, method, search, vertex, dist, coords);
+    }
 }
 
 extern "C" void hs_find_nearest(void *h, long long n, const double *q, int method, int search, int32_t *coords, double *dist)

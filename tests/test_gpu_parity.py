@@ -32,10 +32,11 @@ def test_extension_is_loaded_and_gpu_present():
 
 
 @pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[4:-4] for p in GOLDEN])
-@pytest.mark.parametrize('gather', [1, 2], ids=['strided', 'cellmajor'])
-def test_cuda_matches_reference_golden(path, gather):
+@pytest.mark.parametrize('variant', [(1, 0), (2, 0), (2, 1)], ids=['strided', 'cellmajor-staged', 'cellmajor-direct'])
+def test_cuda_matches_reference_golden(path, variant):
+    gather, staged_off = variant
     z, axes, nbasic = load_golden(path)
-    T = _table(axes, z['grid'], nbasic, gather=gather)
+    T = _table(axes, z['grid'], nbasic, gather=gather, staged=staged_off)
     check_engine_against_golden(
         z, T.find, lambda idx, flg, nrm: T.hypercubes_raw(nrm, idx, flg), T.ndpolate,
         lambda q, idx, flg, nrm, m, s: T.find_nearest(q, m, s), T.distance, T.masks)
