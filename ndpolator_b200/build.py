@@ -11,14 +11,15 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libndpb200.so')
-SOURCES = ['ndp_api.cu']
-HEADERS = ['ndp_core.cuh', 'ndp_kernels.cuh', 'ndp_table.cuh', os.path.join('..', '..', 'include', 'ndpb200.h')]
+SOURCES = ['ndp_api.cu', 'ndp_tu_main_strided.cu', 'ndp_tu_main_cellmajor.cu', 'ndp_tu_finish.cu',
+           'ndp_tu_search.cu', 'ndp_tu_staged.cu']
+HEADERS = ['ndp_core.cuh', 'ndp_kernels.cuh', 'ndp_table.cuh', 'ndp_launch.h', os.path.join('..', '..', 'include', 'ndpb200.h')]
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-lineinfo', '-O3', '-std=c++17', '--extended-lambda',
     '-fmad=false',
-    '-Xcompiler', '-fPIC', '-shared',
+    '-Xcompiler', '-fPIC',
 ]
 
 
@@ -38,15 +39,33 @@ def stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compiles csrc/*.cu into ndpolator_b200/libndpb200.so if missing or out of date."""
+    """Compiles csrc/*.cu (one object per kernel family, in parallel) and links
+    ndpolator_b200/libndpb200.so, if missing or out of date."""
     if not force and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, 'build')
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + '.o')
+        cmd = [nvcc] + NVCC_FLAGS + ['-c', '-o', obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(' '.join(cmd))
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n' + res.stdout + res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs
     if verbose:
         print(' '.join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+        raise RuntimeError('link failed:\n' + res.stdout + res.stderr)
     return LIB
 
 

@@ -16,7 +16,7 @@
 
 #include "../../include/ndpb200.h"
 #include "ndp_core.cuh"
-#include "ndp_kernels.cuh"
+#include "ndp_launch.h"
 #include "ndp_table.cuh"
 
 static_assert(NDPB_MAX_AXES == NDP_MAX_AXES, "header and core disagree on the axis limit");
@@ -51,6 +51,7 @@ struct Pyramid {
     NdpPyramid dev{};                       // host copy of the descriptor (device pointers inside)
     NdpPyramid *d_desc = nullptr;           // the same descriptor in device memory (kernels read it there)
     std::vector<uint32_t *> owned;
+    short *prevv = nullptr, *nextv = nullptr;
     int count = 0;                          // set bits at level 0
 };
 
@@ -163,6 +164,18 @@ static int build_pyramid(ndpb_table *t, Pyramid &P, uint32_t *level0, int nvar, 
     CU(cudaStreamSynchronize(t->s_compute));
     D.first_clear = (first == INT_MAX) ? -1 : first;
     D.any_set = (top & 1u) ? 1 : 0;
+    D.prevv = D.nextv = nullptr;
+    if (nvar >= 1 && dim0[nvar - 1] <= 32767) {       // row tables along the last pyramid axis
+        long long npts = 1;
+        for (int j = 0; j < nvar; j++) npts *= dim0[j];
+        const long long nrows = npts / dim0[nvar - 1];
+        CU(cudaMalloc(&P.prevv, sizeof(short) * npts));
+        CU(cudaMalloc(&P.nextv, sizeof(short) * npts));
+        k_row_tables<<<blocks_for(nrows), NDP_BLOCK, 0, t->s_compute>>>(level0, nrows, dim0[nvar - 1], P.prevv, P.nextv);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(t->s_compute));
+        D.prevv = P.prevv; D.nextv = P.nextv;
+    }
     CU(cudaMalloc(&P.d_desc, sizeof(NdpPyramid)));
     CU(cudaMemcpy(P.d_desc, &D, sizeof(NdpPyramid), cudaMemcpyHostToDevice));
     return NDPB_OK;
@@ -215,6 +228,7 @@ extern "C" int ndpb_table_destroy(ndpb_table *t)
     for (Pyramid *set : {t->pyr, t->red})
         for (int m = 0; m < 2; m++) {
             for (auto p : set[m].owned) cudaFree(p);
+            cudaFree(set[m].prevv); cudaFree(set[m].nextv);
             cudaFree(set[m].d_desc);
         }
     for (auto &T : t->topo) { cudaFree(T.parent); cudaFree(T.depth); }
@@ -561,36 +575,6 @@ static int ensure_slot(ndpb_table *t, Slot &s, long long nq, bool stage_q, bool 
     return NDPB_OK;
 }
 
-template <int N, bool CM>
-static int launch_main_g(ndpb_table *t, const MainArgs &A, int G, int blocks, size_t smem, cudaStream_t st)
-{
-    switch (G) {
-    case 1: k_main<N, 1, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 2: k_main<N, 2, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 4: k_main<N, 4, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 8: k_main<N, 8, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 16: k_main<N, 16, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    default: k_main<N, 32, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    }
-    CU(cudaGetLastError());
-    t->st_launches++;
-    return NDPB_OK;
-}
-
-template <bool CM>
-static int launch_main_n(ndpb_table *t, const MainArgs &A, int G, int blocks, size_t smem, cudaStream_t st)
-{
-    switch (t->g.naxes) {
-    case 1: return launch_main_g<1, CM>(t, A, G, blocks, smem, st);
-    case 2: return launch_main_g<2, CM>(t, A, G, blocks, smem, st);
-    case 3: return launch_main_g<3, CM>(t, A, G, blocks, smem, st);
-    case 4: return launch_main_g<4, CM>(t, A, G, blocks, smem, st);
-    case 5: return launch_main_g<5, CM>(t, A, G, blocks, smem, st);
-    case 6: return launch_main_g<6, CM>(t, A, G, blocks, smem, st);
-    default: return launch_main_g<0, false>(t, A, G, blocks, smem, st);
-    }
-}
-
 static int launch_main(ndpb_table *t, const MainArgs &A, cudaStream_t st)
 {
     const NdpGeom &g = t->g;
@@ -599,31 +583,17 @@ static int launch_main(ndpb_table *t, const MainArgs &A, cudaStream_t st)
     const long long groups_per_block = NDP_BLOCK / G;
     const int blocks = (int) std::min<long long>((A.n + groups_per_block - 1) / groups_per_block, (long long) t->sm_count * 8);
     const size_t smem = smem_bytes(t);
-    return A.cells ? launch_main_n<true>(t, A, G, blocks, smem, st) : launch_main_n<false>(t, A, G, blocks, smem, st);
-}
-
-template <bool CM>
-static int launch_finish_n(ndpb_table *t, const FinishArgs &A, cudaStream_t st)
-{
-    const int blocks = t->sm_count * 8;
-    const size_t smem = smem_bytes(t);
-    switch (t->g.naxes) {
-    case 1: k_finish<1, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 2: k_finish<2, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 3: k_finish<3, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 4: k_finish<4, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 5: k_finish<5, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 6: k_finish<6, CM><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    default: k_finish<0, false><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    }
-    CU(cudaGetLastError());
+    if (A.cells && g.naxes <= 6) CU(ndp_launch_main_cellmajor(A, g.naxes, G, blocks, smem, st));
+    else CU(ndp_launch_main_strided(A, g.naxes, G, blocks, smem, st));
     t->st_launches++;
     return NDPB_OK;
 }
 
 static int launch_finish(ndpb_table *t, const FinishArgs &A, cudaStream_t st)
 {
-    return A.cells ? launch_finish_n<true>(t, A, st) : launch_finish_n<false>(t, A, st);
+    CU(ndp_launch_finish(A, t->g.naxes, A.cells != nullptr, t->sm_count * 8, smem_bytes(t), st));
+    t->st_launches++;
+    return NDPB_OK;
 }
 
 // The bulk-copy staged gather serves scalar tables with a cell-major copy, 2..6 axes.
@@ -640,35 +610,12 @@ static size_t staged_smem(const ndpb_table *t)
     return ticks + 128 + (size_t) NDP_STAGED_WARPS * NDP_STAGED_STAGES * 32 * slot;
 }
 
-template <int N, int MODE>
-static int launch_staged_nm(ndpb_table *t, const StagedArgs &A, long long items, cudaStream_t st)
-{
-    const size_t smem = staged_smem(t);
-    static thread_local int configured_device = -1;
-    CU(cudaFuncSetAttribute(k_gather_staged<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    (void) configured_device;
-    int per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather_staged<N, MODE>, NDP_STAGED_WARPS * 32, smem));
-    if (per_sm < 1) per_sm = 1;
-    const long long tiles = (items + 31) / 32;
-    const long long want = (tiles + NDP_STAGED_WARPS - 1) / NDP_STAGED_WARPS;
-    const int blocks = (int) std::max<long long>(1, std::min<long long>(want, (long long) t->sm_count * per_sm));
-    k_gather_staged<N, MODE><<<blocks, NDP_STAGED_WARPS * 32, smem, st>>>(A);
-    CU(cudaGetLastError());
-    t->st_launches++;
-    return NDPB_OK;
-}
-
 template <int MODE>
 static int launch_staged(ndpb_table *t, const StagedArgs &A, long long items, cudaStream_t st)
 {
-    switch (t->g.naxes) {
-    case 2: return launch_staged_nm<2, MODE>(t, A, items, st);
-    case 3: return launch_staged_nm<3, MODE>(t, A, items, st);
-    case 4: return launch_staged_nm<4, MODE>(t, A, items, st);
-    case 5: return launch_staged_nm<5, MODE>(t, A, items, st);
-    default: return launch_staged_nm<6, MODE>(t, A, items, st);
-    }
+    CU(ndp_launch_staged(A, t->g.naxes, MODE, t->sm_count, items, staged_smem(t), st));
+    t->st_launches++;
+    return NDPB_OK;
 }
 
 static bool use_brute(const ndpb_table *t, int search)
@@ -691,22 +638,13 @@ static int launch_search(ndpb_table *t, SearchArgs &A, long long upper, bool har
     const long long cap = (long long) t->sm_count * 8;
     if (hard) {
         const int blocks = (int) std::min<long long>((upper + NDP_BLOCK - 1) / NDP_BLOCK, cap);
-        k_search_hard<<<std::max(blocks, 1), NDP_BLOCK, smem, st>>>(A);
+        CU(ndp_launch_search_hard(A, std::max(blocks, 1), smem, st));
     } else if (use_brute(t, A.search)) {
         const int blocks = (int) std::min<long long>((upper * 32 + NDP_BLOCK - 1) / NDP_BLOCK, cap);
-        k_search_brute<<<std::max(blocks, 1), NDP_BLOCK, smem, st>>>(A);
+        CU(ndp_launch_search_brute(A, std::max(blocks, 1), smem, st));
     } else {
         const int blocks = (int) std::min<long long>((upper + NDP_BLOCK - 1) / NDP_BLOCK, cap);
-        const int nbk = std::max(blocks, 1);
-        switch (t->g.naxes) {
-        case 1: k_search_fast<1><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
-        case 2: k_search_fast<2><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
-        case 3: k_search_fast<3><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
-        case 4: k_search_fast<4><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
-        case 5: k_search_fast<5><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
-        case 6: k_search_fast<6><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
-        default: k_search_fast<0><<<nbk, NDP_BLOCK, smem, st>>>(A); break;
-        }
+        CU(ndp_launch_search_fast(A, t->g.naxes, std::max(blocks, 1), smem, st));
     }
     CU(cudaGetLastError());
     t->st_launches++;
@@ -973,8 +911,7 @@ extern "C" int ndpb_find(ndpb_table *t, const double *query_pts, int64_t n,
     A.g = t->g; A.ticks = t->ticks; A.nticks = t->nticks; A.ticks_in_smem = ticks_in_smem(t);
     A.q = q.dev; A.n = n; A.indices = idx.dev; A.flags = flg.dev; A.normed = nrm.dev;
     const int blocks = (int) std::min<long long>(((long long) e + NDP_BLOCK - 1) / NDP_BLOCK, (long long) t->sm_count * 16);
-    k_import<<<blocks, NDP_BLOCK, smem_bytes(t), t->s_compute>>>(A);
-    CU(cudaGetLastError());
+    CU(ndp_launch_import(A, blocks, smem_bytes(t), t->s_compute));
     t->st_launches++;
     CU(cudaStreamSynchronize(t->s_compute));
     if ((rc = idx.back()) || (rc = flg.back()) || (rc = nrm.back())) return rc;
@@ -999,8 +936,7 @@ extern "C" int ndpb_hypercubes(ndpb_table *t, const double *normed, const int32_
     HypercubeArgs A{};
     A.g = t->g; A.grid = t->grid; A.normed = nrm.dev; A.indices = idx.dev; A.flags = flg.dev; A.n = n;
     A.dim = dm.dev; A.fdhc = fd.dev; A.v = vv.dev;
-    k_hypercubes<<<blocks_for(n), NDP_BLOCK, 0, t->s_compute>>>(A);
-    CU(cudaGetLastError());
+    CU(ndp_launch_hypercubes(A, blocks_for(n), t->s_compute));
     t->st_launches++;
     CU(cudaStreamSynchronize(t->s_compute));
     if ((rc = dm.back()) || (rc = fd.back()) || (rc = vv.back())) return rc;

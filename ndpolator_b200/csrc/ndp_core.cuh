@@ -72,6 +72,10 @@ struct NdpPyramid {
     int dim[NDP_MAX_LEVELS][NDP_MAX_AXES];      // indexed by pyramid axis j
     int stride[NDP_MAX_LEVELS][NDP_MAX_AXES];
     const uint32_t *bits[NDP_MAX_LEVELS];
+    // per level-0 lattice point, along the LAST pyramid axis: nearest set coordinate at or below /
+    // at or above it (-1: none); nullptr when not built (axis longer than 32767 ticks)
+    const short *prevv;
+    const short *nextv;
     int first_clear;                  // lowest vertex id whose level-0 bit is clear, or -1 (full pyramid only)
     int any_set;                      // 0 when the mask is empty
 };
@@ -551,14 +555,17 @@ NDP_HD void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, con
 }
 
 // Expanding-shell search around the lattice point p0 the query rounds to, over the
-// axes pyramid P spans (level 0 of P is the mask itself).  Shell R holds the points
-// at Chebyshev distance R from p0.  After shell R, every unscanned point differs
-// from p0 by more than R on some axis, so by per-axis convexity its metric is at
-// least LB_R = min over (axis, side) of the ordered sum with that axis' term
-// evaluated R+1 ticks away and every other axis at its own minimum; the best point
-// so far is final once it is strictly below LB_R (a tie with LB_R keeps going).
+// axes pyramid P spans.  Shells are taken over all pyramid axes but the last: a shell
+// point is a ROW of the mask along the last axis, and along a row the metric is
+// convex in the coordinate, so only the set coordinates nearest to p0 on either
+// side can win -- read in O(1) from the prevv/nextv tables (plus any further ones
+// that score exactly the same after rounding, for the tie rules).  After shell R every unscanned
+// row differs from p0 by more than R on some shell axis, so its metric is at least
+// LB_R = min over (axis, side) of the ordered sum with that axis' term evaluated
+// R+1 ticks away and every other axis at its own minimum; the best point so far is
+// final once it is strictly below LB_R (equality keeps going: ties matter).
 // Returns true when proven; otherwise leaves the best so far in `hit` as a seed
-// (hit.vertex < 0: nothing found yet) after about `budget` points.
+// (hit.vertex < 0: nothing found yet) after about `budget` rows.
 NDP_HD bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
                             const int *fixed, const NdpTopo *topo, int budget, NdpHit &hit)
 {
@@ -571,6 +578,7 @@ NDP_HD bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode, con
     int base = 0;
 
     hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_OK; hit.hard = 1;
+    if (nv < 1 || !P.prevv) return false;
     for (int a = 0; a < nb; a++) jof[a] = -1;
     for (int j = 0; j < nv; j++) jof[P.var_axis[j]] = j;
     for (int a = 0; a < nb; a++) {
@@ -581,65 +589,88 @@ NDP_HD bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode, con
         const int c = (int) p;
         if (!(c >= lo && c <= g.len[a] - 1)) return false;
         const double t0 = ndp_axis_term(mode, Q.qc[a], c, c);
-        // p0 must be the per-axis minimiser for the shell bound to hold
+        // p0 must be the per-axis minimiser for the shell bound and the row argument to hold
         if (c - 1 >= lo && ndp_axis_term(mode, Q.qc[a], c - 1, c - 1) < t0) return false;
         if (c + 1 <= g.len[a] - 1 && ndp_axis_term(mode, Q.qc[a], c + 1, c + 1) < t0) return false;
         if (!(t0 == t0)) return false;
         p0[jof[a]] = c; tmin[a] = t0;
     }
+    const int ns = nv - 1;                         // shell axes; the last pyramid axis is the row axis
+    const int aL = P.var_axis[ns];
+    const int lenL = g.len[aL];
 
     int best = -1;
     double bestd = 0.0;
     bool tie = false;
-    int scanned = 0;
+    int rows = 0;
+
+    // scores the set coordinate c of the current row (row_vid = vertex id without the row axis);
+    // returns its metric
+    auto score = [&](const int *off, int row_vid, int c) -> double {
+        double d = 0.0;
+        for (int a = 0; a < nb; a++) {
+            const int j = jof[a];
+            if (j < 0) d += tmin[a];
+            else if (j == ns) d += ndp_axis_term(mode, Q.qc[a], c, c);
+            else d += ndp_axis_term(mode, Q.qc[a], p0[j] + off[j], p0[j] + off[j]);
+        }
+        d = ndp_add_assoc(g, mode, Q, d);
+        const int vid = row_vid + c * g.bstride[aL];
+        if (best < 0 || d < bestd) { best = vid; bestd = d; tie = false; }
+        else if (d == bestd && vid != best) {
+            if (!kd) { if (vid < best) best = vid; }                     // _compare_indexed_dists, :101-112
+            else if (topo) { if (ndp_tree_beats(g, mode, *topo, Q, vid, best)) best = vid; }
+            else tie = true;
+        }
+        return d;
+    };
+
     for (int R = 0;; R++) {
-        // --- scan shell R: odometer over [-R, R]^nv, keeping offsets with Chebyshev norm R
         int off[NDP_MAX_AXES];
-        for (int j = 0; j < nv; j++) off[j] = -R;
+        for (int j = 0; j < ns; j++) off[j] = -R;
         for (;;) {
-            int cheb = 0, flat = 0, vid = base;
+            int cheb = 0, rowflat = 0, row_vid = base;
             bool inside = true;
-            for (int j = 0; j < nv; j++) {
+            for (int j = 0; j < ns; j++) {
                 const int o = off[j] < 0 ? -off[j] : off[j];
                 if (o > cheb) cheb = o;
                 const int a = P.var_axis[j];
                 const int c = p0[j] + off[j];
                 if (c < lo || c > g.len[a] - 1) inside = false;
-                flat += c * P.stride[0][j];
-                vid += c * g.bstride[a];
+                rowflat += c * P.stride[0][j];
+                row_vid += c * g.bstride[a];
             }
             if (cheb == R && inside) {
-                scanned++;
-                if (ndp_bit(P.bits[0], flat)) {
-                    double d = 0.0;
-                    for (int a = 0; a < nb; a++) {
-                        const int j = jof[a];
-                        d += (j < 0) ? tmin[a] : ndp_axis_term(mode, Q.qc[a], p0[j] + off[j], p0[j] + off[j]);
-                    }
-                    d = ndp_add_assoc(g, mode, Q, d);
-                    if (best < 0 || d < bestd) { best = vid; bestd = d; tie = false; }
-                    else if (d == bestd && vid != best) {
-                        if (!kd) { if (vid < best) best = vid; }
-                        else if (topo) { if (ndp_tree_beats(g, mode, *topo, Q, vid, best)) best = vid; }
-                        else tie = true;
-                    }
+                rows++;
+                // Set coordinates of the row, outward from p0 on either side.  The metric grows
+                // (weakly, after rounding) with the distance from p0, so a side is exhausted as
+                // soon as a coordinate scores strictly above the best so far; equal scores keep
+                // going because ties are decided by the reference's rules, not by us.
+                int c = P.prevv[rowflat + p0[ns]];
+                while (c >= lo) {
+                    if (score(off, row_vid, c) > bestd) break;
+                    c = (c - 1 >= lo) ? P.prevv[rowflat + c - 1] : -1;
+                }
+                c = (p0[ns] + 1 <= lenL - 1) ? P.nextv[rowflat + p0[ns] + 1] : -1;
+                while (c >= lo) {
+                    if (score(off, row_vid, c) > bestd) break;
+                    c = (c + 1 <= lenL - 1) ? P.nextv[rowflat + c + 1] : -1;
                 }
             }
-            // next offset; interior points (norm < R) are skipped by jumping the last axis
-            int j = nv - 1;
-            if (nv > 0 && R > 0) {
-                // when all leading offsets are strictly inside, the last axis only takes -R and +R
+            // next shell offset; interior offsets (norm < R) are skipped by jumping the last shell axis
+            int j = ns - 1;
+            if (ns > 0 && R > 0) {
                 bool lead_inside = true;
-                for (int jj = 0; jj < nv - 1; jj++) { const int o = off[jj] < 0 ? -off[jj] : off[jj]; if (o == R) lead_inside = false; }
+                for (int jj = 0; jj < ns - 1; jj++) { const int o = off[jj] < 0 ? -off[jj] : off[jj]; if (o == R) lead_inside = false; }
                 if (lead_inside && off[j] == -R) { off[j] = R; continue; }
             }
             while (j >= 0) { if (++off[j] <= R) break; off[j] = -R; j--; }
             if (j < 0) break;
         }
-        // --- lower bound for everything beyond shell R
+        // lower bound for every row beyond shell R
         bool any_beyond = false;
         double lb = 0.0;
-        for (int j = 0; j < nv; j++) {
+        for (int j = 0; j < ns; j++) {
             const int a = P.var_axis[j];
             for (int sgn = -1; sgn <= 1; sgn += 2) {
                 const int c = p0[j] + sgn * (R + 1);
@@ -652,12 +683,12 @@ NDP_HD bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode, con
             }
         }
         hit.vertex = best; hit.dsel = bestd; hit.status = tie ? NDP_SEARCH_TIE : NDP_SEARCH_OK;
-        if (!any_beyond) {                       // the whole slice has been scanned
+        if (!any_beyond) {                       // every row of the slice has been scanned
             if (best < 0) hit.status = NDP_SEARCH_EMPTY;
             return true;
         }
         if (best >= 0 && bestd < lb) return true;
-        if (scanned >= budget) return false;
+        if (rows >= budget) return false;
     }
 }
 

@@ -47,6 +47,7 @@ struct ImportArgs {
     int *indices; int *flags; double *normed;
 };
 
+#if defined(NDP_TU_TAPS)
 __global__ void __launch_bounds__(NDP_BLOCK) k_import(const __grid_constant__ ImportArgs A)
 {
     extern __shared__ double s_ticks[];
@@ -62,6 +63,8 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_import(const __grid_constant__ Im
     }
 }
 
+#endif  // NDP_TU_TAPS
+
 // ---------------------------------------------------------------------------
 // k_hypercubes: the tap behind cndpolator.hypercubes
 // ---------------------------------------------------------------------------
@@ -72,6 +75,7 @@ struct HypercubeArgs {
     int *dim; int *fdhc; double *v;
 };
 
+#if defined(NDP_TU_TAPS)
 __global__ void __launch_bounds__(NDP_BLOCK) k_hypercubes(const __grid_constant__ HypercubeArgs A)
 {
     const NdpGeom &g = A.g;
@@ -110,6 +114,8 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_hypercubes(const __grid_constant_
     }
 }
 
+#endif  // NDP_TU_TAPS
+
 // ---------------------------------------------------------------------------
 // k_main
 // ---------------------------------------------------------------------------
@@ -125,6 +131,7 @@ struct MainArgs {
     NdpCounters *ctr;
 };
 
+#if defined(NDP_TU_MAIN)
 // N: compile-time axis count (0 = runtime).  G: lanes cooperating on one query,
 // each owning components k = lane, lane+G, ... (G = 1 for scalar tables).
 template <int N, int G, bool CM>
@@ -191,6 +198,8 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_main(const __gr
     }
 }
 
+#endif  // NDP_TU_MAIN
+
 // ---------------------------------------------------------------------------
 // k_search / k_search_brute
 // ---------------------------------------------------------------------------
@@ -214,6 +223,7 @@ struct SearchArgs {
     NdpCounters *ctr;
 };
 
+#if defined(NDP_TU_SEARCH)
 __device__ __forceinline__ void ndp_publish(const SearchArgs &A, const NdpQuery &Q, long long t, long long i, NdpHit hit)
 {
     const NdpGeom &g = A.g;
@@ -351,6 +361,8 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_brute(const __grid_constan
     }
 }
 
+#endif  // NDP_TU_SEARCH
+
 // ---------------------------------------------------------------------------
 // k_finish
 // ---------------------------------------------------------------------------
@@ -367,6 +379,7 @@ struct FinishArgs {
     double *interps;
 };
 
+#if defined(NDP_TU_FINISH)
 template <int N, bool CM>
 __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __grid_constant__ FinishArgs A)
 {
@@ -391,6 +404,8 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __
             A.interps[i * V + k] = ndp_finish_component<N, CM, false>(g, A.grid, A.cells, A.method, idx, nrm, coords, k);
     }
 }
+#endif  // NDP_TU_FINISH
+
 
 // ---------------------------------------------------------------------------
 // Staged gather (scalar tables, cell-major layout): k_gather_staged
@@ -411,6 +426,19 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __
 #define NDP_STAGED_WARPS 4
 #define NDP_STAGED_STAGES 2
 
+struct StagedArgs {
+    NdpGeom g;
+    const double *ticks; int nticks;
+    const double *cells;
+    const double *q; long long n;      // MODE 0: number of queries; MODE 1: unused
+    double *interps; double *dists;
+    int method;
+    int *offlist;                      // MODE 0: out; MODE 1: in (query id per work item)
+    const int *chosen;                 // MODE 1: winning vertex per work item
+    NdpCounters *ctr;
+};
+
+#if defined(NDP_TU_STAGED)
 __device__ __forceinline__ unsigned ndp_smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void ndp_mbar_init(unsigned bar, unsigned count)
@@ -438,18 +466,6 @@ __device__ __forceinline__ void ndp_mbar_wait(unsigned bar, unsigned parity)
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
-
-struct StagedArgs {
-    NdpGeom g;
-    const double *ticks; int nticks;
-    const double *cells;
-    const double *q; long long n;      // MODE 0: number of queries; MODE 1: unused
-    double *interps; double *dists;
-    int method;
-    int *offlist;                      // MODE 0: out; MODE 1: in (query id per work item)
-    const int *chosen;                 // MODE 1: winning vertex per work item
-    NdpCounters *ctr;
-};
 
 template <int N>
 struct NdpStagedItem {                 // what a lane keeps between issuing a tile and reducing it
@@ -585,3 +601,4 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
         st ^= 1;
     }
 }
+#endif  // NDP_TU_STAGED

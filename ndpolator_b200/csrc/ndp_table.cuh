@@ -116,6 +116,25 @@ __global__ void k_mask_slice(const __grid_constant__ SliceArgs A)
     if ((threadIdx.x & 31) == 0 && p < A.nslice) A.out[p >> 5] = word;
 }
 
+// Row tables of a level-0 mask whose last axis has `len` ticks: per lattice point the nearest set
+// coordinate at or below (prevv) and at or above (nextv) along that axis, -1 when there is none.
+__global__ void k_row_tables(const uint32_t *__restrict__ bits, long long nrows, int len, short *prevv, short *nextv)
+{
+    const long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const long long b0 = r * len;
+    short last = -1;
+    for (int c = 0; c < len; c++) {
+        if (ndp_bit(bits, (int) (b0 + c))) last = (short) c;
+        prevv[b0 + c] = last;
+    }
+    last = -1;
+    for (int c = len - 1; c >= 0; c--) {
+        if (ndp_bit(bits, (int) (b0 + c))) last = (short) c;
+        nextv[b0 + c] = last;
+    }
+}
+
 // lowest vertex id whose bit is clear (for the 1e10 sentinel of the full scan); *out preset to INT_MAX
 __global__ void k_first_clear(const uint32_t *__restrict__ bits, int nverts, int *out)
 {

@@ -1,0 +1,42 @@
+// nearest-search kernels and the find / hypercubes taps
+#define NDP_TU_SEARCH
+#define NDP_TU_TAPS
+#include "ndp_launch.h"
+
+cudaError_t ndp_launch_import(const ImportArgs &A, int blocks, size_t smem, cudaStream_t st)
+{
+    k_import<<<blocks, NDP_BLOCK, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t ndp_launch_hypercubes(const HypercubeArgs &A, int blocks, cudaStream_t st)
+{
+    k_hypercubes<<<blocks, NDP_BLOCK, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t ndp_launch_search_fast(const SearchArgs &A, int naxes, int blocks, size_t smem, cudaStream_t st)
+{
+    switch (naxes) {
+    case 1: k_search_fast<1><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 2: k_search_fast<2><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 3: k_search_fast<3><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 4: k_search_fast<4><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 5: k_search_fast<5><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 6: k_search_fast<6><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    default: k_search_fast<0><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t ndp_launch_search_hard(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st)
+{
+    k_search_hard<<<blocks, NDP_BLOCK, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t ndp_launch_search_brute(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st)
+{
+    k_search_brute<<<blocks, NDP_BLOCK, smem, st>>>(A);
+    return cudaGetLastError();
+}

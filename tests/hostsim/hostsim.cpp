@@ -17,7 +17,7 @@
 
 #include "../../ndpolator_b200/csrc/ndp_core.cuh"
 
-struct HsPyr { NdpPyramid dev; std::vector<std::vector<uint32_t>> levels; };
+struct HsPyr { NdpPyramid dev; std::vector<std::vector<uint32_t>> levels; std::vector<short> prevv, nextv; };
 
 struct HsTable {
     NdpGeom g;
@@ -70,6 +70,20 @@ static void build_pyr(HsTable *t, HsPyr &P, std::vector<uint32_t> level0, int nv
     D.first_clear = -1;
     if (full) for (int v = 0; v < g.nverts; v++) if (!ndp_bit(D.bits[0], v)) { D.first_clear = v; break; }
     D.any_set = ndp_bit(D.bits[D.nlev - 1], 0) ? 1 : 0;
+    D.prevv = D.nextv = nullptr;
+    if (nvar >= 1 && dim0[nvar - 1] <= 32767) {          // mirrors k_row_tables
+        long long npts = 1;
+        for (int j = 0; j < nvar; j++) npts *= dim0[j];
+        const int len = dim0[nvar - 1];
+        P.prevv.assign(npts, -1); P.nextv.assign(npts, -1);
+        for (long long r = 0; r < npts / len; r++) {
+            short last = -1;
+            for (int c = 0; c < len; c++) { if (ndp_bit(D.bits[0], (int) (r * len + c))) last = (short) c; P.prevv[r * len + c] = last; }
+            last = -1;
+            for (int c = len - 1; c >= 0; c--) { if (ndp_bit(D.bits[0], (int) (r * len + c))) last = (short) c; P.nextv[r * len + c] = last; }
+        }
+        D.prevv = P.prevv.data(); D.nextv = P.nextv.data();
+    }
 }
 
 // mirrors k_mask_variance + k_mask_slice + build_reduced()
