@@ -607,7 +607,7 @@ static size_t staged_smem(const ndpb_table *t)
 {
     const size_t ticks = ((size_t) t->nticks * 8 + 127) & ~(size_t) 127;
     const size_t slot = ((size_t) 8 << t->g.naxes) + 16;
-    return ticks + 128 + (size_t) NDP_STAGED_WARPS * NDP_STAGED_STAGES * 32 * slot;
+    return ticks + (size_t) NDP_STAGED_WARPS * NDP_STAGED_STAGES * 32 * slot;
 }
 
 template <int MODE>

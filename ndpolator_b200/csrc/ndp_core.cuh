@@ -391,9 +391,11 @@ struct NdpHit {
 };
 
 // N > 0: number of axes known at compile time (everything stays in registers).
-template <int N>
-NDP_HD bool ndp_search_fast(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q, NdpHit &hit)
+// MODE >= 0: search mode known at compile time (the metric's branches fold away).
+template <int N, int MODE = -1>
+NDP_HD bool ndp_search_fast(const NdpGeom &g, const NdpPyramid &P, int mode_rt, const NdpQuery &Q, NdpHit &hit)
 {
+    const int mode = (MODE >= 0) ? MODE : mode_rt;
     constexpr int M = N ? N : NDP_MAX_AXES;
     const int nb = g.nbasic;
     const bool cells = (mode == NDP_MODE_KD_LINEAR || mode == NDP_MODE_LS_LINEAR);

@@ -246,7 +246,7 @@ __device__ __forceinline__ void ndp_publish(const SearchArgs &A, const NdpQuery 
 
 // Pass 1: the rounded lattice point, proven optimal by its axis neighbours.  What it
 // cannot settle goes to the hard list so that pass 2 runs with full warps.
-template <int N>
+template <int N, int MODE>
 __global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant__ SearchArgs A)
 {
     extern __shared__ double s_ticks[];
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant
             NdpQuery Q;
             ndp_make_query(g, idx, nrm, Q);
             NdpHit hit;
-            if (ndp_search_fast<N>(g, *A.F, mode, Q, hit)) {
+            if (ndp_search_fast<N, MODE>(g, *A.F, mode, Q, hit)) {
                 ndp_scan_sentinel(*A.F, mode, hit);
                 ndp_publish(A, Q, t, i, hit);
             } else hard = true;
@@ -410,15 +410,23 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __
 // ---------------------------------------------------------------------------
 // Staged gather (scalar tables, cell-major layout): k_gather_staged
 //
-// The cell of a query is one contiguous (8 << N)-byte block, so instead of
-// holding 2^N load destinations in registers while DRAM answers, every lane hands
-// its block to the bulk-copy engine (cp.async.bulk -> shared memory, completion
-// counted on an mbarrier) and goes on to import the NEXT tile's queries; the
-// reduction of a tile runs one iteration later out of shared memory.  Each warp
-// owns a private two-stage ring (its own slots and mbarriers), so there is no
-// block-wide synchronisation in the loop and memory-level parallelism no longer
-// depends on occupancy.  Slots are padded by 16 bytes so that the 128-bit
-// shared loads of a quarter-warp fall into distinct bank groups.
+// The cell of a query is one contiguous (8 << N)-byte block.  Instead of holding
+// 2^N load destinations in registers while DRAM answers, the warp copies the
+// blocks of a 32-query tile asynchronously into shared memory (cp.async, LDGSTS)
+// and goes on to import the NEXT tile's queries; the reduction of a tile runs one
+// iteration later out of shared memory.  Each warp owns a private two-stage ring,
+// so there is no block-wide synchronisation in the loop and memory-level
+// parallelism no longer depends on register-limited occupancy.
+//
+// Lane pairs cooperate on their two blocks so that every 16-byte cp.async of a
+// pair lands in the same 32-byte sector (full-sector requests to L2, no
+// over-fetch).  Slots are padded by 16 bytes so that the 128-bit shared loads of
+// a quarter-warp fall into distinct bank groups.
+//
+// (Round-1 note: the first version issued one cp.async.bulk per lane with an
+// mbarrier per warp; ncu showed the bulk copy takes uniform-register operands, so
+// the compiler serialises the 32 lanes through an ELECT/R2UR loop -- 25 % of the
+// kernel's instructions.  profiles/r01c_*.  Per-thread LDGSTS has no such loop.)
 //
 // MODE 0: the k_main work (import + classify + gather + reduce + off-grid list)
 // MODE 1: the k_finish work for LINEAR extrapolation (cell below the found corner)
@@ -441,38 +449,20 @@ struct StagedArgs {
 #if defined(NDP_TU_STAGED)
 __device__ __forceinline__ unsigned ndp_smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void ndp_mbar_init(unsigned bar, unsigned count)
+__device__ __forceinline__ void ndp_cp_async16(unsigned dst, const void *src)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void ndp_mbar_arrive(unsigned bar)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void ndp_mbar_arrive_expect_tx(unsigned bar, unsigned bytes)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ndp_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void ndp_mbar_wait(unsigned bar, unsigned parity)
-{
-    unsigned done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
+__device__ __forceinline__ void ndp_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void ndp_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
 template <int N>
 struct NdpStagedItem {                 // what a lane keeps between issuing a tile and reducing it
     long long i;                       // query id (-1: lane idle)
     double x[N];                       // interpolation weights
     unsigned pinmask, selbits;
-    bool issued;                       // a bulk copy is in flight for this lane
+    bool issued;                       // this lane's cell is being copied
 };
 
 template <int N, int MODE>
@@ -480,30 +470,23 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
 {
     constexpr unsigned CELL_BYTES = 8u << N;
     constexpr unsigned SLOT = CELL_BYTES + 16u;
+    constexpr int CHUNKS = (int) (CELL_BYTES / 16u);      // 16-byte pieces per cell (N >= 2: at least 2)
     extern __shared__ __align__(128) unsigned char ndp_smem[];
     const NdpGeom &g = A.g;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // shared layout: ticks | mbarriers | slots
+    // shared layout: ticks | slots
     double *s_ticks = reinterpret_cast<double *>(ndp_smem);
     const unsigned ticks_bytes = ((unsigned) A.nticks * 8u + 127u) & ~127u;
-    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(ndp_smem + ticks_bytes);
-    unsigned char *s_slots = ndp_smem + ticks_bytes + 128u;
+    unsigned char *s_slots = ndp_smem + ticks_bytes;
 
     for (int i = threadIdx.x; i < A.nticks; i += blockDim.x) s_ticks[i] = A.ticks[i];
-    if (lane == 0)
-        for (int st = 0; st < NDP_STAGED_STAGES; st++) ndp_mbar_init(ndp_smem_u32(&s_bar[warp * NDP_STAGED_STAGES + st]), 32);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    unsigned bar[NDP_STAGED_STAGES], slot[NDP_STAGED_STAGES];
-    const unsigned char *slot_ptr[NDP_STAGED_STAGES];
-#pragma unroll
-    for (int st = 0; st < NDP_STAGED_STAGES; st++) {
-        bar[st] = ndp_smem_u32(&s_bar[warp * NDP_STAGED_STAGES + st]);
-        slot_ptr[st] = s_slots + ((size_t) (warp * NDP_STAGED_STAGES + st) * 32 + lane) * SLOT;
-        slot[st] = ndp_smem_u32(slot_ptr[st]);
-    }
+    // slot of lane L in stage st of this warp
+    auto slot_of = [&](int st, unsigned L) -> unsigned char * {
+        return s_slots + ((size_t) (warp * NDP_STAGED_STAGES + st) * 32 + L) * SLOT;
+    };
 
     const long long total = (MODE == 0) ? A.n : (long long) A.ctr->n_off;
     const long long ntiles = (total + 31) / 32;
@@ -511,7 +494,7 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
     const long long tile0 = (long long) blockIdx.x * NDP_STAGED_WARPS + warp;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-    // issue: import the lane's query of `tile`, start its bulk copy into stage st
+    // issue: import the lane's query of `tile`, start the pair-cooperative copy into stage st
     auto produce = [&](long long tile, int st, NdpStagedItem<N> &it) {
         const long long w = tile * 32 + lane;
         it.i = -1; it.issued = false; it.pinmask = 0; it.selbits = 0;
@@ -525,8 +508,15 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
             if (MODE == 0) {
                 const bool oob = ndp_classify<N>(g, flg, nrm, it.pinmask, it.selbits);
                 it.issued = !oob;
+                if (g.small) {
+                    int c32 = 0;
 #pragma unroll
-                for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; cell += (long long) (idx[a] - 1) * g.cstride[a]; }
+                    for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; c32 += (idx[a] - 1) * g.cstride32[a]; }
+                    cell = c32;
+                } else {
+#pragma unroll
+                    for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; cell += (long long) (idx[a] - 1) * g.cstride[a]; }
+                }
             } else {
                 const int vertex = A.chosen[w];
                 it.issued = true;
@@ -540,22 +530,32 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
                 }
             }
         }
-        if (it.issued) {
-            ndp_mbar_arrive_expect_tx(bar[st], CELL_BYTES);
-            ndp_bulk_g2s(slot[st], A.cells + (cell << N), CELL_BYTES, bar[st]);
-        } else {
-            ndp_mbar_arrive(bar[st]);
+        // the pair (lane & ~1, lane | 1) copies its two cells together: in step k both lanes fetch
+        // the two halves of one 32-byte sector of cell u
+        const unsigned long long mine = it.issued ? (unsigned long long) (A.cells + (cell << N)) : 0ull;
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, 1);
+        const unsigned half = lane & 1u;
+#pragma unroll
+        for (int k = 0; k < CHUNKS; k++) {
+            const unsigned u = (unsigned) k / (CHUNKS / 2);             // whose cell: 0 = even lane's, 1 = odd lane's
+            const unsigned sector = (unsigned) k % (CHUNKS / 2);
+            const unsigned chunk = 2u * sector + half;
+            const unsigned long long src = (u == half) ? mine : other;
+            if (src) {
+                const unsigned dst = ndp_smem_u32(slot_of(st, (lane & ~1u) + u)) + chunk * 16u;
+                ndp_cp_async16(dst, reinterpret_cast<const unsigned char *>(src) + chunk * 16u);
+            }
         }
+        ndp_cp_async_commit();
     };
 
-    // reduce: wait for the tile's copies, interpolate out of shared memory, write results
-    auto consume = [&](int st, unsigned parity, const NdpStagedItem<N> &it) {
-        ndp_mbar_wait(bar[st], parity);
+    // reduce: the tile's copies have landed; interpolate out of shared memory, write results
+    auto consume = [&](int st, const NdpStagedItem<N> &it) {
         bool need_search = false;
         if (it.i >= 0) {
             bool fdhc = false;
             if (it.issued) {
-                const double2 *b2 = reinterpret_cast<const double2 *>(slot_ptr[st]);
+                const double2 *b2 = reinterpret_cast<const double2 *>(slot_of(st, lane));
                 bool bad = false;
                 const double val = ndp_cell_reduce<N>([&](double *fv) {
 #pragma unroll
@@ -582,22 +582,25 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
         }
     };
 
-    // N == 1 has an 8-byte cell, below the 16-byte granule of the bulk copy: not launched for N == 1
     NdpStagedItem<N> item[NDP_STAGED_STAGES];
-    unsigned parity[NDP_STAGED_STAGES] = {0, 0};
     if (tile0 < ntiles) produce(tile0, 0, item[0]);
     int st = 0;
     for (long long tile = tile0; tile < ntiles; tile += tile_stride) {
         const long long next = tile + tile_stride;
+        // one commit per iteration (possibly empty) keeps the group count uniform: everything
+        // but the newest group -- the tile being consumed included -- is complete after wait<1>
         if (st == 0) {
-            if (next < ntiles) produce(next, 1, item[1]);
-            consume(0, parity[0], item[0]);
-            parity[0] ^= 1u;
+            if (next < ntiles) produce(next, 1, item[1]); else ndp_cp_async_commit();
+            ndp_cp_async_wait<1>();
+            __syncwarp();                      // the partner lane's copies into my slot are visible
+            consume(0, item[0]);
         } else {
-            if (next < ntiles) produce(next, 0, item[0]);
-            consume(1, parity[1], item[1]);
-            parity[1] ^= 1u;
+            if (next < ntiles) produce(next, 0, item[0]); else ndp_cp_async_commit();
+            ndp_cp_async_wait<1>();
+            __syncwarp();
+            consume(1, item[1]);
         }
+        __syncwarp();                          // slots of this stage are free for the pair to overwrite
         st ^= 1;
     }
 }

@@ -15,18 +15,29 @@ cudaError_t ndp_launch_hypercubes(const HypercubeArgs &A, int blocks, cudaStream
     return cudaGetLastError();
 }
 
-cudaError_t ndp_launch_search_fast(const SearchArgs &A, int naxes, int blocks, size_t smem, cudaStream_t st)
+template <int MODE>
+static cudaError_t fast_by_axes(const SearchArgs &A, int naxes, int blocks, size_t smem, cudaStream_t st)
 {
     switch (naxes) {
-    case 1: k_search_fast<1><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 2: k_search_fast<2><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 3: k_search_fast<3><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 4: k_search_fast<4><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 5: k_search_fast<5><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    case 6: k_search_fast<6><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
-    default: k_search_fast<0><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 1: k_search_fast<1, MODE><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 2: k_search_fast<2, MODE><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 3: k_search_fast<3, MODE><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 4: k_search_fast<4, MODE><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 5: k_search_fast<5, MODE><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case 6: k_search_fast<6, MODE><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    default: k_search_fast<0, MODE><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
     }
     return cudaGetLastError();
+}
+
+cudaError_t ndp_launch_search_fast(const SearchArgs &A, int naxes, int blocks, size_t smem, cudaStream_t st)
+{
+    switch (ndp_mode_of(A.method, A.search)) {
+    case NDP_MODE_KD_NEAREST: return fast_by_axes<NDP_MODE_KD_NEAREST>(A, naxes, blocks, smem, st);
+    case NDP_MODE_KD_LINEAR: return fast_by_axes<NDP_MODE_KD_LINEAR>(A, naxes, blocks, smem, st);
+    case NDP_MODE_LS_NEAREST: return fast_by_axes<NDP_MODE_LS_NEAREST>(A, naxes, blocks, smem, st);
+    default: return fast_by_axes<NDP_MODE_LS_LINEAR>(A, naxes, blocks, smem, st);
+    }
 }
 
 cudaError_t ndp_launch_search_hard(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st)

@@ -253,7 +253,14 @@ static void search_one_n(HsTable *t, const double *qrow, int method, int search,
     ndp_import_query<0>(g, t->ticks.data(), qrow, idx, flg, nrm);
     NdpQuery Q; ndp_make_query(g, idx, nrm, Q);
     NdpHit hit;
-    if (!ndp_search_fast<N>(g, t->pyr[m].dev, mode, Q, hit)) {
+    bool fast;
+    switch (mode) {      // mirrors the dispatch of k_search_fast<N, MODE>
+    case 0: fast = ndp_search_fast<N, 0>(g, t->pyr[m].dev, mode, Q, hit); break;
+    case 1: fast = ndp_search_fast<N, 1>(g, t->pyr[m].dev, mode, Q, hit); break;
+    case 2: fast = ndp_search_fast<N, 2>(g, t->pyr[m].dev, mode, Q, hit); break;
+    default: fast = ndp_search_fast<N, 3>(g, t->pyr[m].dev, mode, Q, hit); break;
+    }
+    if (!fast) {
         t->n_hard++;
         ndp_search_descend(g, t->pyr[m].dev, t->red[m].dev, mode, Q, nullptr, hit);
         if (hit.status == NDP_SEARCH_TIE) {
