@@ -384,7 +384,7 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
         return NDPB_OK;
     }
     if (k == "staged") {
-        if (value < 0 || value > 1) return fail(NDPB_ERR_INVALID, "staged must be 0 (auto) or 1 (off)");
+        if (value < 0 || value > 3) return fail(NDPB_ERR_INVALID, "staged must be 0 (auto), 1 (off), 2 (cp.async ring) or 3 (L2 prefetch)");
         t->opt_staged = (int) value;
         return NDPB_OK;
     }
@@ -599,7 +599,7 @@ static int launch_finish(ndpb_table *t, const FinishArgs &A, cudaStream_t st)
 // The bulk-copy staged gather serves scalar tables with a cell-major copy, 2..6 axes.
 static bool staged_ok(const ndpb_table *t)
 {
-    return t->opt_staged == 0 && t->cells && t->g.vdim == 1 && t->g.naxes >= 2 && t->g.naxes <= 6 &&
+    return t->opt_staged != 1 && t->cells && t->g.vdim == 1 && t->g.naxes >= 2 && t->g.naxes <= 6 &&
            (size_t) t->nticks * sizeof(double) <= 16 * 1024;
 }
 
@@ -613,7 +613,8 @@ static size_t staged_smem(const ndpb_table *t)
 template <int MODE>
 static int launch_staged(ndpb_table *t, const StagedArgs &A, long long items, cudaStream_t st)
 {
-    CU(ndp_launch_staged(A, t->g.naxes, MODE, t->sm_count, items, staged_smem(t), st));
+    if (t->opt_staged == 2) CU(ndp_launch_staged(A, t->g.naxes, MODE, t->sm_count, items, staged_smem(t), st));
+    else CU(ndp_launch_pf(A, t->g.naxes, MODE, t->sm_count, items, ((size_t) t->nticks * 8 + 15) & ~(size_t) 15, st));
     t->st_launches++;
     return NDPB_OK;
 }

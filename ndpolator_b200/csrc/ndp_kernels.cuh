@@ -604,4 +604,124 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
         st ^= 1;
     }
 }
+
+// ---------------------------------------------------------------------------
+// Prefetch-pipelined gather: k_gather_pf
+//
+// Same work split as k_gather_staged, but the look-ahead costs neither shared
+// memory nor registers: while the current query is being reduced, the thread has
+// already imported its NEXT query and asked L2 for that query's cell
+// (prefetch.global.L2 on its two 128-byte lines).  One iteration later the
+// 128-bit loads of that cell hit L2 instead of paying the DRAM round trip.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void ndp_prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <int N>
+struct NdpPfItem {
+    long long i;                       // query id (-1: idle)
+    const double *cell;                // nullptr: nothing to gather
+    double x[N];
+    unsigned pinmask, selbits;
+};
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(128, (N <= 5 ? 4 : 1)) k_gather_pf(const __grid_constant__ StagedArgs A)
+{
+    constexpr unsigned CELL_BYTES = 8u << N;
+    extern __shared__ __align__(16) unsigned char ndp_smem[];
+    const NdpGeom &g = A.g;
+    const unsigned lane = threadIdx.x & 31;
+    double *s_ticks = reinterpret_cast<double *>(ndp_smem);
+    for (int i = threadIdx.x; i < A.nticks; i += blockDim.x) s_ticks[i] = A.ticks[i];
+    __syncthreads();
+
+    const long long total = (MODE == 0) ? A.n : (long long) A.ctr->n_off;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    const long long rounds = (total + stride - 1) / stride;
+    const long long w0 = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    auto prepare = [&](long long w, NdpPfItem<N> &it) {
+        it.i = -1; it.cell = nullptr; it.pinmask = 0; it.selbits = 0;
+        if (w >= total) return;
+        const long long i = (MODE == 0) ? w : (long long) A.offlist[w];
+        it.i = i;
+        int idx[N], flg[N];
+        double nrm[N];
+        ndp_import_query<N>(g, s_ticks, A.q + i * N, idx, flg, nrm);
+        long long cell = 0;
+        bool gather = true;
+        if (MODE == 0) {
+            gather = !ndp_classify<N>(g, flg, nrm, it.pinmask, it.selbits);
+            if (g.small) {
+                int c32 = 0;
+#pragma unroll
+                for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; c32 += (idx[a] - 1) * g.cstride32[a]; }
+                cell = c32;
+            } else {
+#pragma unroll
+                for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; cell += (long long) (idx[a] - 1) * g.cstride[a]; }
+            }
+        } else {
+            const int vertex = A.chosen[w];
+#pragma unroll
+            for (int a = 0; a < N; a++) {
+                const int c = (a < g.nbasic) ? (vertex / g.bstride[a]) % g.len[a]
+                                             : ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
+                const int sup = c > 1 ? c : 1;                      // :601
+                it.x[a] = nrm[a] + (double) (idx[a] - c);           // :621-622
+                cell += (long long) (sup - 1) * g.cstride[a];
+            }
+        }
+        if (gather) {
+            it.cell = A.cells + (cell << N);
+#pragma unroll
+            for (unsigned off = 0; off < CELL_BYTES; off += 128u)
+                ndp_prefetch_l2(reinterpret_cast<const unsigned char *>(it.cell) + off);
+        }
+    };
+
+    auto finish = [&](const NdpPfItem<N> &it) {
+        bool need_search = false;
+        if (it.i >= 0) {
+            bool fdhc = false;
+            if (it.cell) {
+                const double2 *b2 = reinterpret_cast<const double2 *>(it.cell);
+                bool bad = false;
+                const double val = ndp_cell_reduce<N>([&](double *fv) {
+#pragma unroll
+                    for (int j = 0; j < (1 << N) / 2; j++) { double2 p = b2[j]; fv[2 * j] = p.x; fv[2 * j + 1] = p.y; }
+                }, it.x, it.pinmask, it.selbits, bad);
+                fdhc = !bad;
+                if (MODE == 1 || fdhc) A.interps[it.i] = val;
+            }
+            if (MODE == 0) {
+                if (fdhc) A.dists[it.i] = 0.0;
+                else if (A.method == NDP_M_NONE) { A.interps[it.i] = qnan; A.dists[it.i] = 0.0; }
+                else need_search = true;
+            }
+        }
+        if (MODE == 0) {
+            const unsigned votes = __ballot_sync(0xffffffffu, need_search);
+            if (votes) {
+                int base = 0;
+                const int leader = __ffs(votes) - 1;
+                if ((int) lane == leader) base = atomicAdd(&A.ctr->n_off, __popc(votes));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (need_search) A.offlist[base + __popc(votes & ((1u << lane) - 1u))] = (int) it.i;
+            }
+        }
+    };
+
+    NdpPfItem<N> cur, nxt;
+    prepare(w0, cur);
+    for (long long r = 0; r < rounds; r++) {
+        prepare(w0 + (r + 1) * stride, nxt);      // beyond the end: idle item
+        finish(cur);
+        cur = nxt;
+    }
+}
 #endif  // NDP_TU_STAGED
