@@ -43,7 +43,7 @@ def parse():
     ap.add_argument('--e2e-batch', type=int, default=1 << 24, help='queries per GPU per end-to-end (host buffer) step')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--gather', type=int, default=0, help='0 auto, 1 strided, 2 cell-major')
-    ap.add_argument('--staged', type=int, default=0, help='0 auto, 1 off, 2 cp.async ring, 3 L2 prefetch (same results)')
+    ap.add_argument('--staged', type=int, default=0, help='0 auto (cp.async ring), 1 off (same results)')
     ap.add_argument('--cpu-scale', type=int, default=20, help='ticks per axis of the grid the CPU reference is timed on')
     ap.add_argument('--cpu-queries', type=int, default=20000)
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -110,7 +110,7 @@ int ndpb_table_tree_topology(ndpb_table *t, int method, int32_t *parent, int32_t
 
 /* Tuning knobs that never change results.  Keys: "gather" = 0 auto | 1 strided
  * (original layout) | 2 cell-major; "linear_search" = 0 auto | 1 brute force |
- * 2 lattice; "chunk" = queries per staged chunk for host buffers; "staged" = 0 auto | 1 never use the bulk-copy
+ * 2 lattice; "chunk" = queries per staged chunk for host buffers; "staged" = 0 auto | 1 never use the cp.async
  * staged gather kernel; "stream" = a
  * cudaStream_t (as integer) to launch the kernels on instead of the table's own
  * stream, 0 to restore it. */

@@ -327,6 +327,7 @@ extern "C" int ndpb_table_create(const double *const *axes, const int32_t *axlen
     }
     g.small = (nall < (1LL << 31) - 64) ? 1 : 0;
     for (int a = 0; a < naxes; a++) { g.vstride32[a] = g.small ? (int) g.vstride[a] : 0; g.cstride32[a] = g.small ? (int) g.cstride[a] : 0; }
+    for (int a = 0; a < nbasic; a++) g.inv_bstride[a] = 1.0 / (double) g.bstride[a];
     CUT(cudaMalloc(&t->ticks, sizeof(double) * nticks));
     CUT(cudaMemcpy(t->ticks, flat.data(), sizeof(double) * nticks, cudaMemcpyHostToDevice));
 
@@ -384,7 +385,7 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
         return NDPB_OK;
     }
     if (k == "staged") {
-        if (value < 0 || value > 3) return fail(NDPB_ERR_INVALID, "staged must be 0 (auto), 1 (off), 2 (cp.async ring) or 3 (L2 prefetch)");
+        if (value < 0 || value > 1) return fail(NDPB_ERR_INVALID, "staged must be 0 (auto) or 1 (off)");
         t->opt_staged = (int) value;
         return NDPB_OK;
     }
@@ -613,8 +614,7 @@ static size_t staged_smem(const ndpb_table *t)
 template <int MODE>
 static int launch_staged(ndpb_table *t, const StagedArgs &A, long long items, cudaStream_t st)
 {
-    if (t->opt_staged == 2) CU(ndp_launch_staged(A, t->g.naxes, MODE, t->sm_count, items, staged_smem(t), st));
-    else CU(ndp_launch_pf(A, t->g.naxes, MODE, t->sm_count, items, ((size_t) t->nticks * 8 + 15) & ~(size_t) 15, st));
+    CU(ndp_launch_staged(A, t->g.naxes, MODE, t->sm_count, items, staged_smem(t), st));
     t->st_launches++;
     return NDPB_OK;
 }

@@ -60,6 +60,7 @@ struct NdpGeom {
     int vstride32[NDP_MAX_AXES];      // 32-bit copies of vstride / cstride, valid when small != 0
     int cstride32[NDP_MAX_AXES];
     int small;                        // every vertex and cell index fits in 31 bits
+    double inv_bstride[NDP_MAX_AXES]; // 1.0 / bstride: first guess of the vertex-id decode (then fixed up exactly)
 };
 
 // Bit-packed occupancy pyramid over the basic lattice.  Level 0 = one bit per
@@ -90,6 +91,21 @@ struct NdpTopo {
 NDP_HD bool ndp_bit(const uint32_t *bits, int i)
 {
     return (bits[i >> 5] >> (i & 31)) & 1u;
+}
+
+// Basic vertex id -> coordinates (src/ndpolator.c:235-237), without integer division:
+// the quotient is guessed in floating point and corrected by at most one, which is exact.
+NDP_HD void ndp_decode_vertex(const NdpGeom &g, int vertex, int *coords)
+{
+    int rem = vertex;
+    for (int a = 0; a < g.nbasic; a++) {
+        const int d = g.bstride[a];
+        int q = (int) ((double) rem * g.inv_bstride[a]);
+        int r = rem - q * d;
+        if (r < 0) { q--; r += d; } else if (r >= d) { q++; r -= d; }
+        coords[a] = q;
+        rem = r;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -388,6 +404,8 @@ struct NdpHit {
     double dsel;     // its selection metric
     int status;
     int hard;        // 1 when step (2) ran
+    int has_coords;  // coords[] below already holds the basic coordinates of `vertex`
+    int coords[NDP_MAX_AXES];
 };
 
 // N > 0: number of axes known at compile time (everything stays in registers).
@@ -450,6 +468,10 @@ NDP_HD bool ndp_search_fast(const NdpGeom &g, const NdpPyramid &P, int mode_rt, 
         }
     if (!ok) return false;
     hit.vertex = flat; hit.dsel = d0; hit.status = NDP_SEARCH_OK; hit.hard = 0;
+#pragma unroll
+    for (int a = 0; a < M; a++)
+        if (a < nb) hit.coords[a] = c[a];
+    hit.has_coords = 1;
     return true;
 }
 
@@ -731,7 +753,7 @@ NDP_HD void ndp_search_descend(const NdpGeom &g, const NdpPyramid &F, const NdpP
             if (hit.status != NDP_SEARCH_EMPTY && hit.vertex >= 0) {
                 // the closed-form axes must also be strict minimisers of the rounded total
                 int c[NDP_MAX_AXES];
-                for (int a = 0; a < nb; a++) c[a] = (hit.vertex / g.bstride[a]) % g.len[a];
+                ndp_decode_vertex(g, hit.vertex, c);
                 for (int a = 0; a < nb && ok; a++) {
                     if (is_var[a]) continue;
                     const int keep = c[a];
@@ -770,7 +792,7 @@ NDP_HD void ndp_scan_sentinel(const NdpPyramid &P, int mode, NdpHit &hit)
 // associated ticks.
 NDP_HD void ndp_coords_of(const NdpGeom &g, const NdpQuery &Q, int vertex, int *coords)
 {
-    for (int a = 0; a < g.nbasic; a++) coords[a] = (vertex / g.bstride[a]) % g.len[a];
+    ndp_decode_vertex(g, vertex, coords);
     for (int a = g.nbasic; a < g.naxes; a++) coords[a] = Q.acoord[a];
 }
 

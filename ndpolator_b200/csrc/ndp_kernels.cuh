@@ -236,7 +236,10 @@ __device__ __forceinline__ void ndp_publish(const SearchArgs &A, const NdpQuery 
         ndp_coords_of(g, Q, 0, coords);
         dist = 1e10;
     } else {
-        ndp_coords_of(g, Q, hit.vertex, coords);
+        if (hit.has_coords) {
+            for (int a = 0; a < g.nbasic; a++) coords[a] = hit.coords[a];
+            for (int a = g.nbasic; a < g.naxes; a++) coords[a] = Q.acoord[a];
+        } else ndp_coords_of(g, Q, hit.vertex, coords);
         dist = (mode >= NDP_MODE_LS_NEAREST) ? hit.dsel : ndp_reported_dist(g, A.method, Q, coords);
     }
     A.chosen[t] = hit.vertex;
@@ -269,8 +272,11 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant
             NdpQuery Q;
             ndp_make_query(g, idx, nrm, Q);
             NdpHit hit;
+            hit.has_coords = 0;
             if (ndp_search_fast<N, MODE>(g, *A.F, mode, Q, hit)) {
+                const int v0 = hit.vertex;
                 ndp_scan_sentinel(*A.F, mode, hit);
+                if (hit.vertex != v0) hit.has_coords = 0;
                 ndp_publish(A, Q, t, i, hit);
             } else hard = true;
         }
@@ -303,6 +309,7 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_hard(const __grid_constant
         NdpQuery Q;
         ndp_make_query(g, idx, nrm, Q);
         NdpHit hit;
+        hit.has_coords = 0;
         ndp_search_descend(g, *A.F, *A.R, mode, Q, A.have_topo ? &A.topo : nullptr, hit);
         if (hit.status == NDP_SEARCH_TIE) {
             // provisional (valid) vertex so that k_finish stays in bounds; redone once the topology exists
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_brute(const __grid_constan
             if (ob >= 0 && (best < 0 || od < bestd || (od == bestd && ob < best))) { best = ob; bestd = od; }
         }
         if (lane == 0) {
-            NdpHit hit; hit.vertex = best; hit.dsel = bestd; hit.status = NDP_SEARCH_OK; hit.hard = 0;
+            NdpHit hit; hit.vertex = best; hit.dsel = bestd; hit.status = NDP_SEARCH_OK; hit.hard = 0; hit.has_coords = 0;
             ndp_publish(A, Q, t, i, hit);
         }
     }
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __
         ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
         int coords[NDP_MAX_AXES];
         const int vertex = A.chosen[t];
-        for (int a = 0; a < g.nbasic; a++) coords[a] = (vertex / g.bstride[a]) % g.len[a];
+        ndp_decode_vertex(g, vertex, coords);
         for (int a = g.nbasic; a < n; a++)
             coords[a] = ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
         for (int k = 0; k < V; k++)
@@ -418,10 +425,10 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __
 // so there is no block-wide synchronisation in the loop and memory-level
 // parallelism no longer depends on register-limited occupancy.
 //
-// Lane pairs cooperate on their two blocks so that every 16-byte cp.async of a
-// pair lands in the same 32-byte sector (full-sector requests to L2, no
-// over-fetch).  Slots are padded by 16 bytes so that the 128-bit shared loads of
-// a quarter-warp fall into distinct bank groups.
+// The copy is cooperative: each cell is fetched by 2^(N-1) consecutive lanes with
+// one 16-byte cp.async each, so the memory system sees one contiguous request per
+// cell.  Slots are padded by 16 bytes so that the 128-bit shared loads of a
+// quarter-warp fall into distinct bank groups.
 //
 // (Round-1 note: the first version issued one cp.async.bulk per lane with an
 // mbarrier per warp; ncu showed the bulk copy takes uniform-register operands, so
@@ -520,9 +527,11 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
             } else {
                 const int vertex = A.chosen[w];
                 it.issued = true;
+                int vc[NDP_MAX_AXES];
+                ndp_decode_vertex(g, vertex, vc);
 #pragma unroll
                 for (int a = 0; a < N; a++) {
-                    const int c = (a < g.nbasic) ? (vertex / g.bstride[a]) % g.len[a]
+                    const int c = (a < g.nbasic) ? vc[a]
                                                  : ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
                     const int sup = c > 1 ? c : 1;                      // :601
                     it.x[a] = nrm[a] + (double) (idx[a] - c);           // :621-622
@@ -530,20 +539,25 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
                 }
             }
         }
-        // the pair (lane & ~1, lane | 1) copies its two cells together: in step k both lanes fetch
-        // the two halves of one 32-byte sector of cell u
+        // Cooperative copy: a cell is fetched by LPB consecutive lanes, 16 bytes each, i.e. as ONE
+        // contiguous (8 << N)-byte request -- measured on B200 (tools/probe_gather.cu), random
+        // 256-byte blocks fetched this way stream at the full HBM rate (27 G blocks/s), 5.5x the rate
+        // of one thread walking its own block with sixteen 128-bit loads.
+        constexpr int LPB = CHUNKS < 32 ? CHUNKS : 32;      // lanes per cell
+        constexpr int BPI = 32 / LPB;                       // cells per instruction
         const unsigned long long mine = it.issued ? (unsigned long long) (A.cells + (cell << N)) : 0ull;
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, 1);
-        const unsigned half = lane & 1u;
+        const unsigned sub = lane % LPB, grp = lane / LPB;
 #pragma unroll
-        for (int k = 0; k < CHUNKS; k++) {
-            const unsigned u = (unsigned) k / (CHUNKS / 2);             // whose cell: 0 = even lane's, 1 = odd lane's
-            const unsigned sector = (unsigned) k % (CHUNKS / 2);
-            const unsigned chunk = 2u * sector + half;
-            const unsigned long long src = (u == half) ? mine : other;
+        for (int k = 0; k < 32 / BPI; k++) {
+            const unsigned owner = (unsigned) k * BPI + grp;
+            const unsigned long long src = __shfl_sync(0xffffffffu, mine, owner);
             if (src) {
-                const unsigned dst = ndp_smem_u32(slot_of(st, (lane & ~1u) + u)) + chunk * 16u;
-                ndp_cp_async16(dst, reinterpret_cast<const unsigned char *>(src) + chunk * 16u);
+#pragma unroll
+                for (int c = 0; c < CHUNKS / LPB; c++) {    // cells wider than 512 bytes take several sweeps
+                    const unsigned chunk = sub + (unsigned) c * LPB;
+                    ndp_cp_async16(ndp_smem_u32(slot_of(st, owner)) + chunk * 16u,
+                                   reinterpret_cast<const unsigned char *>(src) + chunk * 16u);
+                }
             }
         }
         ndp_cp_async_commit();
@@ -605,123 +619,4 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
     }
 }
 
-// ---------------------------------------------------------------------------
-// Prefetch-pipelined gather: k_gather_pf
-//
-// Same work split as k_gather_staged, but the look-ahead costs neither shared
-// memory nor registers: while the current query is being reduced, the thread has
-// already imported its NEXT query and asked L2 for that query's cell
-// (prefetch.global.L2 on its two 128-byte lines).  One iteration later the
-// 128-bit loads of that cell hit L2 instead of paying the DRAM round trip.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void ndp_prefetch_l2(const void *p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-template <int N>
-struct NdpPfItem {
-    long long i;                       // query id (-1: idle)
-    const double *cell;                // nullptr: nothing to gather
-    double x[N];
-    unsigned pinmask, selbits;
-};
-
-template <int N, int MODE>
-__global__ void __launch_bounds__(128, (N <= 5 ? 4 : 1)) k_gather_pf(const __grid_constant__ StagedArgs A)
-{
-    constexpr unsigned CELL_BYTES = 8u << N;
-    extern __shared__ __align__(16) unsigned char ndp_smem[];
-    const NdpGeom &g = A.g;
-    const unsigned lane = threadIdx.x & 31;
-    double *s_ticks = reinterpret_cast<double *>(ndp_smem);
-    for (int i = threadIdx.x; i < A.nticks; i += blockDim.x) s_ticks[i] = A.ticks[i];
-    __syncthreads();
-
-    const long long total = (MODE == 0) ? A.n : (long long) A.ctr->n_off;
-    const long long stride = (long long) gridDim.x * blockDim.x;
-    const long long rounds = (total + stride - 1) / stride;
-    const long long w0 = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-
-    auto prepare = [&](long long w, NdpPfItem<N> &it) {
-        it.i = -1; it.cell = nullptr; it.pinmask = 0; it.selbits = 0;
-        if (w >= total) return;
-        const long long i = (MODE == 0) ? w : (long long) A.offlist[w];
-        it.i = i;
-        int idx[N], flg[N];
-        double nrm[N];
-        ndp_import_query<N>(g, s_ticks, A.q + i * N, idx, flg, nrm);
-        long long cell = 0;
-        bool gather = true;
-        if (MODE == 0) {
-            gather = !ndp_classify<N>(g, flg, nrm, it.pinmask, it.selbits);
-            if (g.small) {
-                int c32 = 0;
-#pragma unroll
-                for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; c32 += (idx[a] - 1) * g.cstride32[a]; }
-                cell = c32;
-            } else {
-#pragma unroll
-                for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; cell += (long long) (idx[a] - 1) * g.cstride[a]; }
-            }
-        } else {
-            const int vertex = A.chosen[w];
-#pragma unroll
-            for (int a = 0; a < N; a++) {
-                const int c = (a < g.nbasic) ? (vertex / g.bstride[a]) % g.len[a]
-                                             : ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
-                const int sup = c > 1 ? c : 1;                      // :601
-                it.x[a] = nrm[a] + (double) (idx[a] - c);           // :621-622
-                cell += (long long) (sup - 1) * g.cstride[a];
-            }
-        }
-        if (gather) {
-            it.cell = A.cells + (cell << N);
-#pragma unroll
-            for (unsigned off = 0; off < CELL_BYTES; off += 128u)
-                ndp_prefetch_l2(reinterpret_cast<const unsigned char *>(it.cell) + off);
-        }
-    };
-
-    auto finish = [&](const NdpPfItem<N> &it) {
-        bool need_search = false;
-        if (it.i >= 0) {
-            bool fdhc = false;
-            if (it.cell) {
-                const double2 *b2 = reinterpret_cast<const double2 *>(it.cell);
-                bool bad = false;
-                const double val = ndp_cell_reduce<N>([&](double *fv) {
-#pragma unroll
-                    for (int j = 0; j < (1 << N) / 2; j++) { double2 p = b2[j]; fv[2 * j] = p.x; fv[2 * j + 1] = p.y; }
-                }, it.x, it.pinmask, it.selbits, bad);
-                fdhc = !bad;
-                if (MODE == 1 || fdhc) A.interps[it.i] = val;
-            }
-            if (MODE == 0) {
-                if (fdhc) A.dists[it.i] = 0.0;
-                else if (A.method == NDP_M_NONE) { A.interps[it.i] = qnan; A.dists[it.i] = 0.0; }
-                else need_search = true;
-            }
-        }
-        if (MODE == 0) {
-            const unsigned votes = __ballot_sync(0xffffffffu, need_search);
-            if (votes) {
-                int base = 0;
-                const int leader = __ffs(votes) - 1;
-                if ((int) lane == leader) base = atomicAdd(&A.ctr->n_off, __popc(votes));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (need_search) A.offlist[base + __popc(votes & ((1u << lane) - 1u))] = (int) it.i;
-            }
-        }
-    };
-
-    NdpPfItem<N> cur, nxt;
-    prepare(w0, cur);
-    for (long long r = 0; r < rounds; r++) {
-        prepare(w0 + (r + 1) * stride, nxt);      // beyond the end: idle item
-        finish(cur);
-        cur = nxt;
-    }
-}
 #endif  // NDP_TU_STAGED

@@ -19,37 +19,6 @@ static cudaError_t go(const StagedArgs &A, int sm_count, long long items, size_t
     return cudaGetLastError();
 }
 
-template <int N, int MODE>
-static cudaError_t go_pf(const StagedArgs &A, int sm_count, long long items, size_t ticks_bytes, cudaStream_t st)
-{
-    int per_sm = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather_pf<N, MODE>, 128, ticks_bytes);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    const long long want = (items + 127) / 128;
-    const int blocks = (int) std::max<long long>(1, std::min<long long>(want, (long long) sm_count * per_sm));
-    k_gather_pf<N, MODE><<<blocks, 128, ticks_bytes, st>>>(A);
-    return cudaGetLastError();
-}
-
-template <int MODE>
-static cudaError_t pf_by_axes(const StagedArgs &A, int naxes, int sm_count, long long items, size_t ticks_bytes, cudaStream_t st)
-{
-    switch (naxes) {
-    case 2: return go_pf<2, MODE>(A, sm_count, items, ticks_bytes, st);
-    case 3: return go_pf<3, MODE>(A, sm_count, items, ticks_bytes, st);
-    case 4: return go_pf<4, MODE>(A, sm_count, items, ticks_bytes, st);
-    case 5: return go_pf<5, MODE>(A, sm_count, items, ticks_bytes, st);
-    default: return go_pf<6, MODE>(A, sm_count, items, ticks_bytes, st);
-    }
-}
-
-cudaError_t ndp_launch_pf(const StagedArgs &A, int naxes, int mode, int sm_count, long long items, size_t ticks_bytes, cudaStream_t st)
-{
-    return mode == 0 ? pf_by_axes<0>(A, naxes, sm_count, items, ticks_bytes, st)
-                     : pf_by_axes<1>(A, naxes, sm_count, items, ticks_bytes, st);
-}
-
 template <int MODE>
 static cudaError_t by_axes(const StagedArgs &A, int naxes, int sm_count, long long items, size_t smem, cudaStream_t st)
 {

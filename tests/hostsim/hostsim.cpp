@@ -139,6 +139,7 @@ extern "C" void *hs_create(int naxes, int nbasic, const int *axlen, const double
     }
     g.small = (nall < (1LL << 31) - 64) ? 1 : 0;
     for (int a = 0; a < naxes; a++) { g.vstride32[a] = g.small ? (int) g.vstride[a] : 0; g.cstride32[a] = g.small ? (int) g.cstride[a] : 0; }
+    for (int a = 0; a < nbasic; a++) g.inv_bstride[a] = 1.0 / (double) g.bstride[a];
     if (!grid) return t;
     t->grid.assign(grid, grid + nall * vdim);
     // masks: mirrors k_vmask_bits / k_hcmask_bits
@@ -253,6 +254,7 @@ static void search_one_n(HsTable *t, const double *qrow, int method, int search,
     ndp_import_query<0>(g, t->ticks.data(), qrow, idx, flg, nrm);
     NdpQuery Q; ndp_make_query(g, idx, nrm, Q);
     NdpHit hit;
+    hit.has_coords = 0;
     bool fast;
     switch (mode) {      // mirrors the dispatch of k_search_fast<N, MODE>
     case 0: fast = ndp_search_fast<N, 0>(g, t->pyr[m].dev, mode, Q, hit); break;
@@ -323,7 +325,7 @@ static void ndpolate_n(HsTable *t, long long nq, const double *q, int method, in
         search_one(t, q + i * n, method, search, &vertex, &dists[i], coords);
         // mirrors k_finish: coords are re-derived from the chosen vertex
         int c2[NDP_MAX_AXES];
-        for (int a = 0; a < g.nbasic; a++) c2[a] = (vertex / g.bstride[a]) % g.len[a];
+        ndp_decode_vertex(g, vertex, c2);
         for (int a = g.nbasic; a < n; a++) c2[a] = ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
         for (int k = 0; k < V; k++)
             interps[i * V + k] = ndp_finish_component<N, CM, false>(g, t->grid.data(), cells, method, idx, nrm, c2, k);
