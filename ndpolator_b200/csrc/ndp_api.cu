@@ -385,7 +385,7 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
         return NDPB_OK;
     }
     if (k == "staged") {
-        if (value < 0 || value > 1) return fail(NDPB_ERR_INVALID, "staged must be 0 (auto) or 1 (off)");
+        if (value < 0 || value > 2) return fail(NDPB_ERR_INVALID, "staged must be 0 (auto: one stage, many warps), 1 (off) or 2 (two-stage ring)");
         t->opt_staged = (int) value;
         return NDPB_OK;
     }
@@ -604,17 +604,19 @@ static bool staged_ok(const ndpb_table *t)
            (size_t) t->nticks * sizeof(double) <= 16 * 1024;
 }
 
+static int staged_stages(const ndpb_table *t) { return t->opt_staged == 2 ? 2 : 1; }
+
 static size_t staged_smem(const ndpb_table *t)
 {
     const size_t ticks = ((size_t) t->nticks * 8 + 127) & ~(size_t) 127;
     const size_t slot = ((size_t) 8 << t->g.naxes) + 16;
-    return ticks + (size_t) NDP_STAGED_WARPS * NDP_STAGED_STAGES * 32 * slot;
+    return ticks + (size_t) NDP_STAGED_WARPS * staged_stages(t) * 32 * slot;
 }
 
 template <int MODE>
 static int launch_staged(ndpb_table *t, const StagedArgs &A, long long items, cudaStream_t st)
 {
-    CU(ndp_launch_staged(A, t->g.naxes, MODE, t->sm_count, items, staged_smem(t), st));
+    CU(ndp_launch_staged(A, t->g.naxes, MODE, staged_stages(t), t->sm_count, items, staged_smem(t), st));
     t->st_launches++;
     return NDPB_OK;
 }

@@ -16,7 +16,9 @@
 
 #if defined(__CUDACC__)
 #define NDP_HD __host__ __device__ __forceinline__
+#define NDP_HD_CALL __host__ __device__ __noinline__      // big, rarely-hot helpers: keep the kernels' code small
 #else
+#define NDP_HD_CALL inline
 #define NDP_HD inline
 struct double2 { double x, y; };
 #endif
@@ -137,9 +139,12 @@ NDP_HD void ndp_import_axis_guess(const double *tick, int len, double inv_step, 
     const double rtol = 1e-6;
     if (inv_step > 0.0) {
         const double xr = x + rtol;
-        double gd = floor((xr - first) * inv_step) + 1.0;
-        gd = fmin(fmax(gd, 1.0), (double) (len - 1));          // a NaN guess becomes 1, like the bisection's answer
-        int l = (int) gd;
+        // truncation instead of floor only differs below the first tick, where the clamp decides anyway;
+        // a NaN or huge quotient converts to some integer, is clamped, and then fails or passes the
+        // verification below like any other guess
+        int l = (int) ((xr - first) * inv_step);
+        l = l < len - 2 ? l : len - 2;
+        l = l > 0 ? l + 1 : 1;
         double tl = tick[l], tp = tick[l - 1];
         // one corrective tick either way (the guess from the mean spacing is at most one off on near-uniform axes)
         const bool up = (xr > tl) && (l < len - 1);
@@ -219,10 +224,15 @@ NDP_HD double ndp_cell_reduce(Load load, const double *x, unsigned pinmask, unsi
     bool bad = false;
     if (result != result) {
         load(fv);
+        if (pinmask == 0) {
 #pragma unroll
-        for (int j = 0; j < (1 << N); j++) {
-            bool used = (((unsigned) j ^ selbits) & pinmask) == 0;
-            bad |= used && (fv[j] != fv[j]);
+            for (int j = 0; j < (1 << N); j++) bad |= (fv[j] != fv[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < (1 << N); j++) {
+                bool used = (((unsigned) j ^ selbits) & pinmask) == 0;
+                bad |= used && (fv[j] != fv[j]);
+            }
         }
     }
     nan_used = bad;
@@ -351,7 +361,7 @@ NDP_HD double ndp_tree_pos(const NdpGeom &g, int mode, int v, int ax)
 }
 
 // true when vertex A precedes vertex B (A != B) in the reference's traversal for query Q
-NDP_HD bool ndp_tree_beats(const NdpGeom &g, int mode, const NdpTopo &T, const NdpQuery &Q, int A, int B)
+NDP_HD_CALL bool ndp_tree_beats(const NdpGeom &g, int mode, const NdpTopo &T, const NdpQuery &Q, int A, int B)
 {
     int a = A, b = B, ca = -1, cb = -1;          // ca/cb: child of the meeting node on A's / B's side
     int da = T.depth[a], db = T.depth[b];
@@ -478,7 +488,7 @@ NDP_HD bool ndp_search_fast(const NdpGeom &g, const NdpPyramid &P, int mode_rt, 
 // Descent over pyramid P.  When P spans only some basic axes (the mask does not
 // depend on the others), fixed[] holds the coordinate of every other axis and the
 // descent runs on that slice; the metric still sums all basic axes in order.
-NDP_HD void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
+NDP_HD_CALL void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
                             const int *fixed, const NdpTopo *topo, NdpHit &hit, bool seeded = false)
 {
     const int nb = g.nbasic, nv = P.nvar;
@@ -590,7 +600,7 @@ NDP_HD void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, con
 // final once it is strictly below LB_R (equality keeps going: ties matter).
 // Returns true when proven; otherwise leaves the best so far in `hit` as a seed
 // (hit.vertex < 0: nothing found yet) after about `budget` rows.
-NDP_HD bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
+NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
                             const int *fixed, const NdpTopo *topo, int budget, NdpHit &hit)
 {
     const int nb = g.nbasic, nv = P.nvar;

@@ -439,7 +439,6 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __
 // MODE 1: the k_finish work for LINEAR extrapolation (cell below the found corner)
 // ---------------------------------------------------------------------------
 #define NDP_STAGED_WARPS 4
-#define NDP_STAGED_STAGES 2
 
 struct StagedArgs {
     NdpGeom g;
@@ -472,8 +471,11 @@ struct NdpStagedItem {                 // what a lane keeps between issuing a ti
     bool issued;                       // this lane's cell is being copied
 };
 
-template <int N, int MODE>
-__global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gather_staged(const __grid_constant__ StagedArgs A)
+// STAGES == 2: each warp overlaps its own copy with its own next import (fewer, fatter warps);
+// STAGES == 1: no intra-warp overlap, twice the resident warps hide the latency instead.
+template <int N, int MODE, int STAGES>
+__global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? (STAGES == 1 ? 5 : 3) : 1))
+k_gather_staged(const __grid_constant__ StagedArgs A)
 {
     constexpr unsigned CELL_BYTES = 8u << N;
     constexpr unsigned SLOT = CELL_BYTES + 16u;
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
 
     // slot of lane L in stage st of this warp
     auto slot_of = [&](int st, unsigned L) -> unsigned char * {
-        return s_slots + ((size_t) (warp * NDP_STAGED_STAGES + st) * 32 + L) * SLOT;
+        return s_slots + ((size_t) (warp * STAGES + st) * 32 + L) * SLOT;
     };
 
     const long long total = (MODE == 0) ? A.n : (long long) A.ctr->n_off;
@@ -545,19 +547,22 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
         // of one thread walking its own block with sixteen 128-bit loads.
         constexpr int LPB = CHUNKS < 32 ? CHUNKS : 32;      // lanes per cell
         constexpr int BPI = 32 / LPB;                       // cells per instruction
-        const unsigned long long mine = it.issued ? (unsigned long long) (A.cells + (cell << N)) : 0ull;
+        // owners broadcast their cell number (one 32-bit shuffle when the table is small enough)
         const unsigned sub = lane % LPB, grp = lane / LPB;
+        const unsigned dst0 = ndp_smem_u32(slot_of(st, grp)) + sub * 16u;
+        const unsigned char *src0 = reinterpret_cast<const unsigned char *>(A.cells) + sub * 16u;
+        const long long mine = it.issued ? cell : -1;
 #pragma unroll
         for (int k = 0; k < 32 / BPI; k++) {
             const unsigned owner = (unsigned) k * BPI + grp;
-            const unsigned long long src = __shfl_sync(0xffffffffu, mine, owner);
-            if (src) {
+            long long oc;
+            if (g.small) oc = __shfl_sync(0xffffffffu, (int) mine, owner);
+            else oc = __shfl_sync(0xffffffffu, mine, owner);
+            if (oc >= 0) {
 #pragma unroll
-                for (int c = 0; c < CHUNKS / LPB; c++) {    // cells wider than 512 bytes take several sweeps
-                    const unsigned chunk = sub + (unsigned) c * LPB;
-                    ndp_cp_async16(ndp_smem_u32(slot_of(st, owner)) + chunk * 16u,
-                                   reinterpret_cast<const unsigned char *>(src) + chunk * 16u);
-                }
+                for (int c = 0; c < CHUNKS / LPB; c++)      // cells wider than 512 bytes take several sweeps
+                    ndp_cp_async16(dst0 + (unsigned) k * BPI * SLOT + (unsigned) c * LPB * 16u,
+                                   src0 + oc * (long long) CELL_BYTES + (long long) c * LPB * 16);
             }
         }
         ndp_cp_async_commit();
@@ -596,7 +601,18 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
         }
     };
 
-    NdpStagedItem<N> item[NDP_STAGED_STAGES];
+    if (STAGES == 1) {
+        NdpStagedItem<N> item;
+        for (long long tile = tile0; tile < ntiles; tile += tile_stride) {
+            produce(tile, 0, item);
+            ndp_cp_async_wait<0>();
+            __syncwarp();                      // the other lanes' copies into my slot are visible
+            consume(0, item);
+            __syncwarp();                      // the slots may be overwritten by the next tile's copies
+        }
+        return;
+    }
+    NdpStagedItem<N> item[2];
     if (tile0 < ntiles) produce(tile0, 0, item[0]);
     int st = 0;
     for (long long tile = tile0; tile < ntiles; tile += tile_stride) {
@@ -604,19 +620,18 @@ __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? 3 : 1)) k_gat
         // one commit per iteration (possibly empty) keeps the group count uniform: everything
         // but the newest group -- the tile being consumed included -- is complete after wait<1>
         if (st == 0) {
-            if (next < ntiles) produce(next, 1, item[1]); else ndp_cp_async_commit();
+            if (next < ntiles) produce(next, STAGES - 1, item[1]); else ndp_cp_async_commit();
             ndp_cp_async_wait<1>();
-            __syncwarp();                      // the partner lane's copies into my slot are visible
+            __syncwarp();
             consume(0, item[0]);
         } else {
             if (next < ntiles) produce(next, 0, item[0]); else ndp_cp_async_commit();
             ndp_cp_async_wait<1>();
             __syncwarp();
-            consume(1, item[1]);
+            consume(STAGES - 1, item[1]);
         }
-        __syncwarp();                          // slots of this stage are free for the pair to overwrite
+        __syncwarp();
         st ^= 1;
     }
 }
-
 #endif  // NDP_TU_STAGED
