@@ -16,7 +16,7 @@
 
 #if defined(__CUDACC__)
 #define NDP_HD __host__ __device__ __forceinline__
-#define NDP_HD_CALL __host__ __device__ __noinline__      // big, rarely-hot helpers: keep the kernels' code small
+#define NDP_HD_CALL static __host__ __device__ __noinline__      // big, rarely-hot helpers: keep the kernels' code small
 #else
 #define NDP_HD_CALL inline
 #define NDP_HD inline
