@@ -65,6 +65,7 @@ struct Slot {                               // one in-flight batch
     double *q = nullptr, *interps = nullptr, *dists = nullptr;     // staging (host callers only)
     int *coords = nullptr;
     int *list = nullptr, *chosen = nullptr, *tielist = nullptr, *hardlist = nullptr;
+    int *rec_idx = nullptr; double *rec_nrm = nullptr;             // import products of the off-grid queries
     long long cap_q = 0, cap_work = 0, cap_coords = 0;
     NdpCounters *ctr = nullptr;             // device
     NdpCounters *ctr_host = nullptr;        // pinned
@@ -213,6 +214,7 @@ static void free_slot(Slot &s)
 {
     cudaFree(s.q); cudaFree(s.interps); cudaFree(s.dists); cudaFree(s.coords);
     cudaFree(s.list); cudaFree(s.chosen); cudaFree(s.tielist); cudaFree(s.hardlist); cudaFree(s.ctr);
+    cudaFree(s.rec_idx); cudaFree(s.rec_nrm);
     if (s.ctr_host) cudaFreeHost(s.ctr_host);
     cudaEvent_t *ev[] = {&s.in_done, &s.searched, &s.out_ready, &s.out_done, &s.t0, &s.t1, &s.t2, &s.t3};
     for (auto e : ev) if (*e) cudaEventDestroy(*e);
@@ -566,11 +568,14 @@ static int ensure_slot(ndpb_table *t, Slot &s, long long nq, bool stage_q, bool 
     if (work && nq > s.cap_work) {
         CU(cudaStreamSynchronize(t->s_compute));
         cudaFree(s.list); cudaFree(s.chosen); cudaFree(s.tielist); cudaFree(s.hardlist);
-        s.list = s.chosen = s.tielist = s.hardlist = nullptr; s.cap_work = 0;
+        cudaFree(s.rec_idx); cudaFree(s.rec_nrm);
+        s.list = s.chosen = s.tielist = s.hardlist = s.rec_idx = nullptr; s.rec_nrm = nullptr; s.cap_work = 0;
         CU(cudaMalloc(&s.list, sizeof(int) * nq));
         CU(cudaMalloc(&s.chosen, sizeof(int) * nq));
         CU(cudaMalloc(&s.tielist, sizeof(int) * nq));
         CU(cudaMalloc(&s.hardlist, sizeof(int) * nq));
+        CU(cudaMalloc(&s.rec_idx, sizeof(int) * nq * g.naxes));
+        CU(cudaMalloc(&s.rec_nrm, sizeof(double) * nq * g.naxes));
         s.cap_work = nq;
     }
     return NDPB_OK;
@@ -666,6 +671,7 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
     StagedArgs G{};
     G.g = t->g; G.ticks = t->ticks; G.nticks = t->nticks; G.cells = t->cells; G.q = q; G.n = n;
     G.interps = interps; G.dists = dists; G.method = method; G.offlist = s.list; G.chosen = s.chosen; G.ctr = s.ctr;
+    G.rec_idx = s.rec_idx; G.rec_nrm = s.rec_nrm;
     if (task == TASK_NDPOLATE && staged_ok(t)) {
         int rc = launch_staged<0>(t, G, n, st);
         if (rc) return rc;
@@ -674,6 +680,7 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
         M.g = t->g; M.ticks = t->ticks; M.nticks = t->nticks; M.ticks_in_smem = ticks_in_smem(t);
         M.grid = t->grid; M.cells = t->cells; M.q = q; M.n = n;
         M.interps = interps; M.dists = dists; M.method = method; M.offlist = s.list; M.ctr = s.ctr;
+        M.rec_idx = s.rec_idx; M.rec_nrm = s.rec_nrm;
         int rc = launch_main(t, M, st);
         if (rc) return rc;
     }
@@ -686,6 +693,7 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
         S.count = (task == TASK_NDPOLATE) ? &s.ctr->n_off : nullptr;
         S.count_host = n;
         S.chosen = s.chosen; S.dists = dists; S.coords = coords; S.hardlist = s.hardlist; S.tielist = s.tielist; S.ctr = s.ctr;
+        S.rec_idx = s.rec_idx; S.rec_nrm = s.rec_nrm;
         int rc = launch_search(t, S, n, false, st);
         if (rc) return rc;
         if (!use_brute(t, search)) {                  // pass 2: whatever pass 1 could not prove
@@ -702,7 +710,7 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
         FinishArgs F{};
         F.g = t->g; F.ticks = t->ticks; F.nticks = t->nticks; F.ticks_in_smem = ticks_in_smem(t);
         F.grid = t->grid; F.cells = t->cells; F.q = q; F.method = method;
-        F.list = s.list; F.sublist = nullptr; F.count = &s.ctr->n_off; F.chosen = s.chosen; F.interps = interps;
+        F.list = s.list; F.rec_idx = s.rec_idx; F.rec_nrm = s.rec_nrm; F.sublist = nullptr; F.count = &s.ctr->n_off; F.chosen = s.chosen; F.interps = interps;
         int rc = launch_finish(t, F, st);
         if (rc) return rc;
     }
@@ -735,13 +743,14 @@ static int batch_complete(ndpb_table *t, Slot &s, Task task, const double *q, lo
         S.list = (task == TASK_NDPOLATE) ? s.list : nullptr;
         S.sublist = s.tielist; S.count = &s.ctr->n_tie; S.count_host = 0;
         S.chosen = s.chosen; S.dists = dists; S.coords = coords; S.hardlist = s.hardlist; S.tielist = s.tielist; S.ctr = s.ctr;
+        S.rec_idx = s.rec_idx; S.rec_nrm = s.rec_nrm;
         rc = launch_search(t, S, c.n_tie, true, st);
         if (rc) return rc;
         if (task == TASK_NDPOLATE) {
             FinishArgs F{};
             F.g = t->g; F.ticks = t->ticks; F.nticks = t->nticks; F.ticks_in_smem = ticks_in_smem(t);
             F.grid = t->grid; F.cells = t->cells; F.q = q; F.method = method;
-            F.list = s.list; F.sublist = s.tielist; F.count = &s.ctr->n_tie; F.chosen = s.chosen; F.interps = interps;
+            F.list = s.list; F.rec_idx = s.rec_idx; F.rec_nrm = s.rec_nrm; F.sublist = s.tielist; F.count = &s.ctr->n_tie; F.chosen = s.chosen; F.interps = interps;
             rc = launch_finish(t, F, st);
             if (rc) return rc;
         }

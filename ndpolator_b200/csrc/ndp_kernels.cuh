@@ -128,6 +128,7 @@ struct MainArgs {
     double *interps; double *dists;
     int method;
     int *offlist;             // ids of queries that need the search (method != NONE)
+    int *rec_idx; double *rec_nrm;   // import products of those queries, by list position (n x naxes), or nullptr
     NdpCounters *ctr;
 };
 
@@ -153,10 +154,10 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_main(const __gr
         const long long i = r * per_pass + (long long) blockIdx.x * (NDP_BLOCK / G) + threadIdx.x / G;
         const bool live = i < A.n;
         bool need_search = false;
+        int idx[N ? N : NDP_MAX_AXES], flg[N ? N : NDP_MAX_AXES];
+        double nrm[N ? N : NDP_MAX_AXES];
 
         if (live) {
-            int idx[N ? N : NDP_MAX_AXES], flg[N ? N : NDP_MAX_AXES];
-            double nrm[N ? N : NDP_MAX_AXES];
             ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
             unsigned pinmask, selbits;
             const bool oob = ndp_classify<N>(g, flg, nrm, pinmask, selbits);
@@ -220,6 +221,7 @@ struct SearchArgs {
     int *coords;            // optional (n x naxes) tap, per query id
     int *hardlist;          // positions whose fast path failed
     int *tielist;           // positions whose kd tie could not be settled yet
+    const int *rec_idx; const double *rec_nrm;   // import products by list position (valid when list != nullptr), or nullptr
     NdpCounters *ctr;
 };
 
@@ -268,7 +270,11 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant
             const long long i = A.list ? A.list[t] : t;
             int idx[N ? N : NDP_MAX_AXES], flg[N ? N : NDP_MAX_AXES];
             double nrm[N ? N : NDP_MAX_AXES];
-            ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
+            if (A.list && A.rec_idx) {
+#pragma unroll
+                for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
+                    if (a < n) { idx[a] = A.rec_idx[t * n + a]; nrm[a] = A.rec_nrm[t * n + a]; }
+            } else ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
             NdpQuery Q;
             ndp_make_query(g, idx, nrm, Q);
             NdpHit hit;
@@ -305,7 +311,9 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_hard(const __grid_constant
         const long long i = A.list ? A.list[t] : t;
         int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES];
         double nrm[NDP_MAX_AXES];
-        ndp_import_query<0>(g, tk, A.q + i * n, idx, flg, nrm);
+        if (A.list && A.rec_idx) {
+            for (int a = 0; a < n; a++) { idx[a] = A.rec_idx[t * n + a]; nrm[a] = A.rec_nrm[t * n + a]; }
+        } else ndp_import_query<0>(g, tk, A.q + i * n, idx, flg, nrm);
         NdpQuery Q;
         ndp_make_query(g, idx, nrm, Q);
         NdpHit hit;
@@ -383,6 +391,7 @@ struct FinishArgs {
     const int *sublist;     // positions into list to redo (after tie resolution), or nullptr
     const int *count;       // device count of work items (of sublist when given)
     const int *chosen;
+    const int *rec_idx; const double *rec_nrm;   // import products by list position, or nullptr
     double *interps;
 };
 
@@ -401,7 +410,11 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __
         const long long i = A.list[t];
         int idx[N ? N : NDP_MAX_AXES], flg[N ? N : NDP_MAX_AXES];
         double nrm[N ? N : NDP_MAX_AXES];
-        ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
+        if (A.rec_idx) {
+#pragma unroll
+            for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
+                if (a < n) { idx[a] = A.rec_idx[t * n + a]; nrm[a] = A.rec_nrm[t * n + a]; }
+        } else ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
         int coords[NDP_MAX_AXES];
         const int vertex = A.chosen[t];
         ndp_decode_vertex(g, vertex, coords);
@@ -449,6 +462,7 @@ struct StagedArgs {
     int method;
     int *offlist;                      // MODE 0: out; MODE 1: in (query id per work item)
     const int *chosen;                 // MODE 1: winning vertex per work item
+    int *rec_idx; double *rec_nrm;     // import products by list position: MODE 0 writes, MODE 1 reads (nullptr: re-import)
     NdpCounters *ctr;
 };
 
@@ -466,6 +480,7 @@ __device__ __forceinline__ void ndp_cp_async_wait() { asm volatile("cp.async.wai
 template <int N>
 struct NdpStagedItem {                 // what a lane keeps between issuing a tile and reducing it
     long long i;                       // query id (-1: lane idle)
+    int idx[N];                        // MODE 0: superior corner indices (for the off-grid record)
     double x[N];                       // interpolation weights
     unsigned pinmask, selbits;
     bool issued;                       // this lane's cell is being copied
@@ -513,8 +528,13 @@ k_gather_staged(const __grid_constant__ StagedArgs A)
             it.i = i;
             int idx[N], flg[N];
             double nrm[N];
-            ndp_import_query<N>(g, s_ticks, A.q + i * N, idx, flg, nrm);
+            if (MODE == 1 && A.rec_idx) {
+#pragma unroll
+                for (int a = 0; a < N; a++) { idx[a] = A.rec_idx[w * N + a]; nrm[a] = A.rec_nrm[w * N + a]; }
+            } else ndp_import_query<N>(g, s_ticks, A.q + i * N, idx, flg, nrm);
             if (MODE == 0) {
+#pragma unroll
+                for (int a = 0; a < N; a++) it.idx[a] = idx[a];
                 const bool oob = ndp_classify<N>(g, flg, nrm, it.pinmask, it.selbits);
                 it.issued = !oob;
                 if (g.small) {
@@ -551,18 +571,29 @@ k_gather_staged(const __grid_constant__ StagedArgs A)
         const unsigned sub = lane % LPB, grp = lane / LPB;
         const unsigned dst0 = ndp_smem_u32(slot_of(st, grp)) + sub * 16u;
         const unsigned char *src0 = reinterpret_cast<const unsigned char *>(A.cells) + sub * 16u;
-        const long long mine = it.issued ? cell : -1;
+        if (g.small) {
+            const int mine = it.issued ? (int) cell : -1;
 #pragma unroll
-        for (int k = 0; k < 32 / BPI; k++) {
-            const unsigned owner = (unsigned) k * BPI + grp;
-            long long oc;
-            if (g.small) oc = __shfl_sync(0xffffffffu, (int) mine, owner);
-            else oc = __shfl_sync(0xffffffffu, mine, owner);
-            if (oc >= 0) {
+            for (int k = 0; k < 32 / BPI; k++) {
+                const int oc = __shfl_sync(0xffffffffu, mine, k * BPI + (int) grp);
+                if (oc >= 0) {
 #pragma unroll
-                for (int c = 0; c < CHUNKS / LPB; c++)      // cells wider than 512 bytes take several sweeps
-                    ndp_cp_async16(dst0 + (unsigned) k * BPI * SLOT + (unsigned) c * LPB * 16u,
-                                   src0 + oc * (long long) CELL_BYTES + (long long) c * LPB * 16);
+                    for (int c = 0; c < CHUNKS / LPB; c++)      // cells wider than 512 bytes take several sweeps
+                        ndp_cp_async16(dst0 + (unsigned) (k * BPI) * SLOT + (unsigned) (c * LPB) * 16u,
+                                       src0 + (long long) oc * (long long) CELL_BYTES + (long long) (c * LPB) * 16);
+                }
+            }
+        } else {
+            const long long mine = it.issued ? cell : -1;
+#pragma unroll
+            for (int k = 0; k < 32 / BPI; k++) {
+                const long long oc = __shfl_sync(0xffffffffu, mine, k * BPI + (int) grp);
+                if (oc >= 0) {
+#pragma unroll
+                    for (int c = 0; c < CHUNKS / LPB; c++)
+                        ndp_cp_async16(dst0 + (unsigned) (k * BPI) * SLOT + (unsigned) (c * LPB) * 16u,
+                                       src0 + oc * (long long) CELL_BYTES + (long long) (c * LPB) * 16);
+                }
             }
         }
         ndp_cp_async_commit();
@@ -596,7 +627,14 @@ k_gather_staged(const __grid_constant__ StagedArgs A)
                 const int leader = __ffs(votes) - 1;
                 if ((int) lane == leader) base = atomicAdd(&A.ctr->n_off, __popc(votes));
                 base = __shfl_sync(0xffffffffu, base, leader);
-                if (need_search) A.offlist[base + __popc(votes & ((1u << lane) - 1u))] = (int) it.i;
+                if (need_search) {
+                    const int pos = base + __popc(votes & ((1u << lane) - 1u));
+                    A.offlist[pos] = (int) it.i;
+                    if (A.rec_idx) {
+#pragma unroll
+                        for (int a = 0; a < N; a++) { A.rec_idx[(long long) pos * N + a] = it.idx[a]; A.rec_nrm[(long long) pos * N + a] = it.x[a]; }
+                    }
+                }
             }
         }
     };
