@@ -194,7 +194,12 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_main(const __gr
             const int leader = __ffs(votes) - 1;
             if ((int) lane == leader) base = atomicAdd(&A.ctr->n_off, __popc(votes));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (need_search) A.offlist[base + __popc(votes & ((1u << lane) - 1u))] = (int) i;
+            if (need_search) {
+                const int pos = base + __popc(votes & ((1u << lane) - 1u));
+                A.offlist[pos] = (int) i;
+                if (A.rec_idx)
+                    for (int a = 0; a < n; a++) { A.rec_idx[(long long) pos * n + a] = idx[a]; A.rec_nrm[(long long) pos * n + a] = nrm[a]; }
+            }
         }
     }
 }
