@@ -488,9 +488,11 @@ NDP_HD bool ndp_search_fast(const NdpGeom &g, const NdpPyramid &P, int mode_rt, 
 // Descent over pyramid P.  When P spans only some basic axes (the mask does not
 // depend on the others), fixed[] holds the coordinate of every other axis and the
 // descent runs on that slice; the metric still sums all basic axes in order.
-NDP_HD_CALL void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
+template <int MODE>
+NDP_HD_CALL void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode_rt, const NdpQuery &Q,
                             const int *fixed, const NdpTopo *topo, NdpHit &hit, bool seeded = false)
 {
+    const int mode = (MODE >= 0) ? MODE : mode_rt;
     const int nb = g.nbasic, nv = P.nvar;
     const unsigned nchild = 1u << nv;
     const int top = P.nlev - 1;
@@ -600,15 +602,18 @@ NDP_HD_CALL void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode
 // final once it is strictly below LB_R (equality keeps going: ties matter).
 // Returns true when proven; otherwise leaves the best so far in `hit` as a seed
 // (hit.vertex < 0: nothing found yet) after about `budget` rows.
-NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
+template <int MODE>
+NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode_rt, const NdpQuery &Q,
                             const int *fixed, const NdpTopo *topo, int budget, NdpHit &hit)
 {
+    const int mode = (MODE >= 0) ? MODE : mode_rt;
     const int nb = g.nbasic, nv = P.nvar;
     const bool cells = (mode == NDP_MODE_KD_LINEAR || mode == NDP_MODE_LS_LINEAR);
     const bool kd = mode < NDP_MODE_LS_NEAREST;
     const int lo = cells ? 1 : 0;
     int jof[NDP_MAX_AXES], p0[NDP_MAX_AXES];
     double tmin[NDP_MAX_AXES];        // per basic axis: the smallest term any admissible coordinate can give
+    double term[NDP_MAX_AXES];        // per basic axis: the term of the row being scanned (row axis: unused)
     int base = 0;
 
     hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_OK; hit.hard = 1;
@@ -616,7 +621,7 @@ NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode
     for (int a = 0; a < nb; a++) jof[a] = -1;
     for (int j = 0; j < nv; j++) jof[P.var_axis[j]] = j;
     for (int a = 0; a < nb; a++) {
-        if (jof[a] < 0) { tmin[a] = ndp_axis_term(mode, Q.qc[a], fixed[a], fixed[a]); base += fixed[a] * g.bstride[a]; continue; }
+        if (jof[a] < 0) { tmin[a] = ndp_axis_term(mode, Q.qc[a], fixed[a], fixed[a]); base += fixed[a] * g.bstride[a]; term[a] = tmin[a]; continue; }
         const double hi = (double) (g.len[a] - 1);
         double p = cells ? floor(Q.qc[a]) + 1.0 : rint(Q.qc[a]);
         p = p < (double) lo ? (double) lo : (p > hi ? hi : p);
@@ -627,29 +632,27 @@ NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode
         if (c - 1 >= lo && ndp_axis_term(mode, Q.qc[a], c - 1, c - 1) < t0) return false;
         if (c + 1 <= g.len[a] - 1 && ndp_axis_term(mode, Q.qc[a], c + 1, c + 1) < t0) return false;
         if (!(t0 == t0)) return false;
-        p0[jof[a]] = c; tmin[a] = t0;
+        p0[jof[a]] = c; tmin[a] = t0; term[a] = t0;
     }
     const int ns = nv - 1;                         // shell axes; the last pyramid axis is the row axis
     const int aL = P.var_axis[ns];
     const int lenL = g.len[aL];
+    const int strideL = g.bstride[aL];
+    const double qL = Q.qc[aL];
 
     int best = -1;
     double bestd = 0.0;
     bool tie = false;
     int rows = 0;
 
-    // scores the set coordinate c of the current row (row_vid = vertex id without the row axis);
-    // returns its metric
-    auto score = [&](const int *off, int row_vid, int c) -> double {
+    // scores the set coordinate c of the current row (row_vid = vertex id without the row axis):
+    // the ordered sum of the row's terms with the row axis' own term dropped in; returns the metric
+    auto score = [&](int row_vid, int c) -> double {
+        const double tL = ndp_axis_term(mode, qL, c, c);
         double d = 0.0;
-        for (int a = 0; a < nb; a++) {
-            const int j = jof[a];
-            if (j < 0) d += tmin[a];
-            else if (j == ns) d += ndp_axis_term(mode, Q.qc[a], c, c);
-            else d += ndp_axis_term(mode, Q.qc[a], p0[j] + off[j], p0[j] + off[j]);
-        }
+        for (int a = 0; a < nb; a++) d += (a == aL) ? tL : term[a];
         d = ndp_add_assoc(g, mode, Q, d);
-        const int vid = row_vid + c * g.bstride[aL];
+        const int vid = row_vid + c * strideL;
         if (best < 0 || d < bestd) { best = vid; bestd = d; tie = false; }
         else if (d == bestd && vid != best) {
             if (!kd) { if (vid < best) best = vid; }                     // _compare_indexed_dists, :101-112
@@ -676,18 +679,22 @@ NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode
             }
             if (cheb == R && inside) {
                 rows++;
+                for (int j = 0; j < ns; j++) {
+                    const int a = P.var_axis[j];
+                    term[a] = ndp_axis_term(mode, Q.qc[a], p0[j] + off[j], p0[j] + off[j]);
+                }
                 // Set coordinates of the row, outward from p0 on either side.  The metric grows
                 // (weakly, after rounding) with the distance from p0, so a side is exhausted as
                 // soon as a coordinate scores strictly above the best so far; equal scores keep
                 // going because ties are decided by the reference's rules, not by us.
                 int c = P.prevv[rowflat + p0[ns]];
                 while (c >= lo) {
-                    if (score(off, row_vid, c) > bestd) break;
+                    if (score(row_vid, c) > bestd) break;
                     c = (c - 1 >= lo) ? P.prevv[rowflat + c - 1] : -1;
                 }
                 c = (p0[ns] + 1 <= lenL - 1) ? P.nextv[rowflat + p0[ns] + 1] : -1;
                 while (c >= lo) {
-                    if (score(off, row_vid, c) > bestd) break;
+                    if (score(row_vid, c) > bestd) break;
                     c = (c + 1 <= lenL - 1) ? P.nextv[rowflat + c + 1] : -1;
                 }
             }
@@ -709,8 +716,9 @@ NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode
             for (int sgn = -1; sgn <= 1; sgn += 2) {
                 const int c = p0[j] + sgn * (R + 1);
                 if (c < lo || c > g.len[a] - 1) continue;
+                const double ta = ndp_axis_term(mode, Q.qc[a], c, c);
                 double d = 0.0;
-                for (int b = 0; b < nb; b++) d += (b == a) ? ndp_axis_term(mode, Q.qc[a], c, c) : tmin[b];
+                for (int b = 0; b < nb; b++) d += (b == a) ? ta : tmin[b];
                 d = ndp_add_assoc(g, mode, Q, d);
                 if (!any_beyond || d < lb) lb = d;
                 any_beyond = true;
@@ -733,15 +741,19 @@ NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode
 // both per axis and in the final rounded sum -- otherwise (exact half-way queries,
 // absorbed differences) the full-lattice descent decides.  R is the pyramid over
 // the variant axes only, F the full one.
-NDP_HD void ndp_search_descend(const NdpGeom &g, const NdpPyramid &F, const NdpPyramid &R, int mode,
+template <int MODE>
+NDP_HD void ndp_search_descend(const NdpGeom &g, const NdpPyramid &F, const NdpPyramid &R, int mode_rt,
                                const NdpQuery &Q, const NdpTopo *topo, NdpHit &hit)
 {
+    const int mode = (MODE >= 0) ? MODE : mode_rt;
     const int nb = g.nbasic;
     if (R.nvar < nb && R.any_set) {
         const bool cells = (mode == NDP_MODE_KD_LINEAR || mode == NDP_MODE_LS_LINEAR);
         const int lo = cells ? 1 : 0;
         int fixed[NDP_MAX_AXES];
         bool is_var[NDP_MAX_AXES];
+        double talt_m[NDP_MAX_AXES], talt_p[NDP_MAX_AXES];   // terms of a fixed axis' two neighbours (+inf: none)
+        const double inf = 1e308 * 10.0;
         bool ok = true;
         for (int a = 0; a < nb; a++) is_var[a] = false;
         for (int j = 0; j < R.nvar; j++) is_var[R.var_axis[j]] = true;
@@ -753,26 +765,29 @@ NDP_HD void ndp_search_descend(const NdpGeom &g, const NdpPyramid &F, const NdpP
             const int c = (int) p;
             if (!(c >= lo && c <= g.len[a] - 1)) { ok = false; break; }
             const double t0 = ndp_axis_term(mode, Q.qc[a], c, c);
-            if (c - 1 >= lo && !(ndp_axis_term(mode, Q.qc[a], c - 1, c - 1) > t0)) ok = false;
-            if (c + 1 <= g.len[a] - 1 && !(ndp_axis_term(mode, Q.qc[a], c + 1, c + 1) > t0)) ok = false;
+            talt_m[a] = (c - 1 >= lo) ? ndp_axis_term(mode, Q.qc[a], c - 1, c - 1) : inf;
+            talt_p[a] = (c + 1 <= g.len[a] - 1) ? ndp_axis_term(mode, Q.qc[a], c + 1, c + 1) : inf;
+            if (!(talt_m[a] > t0) || !(talt_p[a] > t0)) ok = false;
             fixed[a] = c;
         }
         if (ok) {
-            if (!ndp_search_ring(g, R, mode, Q, fixed, topo, NDP_RING_BUDGET, hit))
-                ndp_search_hard(g, R, mode, Q, fixed, topo, hit, hit.vertex >= 0);
+            if (!ndp_search_ring<MODE>(g, R, mode, Q, fixed, topo, NDP_RING_BUDGET, hit))
+                ndp_search_hard<MODE>(g, R, mode, Q, fixed, topo, hit, hit.vertex >= 0);
             if (hit.status != NDP_SEARCH_EMPTY && hit.vertex >= 0) {
-                // the closed-form axes must also be strict minimisers of the rounded total
+                // the closed-form axes must also be strict minimisers of the rounded total: re-sum the
+                // winner's terms in order with one fixed axis' term swapped for a neighbour's
                 int c[NDP_MAX_AXES];
+                double tw[NDP_MAX_AXES];
                 ndp_decode_vertex(g, hit.vertex, c);
+                for (int a = 0; a < nb; a++) tw[a] = ndp_axis_term(mode, Q.qc[a], c[a], c[a]);
                 for (int a = 0; a < nb && ok; a++) {
                     if (is_var[a]) continue;
-                    const int keep = c[a];
-                    for (int s = -1; s <= 1; s += 2) {
-                        const int t = keep + s;
-                        if (t < lo || t > g.len[a] - 1) continue;
-                        c[a] = t;
-                        const double d = ndp_metric_vertex(g, mode, Q, c);
-                        c[a] = keep;
+                    for (int s = 0; s < 2; s++) {
+                        const double alt = s ? talt_p[a] : talt_m[a];
+                        if (alt >= inf) continue;
+                        double d = 0.0;
+                        for (int b = 0; b < nb; b++) d += (b == a) ? alt : tw[b];
+                        d = ndp_add_assoc(g, mode, Q, d);
                         if (!(d > hit.dsel)) ok = false;
                     }
                 }
@@ -781,8 +796,8 @@ NDP_HD void ndp_search_descend(const NdpGeom &g, const NdpPyramid &F, const NdpP
         }
     }
     if (!F.any_set) { hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_EMPTY; hit.hard = 1; return; }
-    if (!ndp_search_ring(g, F, mode, Q, nullptr, topo, NDP_RING_BUDGET, hit))
-        ndp_search_hard(g, F, mode, Q, nullptr, topo, hit, hit.vertex >= 0);
+    if (!ndp_search_ring<MODE>(g, F, mode, Q, nullptr, topo, NDP_RING_BUDGET, hit))
+        ndp_search_hard<MODE>(g, F, mode, Q, nullptr, topo, hit, hit.vertex >= 0);
 }
 
 // The full scan scores masked-out vertices 1e10 (:283-286), so beyond 1e5 cells

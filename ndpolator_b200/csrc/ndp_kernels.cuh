@@ -302,8 +302,10 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant
     }
 }
 
-// Pass 2 (and the tie pass): pyramid descent with an explicit per-thread stack.
-__global__ void __launch_bounds__(NDP_BLOCK) k_search_hard(const __grid_constant__ SearchArgs A)
+// Pass 2 (and the tie pass): shell search over mask rows, then pyramid descent with an explicit
+// per-thread stack for whatever the shells cannot prove within their budget.
+template <int MODE>
+__global__ void __launch_bounds__(NDP_BLOCK, 3) k_search_hard(const __grid_constant__ SearchArgs A)
 {
     extern __shared__ double s_ticks[];
     const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_hard(const __grid_constant
         ndp_make_query(g, idx, nrm, Q);
         NdpHit hit;
         hit.has_coords = 0;
-        ndp_search_descend(g, *A.F, *A.R, mode, Q, A.have_topo ? &A.topo : nullptr, hit);
+        ndp_search_descend<MODE>(g, *A.F, *A.R, mode, Q, A.have_topo ? &A.topo : nullptr, hit);
         if (hit.status == NDP_SEARCH_TIE) {
             // provisional (valid) vertex so that k_finish stays in bounds; redone once the topology exists
             A.chosen[t] = hit.vertex;

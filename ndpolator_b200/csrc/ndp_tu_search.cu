@@ -42,7 +42,12 @@ cudaError_t ndp_launch_search_fast(const SearchArgs &A, int naxes, int blocks, s
 
 cudaError_t ndp_launch_search_hard(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st)
 {
-    k_search_hard<<<blocks, NDP_BLOCK, smem, st>>>(A);
+    switch (ndp_mode_of(A.method, A.search)) {
+    case NDP_MODE_KD_NEAREST: k_search_hard<NDP_MODE_KD_NEAREST><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case NDP_MODE_KD_LINEAR: k_search_hard<NDP_MODE_KD_LINEAR><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case NDP_MODE_LS_NEAREST: k_search_hard<NDP_MODE_LS_NEAREST><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    default: k_search_hard<NDP_MODE_LS_LINEAR><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    }
     return cudaGetLastError();
 }
 

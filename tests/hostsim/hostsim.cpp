@@ -264,12 +264,13 @@ static void search_one_n(HsTable *t, const double *qrow, int method, int search,
     }
     if (!fast) {
         t->n_hard++;
-        ndp_search_descend(g, t->pyr[m].dev, t->red[m].dev, mode, Q, nullptr, hit);
+        // the kernels instantiate one k_search_hard per mode; -1 here takes the mode at run time through the same code
+        ndp_search_descend<-1>(g, t->pyr[m].dev, t->red[m].dev, mode, Q, nullptr, hit);
         if (hit.status == NDP_SEARCH_TIE) {
             t->n_tie++;
             build_topo(t, m);
             NdpTopo T{t->parent[m].data(), t->depth[m].data()};
-            ndp_search_descend(g, t->pyr[m].dev, t->red[m].dev, mode, Q, &T, hit);
+            ndp_search_descend<-1>(g, t->pyr[m].dev, t->red[m].dev, mode, Q, &T, hit);
         }
     }
     ndp_scan_sentinel(t->pyr[m].dev, mode, hit);
