@@ -387,7 +387,7 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
         return NDPB_OK;
     }
     if (k == "staged") {
-        if (value < 0 || value > 2) return fail(NDPB_ERR_INVALID, "staged must be 0 (auto: one stage, many warps), 1 (off) or 2 (two-stage ring)");
+        if (value < 0 || value > 3) return fail(NDPB_ERR_INVALID, "staged must be 0 (auto: one stage, 5 CTAs/SM), 1 (off), 2 (two-stage ring) or 3 (one stage, 4 CTAs/SM)");
         t->opt_staged = (int) value;
         return NDPB_OK;
     }
@@ -609,13 +609,13 @@ static bool staged_ok(const ndpb_table *t)
            (size_t) t->nticks * sizeof(double) <= 16 * 1024;
 }
 
-static int staged_stages(const ndpb_table *t) { return t->opt_staged == 2 ? 2 : 1; }
+static int staged_stages(const ndpb_table *t) { return t->opt_staged == 2 ? 2 : (t->opt_staged == 3 ? 3 : 1); }
 
 static size_t staged_smem(const ndpb_table *t)
 {
     const size_t ticks = ((size_t) t->nticks * 8 + 127) & ~(size_t) 127;
     const size_t slot = ((size_t) 8 << t->g.naxes) + 16;
-    return ticks + (size_t) NDP_STAGED_WARPS * staged_stages(t) * 32 * slot;
+    return ticks + (size_t) NDP_STAGED_WARPS * (staged_stages(t) == 2 ? 2 : 1) * 32 * slot;
 }
 
 template <int MODE>

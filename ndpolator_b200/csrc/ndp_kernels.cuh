@@ -495,8 +495,8 @@ struct NdpStagedItem {                 // what a lane keeps between issuing a ti
 
 // STAGES == 2: each warp overlaps its own copy with its own next import (fewer, fatter warps);
 // STAGES == 1: no intra-warp overlap, twice the resident warps hide the latency instead.
-template <int N, int MODE, int STAGES>
-__global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? (STAGES == 1 ? 5 : 3) : 1))
+template <int N, int MODE, int STAGES, int OCC = 5>
+__global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? (STAGES == 1 ? OCC : 3) : 1))
 k_gather_staged(const __grid_constant__ StagedArgs A)
 {
     constexpr unsigned CELL_BYTES = 8u << N;
@@ -525,20 +525,38 @@ k_gather_staged(const __grid_constant__ StagedArgs A)
     const long long tile0 = (long long) blockIdx.x * NDP_STAGED_WARPS + warp;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-    // issue: import the lane's query of `tile`, start the pair-cooperative copy into stage st
-    auto produce = [&](long long tile, int st, NdpStagedItem<N> &it) {
+    // the global-memory inputs of one work item, loaded one tile ahead so that their latency
+    // overlaps the previous tile's copy and reduction
+    struct Raw { long long i; double v[N]; int idx[N]; int vertex; };
+    const bool have_rec = (MODE == 1) && A.rec_idx != nullptr;
+    auto fetch = [&](long long tile, Raw &raw) {
         const long long w = tile * 32 + lane;
+        raw.i = -1; raw.vertex = 0;
+        if (w >= total) return;
+        raw.i = (MODE == 0) ? w : (long long) A.offlist[w];
+        if (MODE == 1) raw.vertex = A.chosen[w];
+        if (have_rec) {
+#pragma unroll
+            for (int a = 0; a < N; a++) { raw.idx[a] = A.rec_idx[w * N + a]; raw.v[a] = A.rec_nrm[w * N + a]; }
+        } else {
+#pragma unroll
+            for (int a = 0; a < N; a++) raw.v[a] = A.q[raw.i * N + a];
+        }
+    };
+
+    // issue: import the lane's query of `tile`, start the cooperative copy into stage st
+    auto produce = [&](const Raw &raw, int st, NdpStagedItem<N> &it) {
         it.i = -1; it.issued = false; it.pinmask = 0; it.selbits = 0;
         long long cell = 0;
-        if (w < total) {
-            const long long i = (MODE == 0) ? w : (long long) A.offlist[w];
+        if (raw.i >= 0) {
+            const long long i = raw.i;
             it.i = i;
             int idx[N], flg[N];
             double nrm[N];
-            if (MODE == 1 && A.rec_idx) {
+            if (have_rec) {
 #pragma unroll
-                for (int a = 0; a < N; a++) { idx[a] = A.rec_idx[w * N + a]; nrm[a] = A.rec_nrm[w * N + a]; }
-            } else ndp_import_query<N>(g, s_ticks, A.q + i * N, idx, flg, nrm);
+                for (int a = 0; a < N; a++) { idx[a] = raw.idx[a]; nrm[a] = raw.v[a]; }
+            } else ndp_import_query<N>(g, s_ticks, raw.v, idx, flg, nrm);
             if (MODE == 0) {
 #pragma unroll
                 for (int a = 0; a < N; a++) it.idx[a] = idx[a];
@@ -554,7 +572,7 @@ k_gather_staged(const __grid_constant__ StagedArgs A)
                     for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; cell += (long long) (idx[a] - 1) * g.cstride[a]; }
                 }
             } else {
-                const int vertex = A.chosen[w];
+                const int vertex = raw.vertex;
                 it.issued = true;
                 int vc[NDP_MAX_AXES];
                 ndp_decode_vertex(g, vertex, vc);
@@ -648,8 +666,11 @@ k_gather_staged(const __grid_constant__ StagedArgs A)
 
     if (STAGES == 1) {
         NdpStagedItem<N> item;
+        Raw raw;
+        if (tile0 < ntiles) fetch(tile0, raw);
         for (long long tile = tile0; tile < ntiles; tile += tile_stride) {
-            produce(tile, 0, item);
+            produce(raw, 0, item);
+            if (tile + tile_stride < ntiles) fetch(tile + tile_stride, raw);   // in flight during the wait below
             ndp_cp_async_wait<0>();
             __syncwarp();                      // the other lanes' copies into my slot are visible
             consume(0, item);
@@ -658,19 +679,20 @@ k_gather_staged(const __grid_constant__ StagedArgs A)
         return;
     }
     NdpStagedItem<N> item[2];
-    if (tile0 < ntiles) produce(tile0, 0, item[0]);
+    Raw raw;
+    if (tile0 < ntiles) { fetch(tile0, raw); produce(raw, 0, item[0]); }
     int st = 0;
     for (long long tile = tile0; tile < ntiles; tile += tile_stride) {
         const long long next = tile + tile_stride;
         // one commit per iteration (possibly empty) keeps the group count uniform: everything
         // but the newest group -- the tile being consumed included -- is complete after wait<1>
         if (st == 0) {
-            if (next < ntiles) produce(next, STAGES - 1, item[1]); else ndp_cp_async_commit();
+            if (next < ntiles) { fetch(next, raw); produce(raw, STAGES - 1, item[1]); } else ndp_cp_async_commit();
             ndp_cp_async_wait<1>();
             __syncwarp();
             consume(0, item[0]);
         } else {
-            if (next < ntiles) produce(next, 0, item[0]); else ndp_cp_async_commit();
+            if (next < ntiles) { fetch(next, raw); produce(raw, 0, item[0]); } else ndp_cp_async_commit();
             ndp_cp_async_wait<1>();
             __syncwarp();
             consume(STAGES - 1, item[1]);
