@@ -387,7 +387,7 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
         return NDPB_OK;
     }
     if (k == "staged") {
-        if (value < 0 || value > 3) return fail(NDPB_ERR_INVALID, "staged must be 0 (auto: one stage, 5 CTAs/SM), 1 (off), 2 (two-stage ring) or 3 (one stage, 4 CTAs/SM)");
+        if (value < 0 || value > 3) return fail(NDPB_ERR_INVALID, "staged must be 0 (auto: one stage, 4 CTAs/SM), 1 (off), 2 (two-stage ring) or 3 (one stage, 5 CTAs/SM)");
         t->opt_staged = (int) value;
         return NDPB_OK;
     }
@@ -609,7 +609,8 @@ static bool staged_ok(const ndpb_table *t)
            (size_t) t->nticks * sizeof(double) <= 16 * 1024;
 }
 
-static int staged_stages(const ndpb_table *t) { return t->opt_staged == 2 ? 2 : (t->opt_staged == 3 ? 3 : 1); }
+// 0 (auto) -> one stage per warp at 4 CTAs per SM (measured best on B200, profiles/r01j); 3 -> one stage at 5 CTAs
+static int staged_stages(const ndpb_table *t) { return t->opt_staged == 2 ? 2 : (t->opt_staged == 3 ? 1 : 3); }
 
 static size_t staged_smem(const ndpb_table *t)
 {

@@ -734,6 +734,185 @@ NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode
     }
 }
 
+// The same shell search with the number of basic axes fixed at compile time: every per-axis
+// quantity is indexed by the basic axis with a constant index, so the whole state lives in
+// registers (the generic version above keeps its arrays in local memory).  kind[a]: 0 = fixed
+// (mask-invariant axis solved in closed form), 1 = shell axis, 2 = the row axis.
+template <int MODE, int NB>
+NDP_HD bool ndp_search_ring_nb(const NdpGeom &g, const NdpPyramid &P, const NdpQuery &Q,
+                               const int *fixed, const NdpTopo *topo, int budget, NdpHit &hit)
+{
+    constexpr int mode = MODE;
+    const int nv = P.nvar;
+    constexpr bool cells = (mode == NDP_MODE_KD_LINEAR || mode == NDP_MODE_LS_LINEAR);
+    constexpr bool kd = mode < NDP_MODE_LS_NEAREST;
+    constexpr int lo = cells ? 1 : 0;
+
+    hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_OK; hit.hard = 1;
+    if (nv < 1 || !P.prevv) return false;
+
+    int kind[NB], pstr[NB], p0[NB], off[NB], len[NB], bstr[NB];
+    double q[NB], tmin[NB], term[NB];
+    bool last_shell[NB];
+#pragma unroll
+    for (int a = 0; a < NB; a++) { kind[a] = 0; pstr[a] = 0; off[a] = 0; last_shell[a] = false; len[a] = g.len[a]; bstr[a] = g.bstride[a]; q[a] = Q.qc[a]; }
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+        if (j < nv) {
+            const int va = P.var_axis[j], st = P.stride[0][j];
+#pragma unroll
+            for (int a = 0; a < NB; a++)
+                if (va == a) { kind[a] = (j == nv - 1) ? 2 : 1; pstr[a] = st; last_shell[a] = (j == nv - 2); }
+        }
+    int base = 0;
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < NB; a++) {
+        if (kind[a] == 0) {
+            p0[a] = fixed[a];
+            tmin[a] = ndp_axis_term(mode, q[a], p0[a], p0[a]);
+            base += p0[a] * bstr[a];
+        } else {
+            const double hi = (double) (len[a] - 1);
+            double p = cells ? floor(q[a]) + 1.0 : rint(q[a]);
+            p = p < (double) lo ? (double) lo : (p > hi ? hi : p);
+            const int c = (int) p;
+            ok &= (c >= lo && c <= len[a] - 1);
+            const double t0 = ndp_axis_term(mode, q[a], c, c);
+            // p0 must be the per-axis minimiser for the shell bound and the row argument to hold
+            if (c - 1 >= lo && ndp_axis_term(mode, q[a], c - 1, c - 1) < t0) ok = false;
+            if (c + 1 <= len[a] - 1 && ndp_axis_term(mode, q[a], c + 1, c + 1) < t0) ok = false;
+            ok &= (t0 == t0);
+            p0[a] = c; tmin[a] = t0;
+        }
+        term[a] = tmin[a];
+    }
+    if (!ok) return false;
+    int p0row = 0, lenrow = 0, bstrrow = 0;
+    double qrow = 0.0;
+#pragma unroll
+    for (int a = 0; a < NB; a++)
+        if (kind[a] == 2) { p0row = p0[a]; lenrow = len[a]; bstrrow = bstr[a]; qrow = q[a]; }
+
+    int best = -1;
+    double bestd = 0.0;
+    bool tie = false;
+    int rows = 0;
+
+    auto score = [&](int row_vid, int c) -> double {
+        const double tL = ndp_axis_term(mode, qrow, c, c);
+        double d = 0.0;
+#pragma unroll
+        for (int a = 0; a < NB; a++) d += (kind[a] == 2) ? tL : term[a];
+        d = ndp_add_assoc(g, mode, Q, d);
+        const int vid = row_vid + c * bstrrow;
+        if (best < 0 || d < bestd) { best = vid; bestd = d; tie = false; }
+        else if (d == bestd && vid != best) {
+            if (!kd) { if (vid < best) best = vid; }                     // _compare_indexed_dists, :101-112
+            else if (topo) { if (ndp_tree_beats(g, mode, *topo, Q, vid, best)) best = vid; }
+            else tie = true;
+        }
+        return d;
+    };
+
+    for (int R = 0;; R++) {
+#pragma unroll
+        for (int a = 0; a < NB; a++) off[a] = (kind[a] == 1) ? -R : 0;
+        for (;;) {
+            int cheb = 0, rowflat = 0, row_vid = base;
+            bool inside = true, lead_inside = true;
+#pragma unroll
+            for (int a = 0; a < NB; a++)
+                if (kind[a] == 1) {
+                    const int o = off[a] < 0 ? -off[a] : off[a];
+                    cheb = o > cheb ? o : cheb;
+                    if (!last_shell[a] && o == R) lead_inside = false;
+                    const int c = p0[a] + off[a];
+                    inside &= (c >= lo && c <= len[a] - 1);
+                    rowflat += c * pstr[a];
+                    row_vid += c * bstr[a];
+                }
+            if (cheb == R && inside) {
+                rows++;
+#pragma unroll
+                for (int a = 0; a < NB; a++)
+                    if (kind[a] == 1) term[a] = ndp_axis_term(mode, q[a], p0[a] + off[a], p0[a] + off[a]);
+                // set coordinates of the row, outward from p0 on either side, while the rounded total
+                // does not exceed the best (equal totals are ties the reference's rules must decide)
+                int c = P.prevv[rowflat + p0row];
+                while (c >= lo) {
+                    if (score(row_vid, c) > bestd) break;
+                    c = (c - 1 >= lo) ? P.prevv[rowflat + c - 1] : -1;
+                }
+                c = (p0row + 1 <= lenrow - 1) ? P.nextv[rowflat + p0row + 1] : -1;
+                while (c >= lo) {
+                    if (score(row_vid, c) > bestd) break;
+                    c = (c + 1 <= lenrow - 1) ? P.nextv[rowflat + c + 1] : -1;
+                }
+            }
+            // next shell offset: an odometer over the shell axes, last shell axis fastest; interior
+            // offsets (all norms < R) are skipped by jumping the last shell axis from -R to +R
+            bool carry = true, jumped = false;
+#pragma unroll
+            for (int a = NB - 1; a >= 0; a--)
+                if (kind[a] == 1 && carry) {
+                    if (last_shell[a] && R > 0 && lead_inside && off[a] == -R) { off[a] = R; carry = false; jumped = true; }
+                    else if (++off[a] <= R) carry = false;
+                    else off[a] = -R;
+                }
+            (void) jumped;
+            if (carry) break;
+        }
+        // lower bound for every row beyond shell R
+        bool any_beyond = false;
+        double lb = 0.0;
+#pragma unroll
+        for (int a = 0; a < NB; a++)
+            if (kind[a] == 1) {
+#pragma unroll
+                for (int sgn = -1; sgn <= 1; sgn += 2) {
+                    const int c = p0[a] + sgn * (R + 1);
+                    if (c >= lo && c <= len[a] - 1) {
+                        const double ta = ndp_axis_term(mode, q[a], c, c);
+                        double d = 0.0;
+#pragma unroll
+                        for (int b = 0; b < NB; b++) d += (b == a) ? ta : tmin[b];
+                        d = ndp_add_assoc(g, mode, Q, d);
+                        if (!any_beyond || d < lb) lb = d;
+                        any_beyond = true;
+                    }
+                }
+            }
+        hit.vertex = best; hit.dsel = bestd; hit.status = tie ? NDP_SEARCH_TIE : NDP_SEARCH_OK;
+        if (!any_beyond) {                       // every row of the slice has been scanned
+            if (best < 0) hit.status = NDP_SEARCH_EMPTY;
+            return true;
+        }
+        if (best >= 0 && bestd < lb) return true;
+        if (rows >= budget) return false;
+    }
+}
+
+// dispatch on the number of basic axes (MODE known at compile time), generic version otherwise
+template <int MODE>
+NDP_HD bool ndp_search_ring_any(const NdpGeom &g, const NdpPyramid &P, int mode, const NdpQuery &Q,
+                                const int *fixed, const NdpTopo *topo, int budget, NdpHit &hit)
+{
+    if (MODE >= 0) {
+        constexpr int M = MODE >= 0 ? MODE : 0;
+        switch (g.nbasic) {
+        case 1: return ndp_search_ring_nb<M, 1>(g, P, Q, fixed, topo, budget, hit);
+        case 2: return ndp_search_ring_nb<M, 2>(g, P, Q, fixed, topo, budget, hit);
+        case 3: return ndp_search_ring_nb<M, 3>(g, P, Q, fixed, topo, budget, hit);
+        case 4: return ndp_search_ring_nb<M, 4>(g, P, Q, fixed, topo, budget, hit);
+        case 5: return ndp_search_ring_nb<M, 5>(g, P, Q, fixed, topo, budget, hit);
+        case 6: return ndp_search_ring_nb<M, 6>(g, P, Q, fixed, topo, budget, hit);
+        default: break;
+        }
+    }
+    return ndp_search_ring<MODE>(g, P, mode, Q, fixed, topo, budget, hit);
+}
+
 // The search proper.  Axes along which the mask does not vary (a property of the
 // table, found at register time; typical of atmosphere-like tables whose voids
 // depend on two of many axes) are solved in closed form: the winner takes the
@@ -771,7 +950,7 @@ NDP_HD void ndp_search_descend(const NdpGeom &g, const NdpPyramid &F, const NdpP
             fixed[a] = c;
         }
         if (ok) {
-            if (!ndp_search_ring<MODE>(g, R, mode, Q, fixed, topo, NDP_RING_BUDGET, hit))
+            if (!ndp_search_ring_any<MODE>(g, R, mode, Q, fixed, topo, NDP_RING_BUDGET, hit))
                 ndp_search_hard<MODE>(g, R, mode, Q, fixed, topo, hit, hit.vertex >= 0);
             if (hit.status != NDP_SEARCH_EMPTY && hit.vertex >= 0) {
                 // the closed-form axes must also be strict minimisers of the rounded total: re-sum the
@@ -796,7 +975,7 @@ NDP_HD void ndp_search_descend(const NdpGeom &g, const NdpPyramid &F, const NdpP
         }
     }
     if (!F.any_set) { hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_EMPTY; hit.hard = 1; return; }
-    if (!ndp_search_ring<MODE>(g, F, mode, Q, nullptr, topo, NDP_RING_BUDGET, hit))
+    if (!ndp_search_ring_any<MODE>(g, F, mode, Q, nullptr, topo, NDP_RING_BUDGET, hit))
         ndp_search_hard<MODE>(g, F, mode, Q, nullptr, topo, hit, hit.vertex >= 0);
 }
 

@@ -245,6 +245,23 @@ extern "C" void hs_find(void *h, long long n, const double *q, int32_t *indices,
 }
 
 // mirrors k_search + ndp_publish, with the deferred tie pass folded in
+// mirrors the per-mode instantiation of k_search_hard<MODE>; HS_GENERIC_RING exercises the run-time-mode
+// generic shell search instead (the path tables with more than 6 basic axes take)
+static void descend_by_mode(const NdpGeom &g, const NdpPyramid &F, const NdpPyramid &R, int mode, const NdpQuery &Q,
+                            const NdpTopo *topo, NdpHit &hit)
+{
+#ifdef HS_GENERIC_RING
+    ndp_search_descend<-1>(g, F, R, mode, Q, topo, hit);
+#else
+    switch (mode) {
+    case 0: ndp_search_descend<0>(g, F, R, mode, Q, topo, hit); break;
+    case 1: ndp_search_descend<1>(g, F, R, mode, Q, topo, hit); break;
+    case 2: ndp_search_descend<2>(g, F, R, mode, Q, topo, hit); break;
+    default: ndp_search_descend<3>(g, F, R, mode, Q, topo, hit); break;
+    }
+#endif
+}
+
 template <int N>
 static void search_one_n(HsTable *t, const double *qrow, int method, int search, int *vertex, double *dist, int *coords)
 {
@@ -264,13 +281,12 @@ static void search_one_n(HsTable *t, const double *qrow, int method, int search,
     }
     if (!fast) {
         t->n_hard++;
-        // the kernels instantiate one k_search_hard per mode; -1 here takes the mode at run time through the same code
-        ndp_search_descend<-1>(g, t->pyr[m].dev, t->red[m].dev, mode, Q, nullptr, hit);
+        descend_by_mode(g, t->pyr[m].dev, t->red[m].dev, mode, Q, nullptr, hit);
         if (hit.status == NDP_SEARCH_TIE) {
             t->n_tie++;
             build_topo(t, m);
             NdpTopo T{t->parent[m].data(), t->depth[m].data()};
-            ndp_search_descend<-1>(g, t->pyr[m].dev, t->red[m].dev, mode, Q, &T, hit);
+            descend_by_mode(g, t->pyr[m].dev, t->red[m].dev, mode, Q, &T, hit);
         }
     }
     ndp_scan_sentinel(t->pyr[m].dev, mode, hit);
