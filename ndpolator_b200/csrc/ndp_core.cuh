@@ -739,7 +739,7 @@ NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode
 // registers (the generic version above keeps its arrays in local memory).  kind[a]: 0 = fixed
 // (mask-invariant axis solved in closed form), 1 = shell axis, 2 = the row axis.
 template <int MODE, int NB>
-NDP_HD bool ndp_search_ring_nb(const NdpGeom &g, const NdpPyramid &P, const NdpQuery &Q,
+NDP_HD_CALL bool ndp_search_ring_nb(const NdpGeom &g, const NdpPyramid &P, const NdpQuery &Q,
                                const int *fixed, const NdpTopo *topo, int budget, NdpHit &hit)
 {
     constexpr int mode = MODE;

@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant
 // Pass 2 (and the tie pass): shell search over mask rows, then pyramid descent with an explicit
 // per-thread stack for whatever the shells cannot prove within their budget.
 template <int MODE>
-__global__ void __launch_bounds__(NDP_BLOCK, 3) k_search_hard(const __grid_constant__ SearchArgs A)
+__global__ void __launch_bounds__(NDP_BLOCK, 2) k_search_hard(const __grid_constant__ SearchArgs A)
 {
     extern __shared__ double s_ticks[];
     const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
