@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.FIELDS}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -92,6 +92,16 @@ class ClockSampler:
                         reasons.add(name)
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_traffic(batch):
+    """DRAM bytes of one launch of the dominant kernel, scaled from the committed ncu capture
+    (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum at its batch size)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+        return t['k_gather_staged<5,0,1,4>']['dram_bytes'] * batch / t['batch']
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -300,9 +310,11 @@ def run_b200(args):
             'gpu_launches': acc['launches'],
             'clocks': clocks,
             'roofline': {
-                'bound': 'hbm', 'kernel': 'k_main (fused import + gather + reduce)',
+                'bound': 'hbm', 'kernel': 'k_gather_staged<N,0> / k_main (fused import + cell gather + reduce)',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': (achieved / peak) if achieved else None, 'traffic': None, 'peak_source': peak_src,
+                'frac': (achieved / peak) if achieved else None,
+                'traffic': measured_traffic(B) if (args.workload == 'C4' and args.scale is None and not args.method) else None,
+                'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': main_bytes, 'avg_launch_ms': main_s * 1e3,
                 'whole_step': {'achieved': step_gbs, 'frac': step_gbs / peak,
                                'note': 'queries/step x SURVEY 8d bytes/query over the whole step (all kernels)'},
