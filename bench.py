@@ -341,6 +341,20 @@ def run_b200(args):
 
 def main():
     args = parse()
+    # Only the JSON line may reach stdout: libraries (NCCL's version banner, for one) write to
+    # fd 1, so everything else is sent to stderr and the line is written to the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, 'w')
+    global print
+    import builtins
+
+    def print(*a, **k):          # noqa: A001 -- the JSON line goes to the real stdout
+        k.setdefault('file', real_stdout)
+        builtins.print(*a, **k)
+        real_stdout.flush()
+
     if args.impl == 'reference':
         run_reference(args)
     else:

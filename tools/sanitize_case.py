@@ -1,0 +1,35 @@
+"""Small end-to-end exercise of every kernel family for compute-sanitizer (development tool).
+    compute-sanitizer --tool memcheck python tools/sanitize_case.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+from cases import adversarial_queries, build_cases  # noqa: E402
+from ndpolator_b200.cndpolator import Table  # noqa: E402
+
+for name, axes, nbasic, grid in build_cases():
+    if name not in ('holed3d', '2basic_1assoc_v2', '5d_corner_void', '7d_runtime_n', 'c3_like_v16'):
+        continue
+    q = adversarial_queries(axes, 3000, np.random.default_rng(1))
+    for gather, staged in ((1, 0), (2, 0), (2, 1), (2, 2)):
+        T = Table(axes, grid, nbasic)
+        T.set_option('gather', gather)
+        T.set_option('staged', staged)
+        T.set_option('chunk', 1024)
+        for m in (0, 1, 2):
+            for s in (0, 1):
+                T.ndpolate(q, m, s)
+        T.find_nearest(q, 1, 0)
+        T.find_nearest(q, 2, 1)
+        T.distance(q)
+        idx, flg, nrm = T.find(q)
+        T.hypercubes_raw(nrm, idx, flg)
+        T.masks()
+        T.tree_topology(1)
+        T.close()
+    print(name, 'ok')
