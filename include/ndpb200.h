@@ -111,15 +111,13 @@ int ndpb_table_tree_topology(ndpb_table *t, int method, int32_t *parent, int32_t
 /* Tuning knobs that never change results.  Keys: "gather" = 0 auto | 1 strided
  * (original layout) | 2 cell-major; "linear_search" = 0 auto | 1 brute force |
  * 2 lattice; "chunk" = queries per staged chunk for host buffers; "staged" = 0 auto | 1 never use the cp.async
- * staged gather kernel; "inline_offgrid" = 1 (default) settle provable off-grid queries
- * inside the gather kernel | 0 always list them for the search kernels; "stream" = a
+ * staged gather kernel; "stream" = a
  * cudaStream_t (as integer) to launch the kernels on instead of the table's own
  * stream, 0 to restore it. */
 int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t value);
 
 /* Per-table counters of the last call, for bench.py / tests:
  * "launches" kernels launched, "offgrid" queries sent to the search,
- * "inline" of those, settled inside the gather kernel,
  * "hard" queries that needed the tree/lattice descent, "ties" queries resolved
  * through the kd topology, "h2d_bytes", "d2h_bytes", "cellmajor" (0/1),
  * "kernel_ns" device time of the main gather kernel (CUDA events). */

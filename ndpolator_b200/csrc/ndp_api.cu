@@ -90,10 +90,10 @@ struct ndpb_table {
     std::mutex mu;
     int sm_count = 148;
     // options
-    int opt_gather = 0, opt_linear_search = 0, opt_staged = 0, opt_inline = 1;
+    int opt_gather = 0, opt_linear_search = 0, opt_staged = 0;
     long long opt_chunk = 1 << 22;
     // stats of the last call
-    long long st_launches = 0, st_offgrid = 0, st_hard = 0, st_ties = 0, st_h2d = 0, st_d2h = 0, st_inline = 0;
+    long long st_launches = 0, st_offgrid = 0, st_hard = 0, st_ties = 0, st_h2d = 0, st_d2h = 0;
     double st_main_ms = 0, st_search_ms = 0, st_finish_ms = 0;
 };
 
@@ -391,10 +391,6 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
         t->opt_staged = (int) value;
         return NDPB_OK;
     }
-    if (k == "inline_offgrid") {
-        t->opt_inline = value ? 1 : 0;
-        return NDPB_OK;
-    }
     if (k == "chunk") {
         if (value < 1024) return fail(NDPB_ERR_INVALID, "chunk must be >= 1024");
         t->opt_chunk = value;
@@ -411,7 +407,6 @@ extern "C" int64_t ndpb_table_stat(const ndpb_table *t, const char *key)
     if (k == "offgrid") return t->st_offgrid;
     if (k == "hard") return t->st_hard;
     if (k == "ties") return t->st_ties;
-    if (k == "inline") return t->st_inline;
     if (k == "h2d_bytes") return t->st_h2d;
     if (k == "d2h_bytes") return t->st_d2h;
     if (k == "cellmajor") return t->cells ? 1 : 0;
@@ -625,9 +620,9 @@ static size_t staged_smem(const ndpb_table *t)
 }
 
 template <int MODE>
-static int launch_staged(ndpb_table *t, const StagedArgs &A, long long items, int search_mode, cudaStream_t st)
+static int launch_staged(ndpb_table *t, const StagedArgs &A, long long items, cudaStream_t st)
 {
-    CU(ndp_launch_staged(A, t->g.naxes, MODE, staged_stages(t), search_mode, t->sm_count, items, staged_smem(t), st));
+    CU(ndp_launch_staged(A, t->g.naxes, MODE, staged_stages(t), t->sm_count, items, staged_smem(t), st));
     t->st_launches++;
     return NDPB_OK;
 }
@@ -677,12 +672,9 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
     StagedArgs G{};
     G.g = t->g; G.ticks = t->ticks; G.nticks = t->nticks; G.cells = t->cells; G.q = q; G.n = n;
     G.interps = interps; G.dists = dists; G.method = method; G.offlist = s.list; G.chosen = s.chosen; G.ctr = s.ctr;
-    G.rec_idx = s.rec_idx; G.rec_nrm = s.rec_nrm; G.grid = t->grid;
-    G.F = (method != NDPB_METHOD_NONE) ? t->pyr[method == NDPB_METHOD_LINEAR ? 1 : 0].d_desc : nullptr;
-    // the in-place proof replaces pass 1 of the lattice search; the literal scan (brute force) keeps its own kernel
-    const int inline_mode = (method != NDPB_METHOD_NONE && t->opt_inline && !use_brute(t, search)) ? ndp_mode_of(method, search) : -1;
+    G.rec_idx = s.rec_idx; G.rec_nrm = s.rec_nrm;
     if (task == TASK_NDPOLATE && staged_ok(t)) {
-        int rc = launch_staged<0>(t, G, n, inline_mode, st);
+        int rc = launch_staged<0>(t, G, n, st);
         if (rc) return rc;
     } else if (task == TASK_NDPOLATE) {
         MainArgs M{};
@@ -713,7 +705,7 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
     }
     CU(cudaEventRecord(s.t2, st));
     if (task == TASK_NDPOLATE && method == NDPB_METHOD_LINEAR && staged_ok(t)) {
-        int rc = launch_staged<1>(t, G, n, -1, st);  // item count is read from the device counter; n bounds the grid
+        int rc = launch_staged<1>(t, G, n, st);      // item count is read from the device counter; n bounds the grid
         if (rc) return rc;
     } else if (task == TASK_NDPOLATE && method != NDPB_METHOD_NONE) {
         FinishArgs F{};
@@ -741,8 +733,7 @@ static int batch_complete(ndpb_table *t, Slot &s, Task task, const double *q, lo
     if (cudaEventElapsedTime(&ms, s.t1, s.t2) == cudaSuccess) t->st_search_ms += ms;
     if (cudaEventElapsedTime(&ms, s.t2, s.t3) == cudaSuccess) t->st_finish_ms += ms;
     const NdpCounters c = *s.ctr_host;
-    t->st_offgrid += (task == TASK_NDPOLATE) ? c.n_off + c.n_inline : (method == NDPB_METHOD_NONE ? 0 : n);
-    t->st_inline += c.n_inline;
+    t->st_offgrid += (task == TASK_NDPOLATE) ? c.n_off : (method == NDPB_METHOD_NONE ? 0 : n);
     t->st_hard += c.n_hard;
     if (c.n_tie > 0) {
         const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;
@@ -772,7 +763,7 @@ static int batch_complete(ndpb_table *t, Slot &s, Task task, const double *q, lo
 
 static void reset_stats(ndpb_table *t)
 {
-    t->st_launches = t->st_offgrid = t->st_hard = t->st_ties = t->st_h2d = t->st_d2h = t->st_inline = 0;
+    t->st_launches = t->st_offgrid = t->st_hard = t->st_ties = t->st_h2d = t->st_d2h = 0;
     t->st_main_ms = t->st_search_ms = t->st_finish_ms = 0;
 }
 

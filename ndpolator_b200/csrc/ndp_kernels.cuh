@@ -24,7 +24,6 @@ struct NdpCounters {      // one per in-flight batch, zeroed before k_main
     int n_tie;            // kd-mode ties met without topology
     int n_hard;           // queries that needed the pyramid descent
     int n_tie_resolved;   // ties settled through the kd topology
-    int n_inline;         // off-grid queries settled inside the gather kernel (never listed)
 };
 
 // ---------------------------------------------------------------------------
@@ -471,8 +470,6 @@ struct StagedArgs {
     int *offlist;                      // MODE 0: out; MODE 1: in (query id per work item)
     const int *chosen;                 // MODE 1: winning vertex per work item
     int *rec_idx; double *rec_nrm;     // import products by list position: MODE 0 writes, MODE 1 reads (nullptr: re-import)
-    const double *grid;                // original layout (nearest-vertex values of the inline off-grid path)
-    const NdpPyramid *F;               // mask pyramid of the extrapolation method (inline off-grid path), or nullptr
     NdpCounters *ctr;
 };
 
@@ -494,19 +491,11 @@ struct NdpStagedItem {                 // what a lane keeps between issuing a ti
     double x[N];                       // interpolation weights
     unsigned pinmask, selbits;
     bool issued;                       // this lane's cell is being copied
-    bool settled;                      // off-grid query whose nearest vertex / hypercube was proven in place
-    double dist;                       // its squared distance
-    long long elem;                    // NEAREST: element of the winning vertex in the original grid
 };
 
 // STAGES == 2: each warp overlaps its own copy with its own next import (fewer, fatter warps);
 // STAGES == 1: no intra-warp overlap, twice the resident warps hide the latency instead.
-// SM >= 0 (MODE 0 only): search mode of the call.  Off-grid lanes then run the proof of
-// k_search_fast in place -- most off-grid queries sit just outside the box, where the clamped
-// lattice point is provably the winner -- and finish in the same pass (LINEAR: the found cell
-// goes through the same staged copy; NEAREST: one vertex load), so only what the proof cannot
-// settle is listed for the search kernels.
-template <int N, int MODE, int STAGES, int OCC = 5, int SM = -1>
+template <int N, int MODE, int STAGES, int OCC = 5>
 __global__ void __launch_bounds__(NDP_STAGED_WARPS * 32, (N <= 5 ? (STAGES == 1 ? OCC : 3) : 1))
 k_gather_staged(const __grid_constant__ StagedArgs A)
 {
@@ -557,7 +546,7 @@ k_gather_staged(const __grid_constant__ StagedArgs A)
 
     // issue: import the lane's query of `tile`, start the cooperative copy into stage st
     auto produce = [&](const Raw &raw, int st, NdpStagedItem<N> &it) {
-        it.i = -1; it.issued = false; it.pinmask = 0; it.selbits = 0; it.settled = false;
+        it.i = -1; it.issued = false; it.pinmask = 0; it.selbits = 0;
         long long cell = 0;
         if (raw.i >= 0) {
             const long long i = raw.i;
@@ -573,51 +562,14 @@ k_gather_staged(const __grid_constant__ StagedArgs A)
                 for (int a = 0; a < N; a++) it.idx[a] = idx[a];
                 const bool oob = ndp_classify<N>(g, flg, nrm, it.pinmask, it.selbits);
                 it.issued = !oob;
-                int sup[N];
-#pragma unroll
-                for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; sup[a] = idx[a]; }
-                if (SM >= 0 && oob) {
-                    // the proof of k_search_fast, in place (src/ndpolator.c:188-352 via ndp_search_fast)
-                    constexpr int SMODE = SM >= 0 ? SM : 0;
-                    constexpr bool linear = (SMODE == NDP_MODE_KD_LINEAR || SMODE == NDP_MODE_LS_LINEAR);
-                    NdpQuery Q;
-                    ndp_make_query(g, idx, nrm, Q);
-                    NdpHit hit;
-                    hit.has_coords = 0;
-                    if (ndp_search_fast<N, SMODE>(g, *A.F, SMODE, Q, hit)) {
-                        const int v0 = hit.vertex;
-                        ndp_scan_sentinel(*A.F, SMODE, hit);
-                        if (hit.vertex == v0) {
-                            int coords[N];
-#pragma unroll
-                            for (int a = 0; a < N; a++) coords[a] = (a < g.nbasic) ? hit.coords[a] : Q.acoord[a];
-                            it.settled = true;
-                            it.dist = (SMODE >= NDP_MODE_LS_NEAREST) ? hit.dsel
-                                                                     : ndp_reported_dist(g, linear ? NDP_M_LINEAR : NDP_M_NEAREST, Q, coords);
-                            if (linear) {
-                                it.issued = true; it.pinmask = 0; it.selbits = 0;
-#pragma unroll
-                                for (int a = 0; a < N; a++) {
-                                    sup[a] = coords[a] > 1 ? coords[a] : 1;                 // :601
-                                    it.x[a] = nrm[a] + (double) (idx[a] - coords[a]);      // :621-622
-                                }
-                            } else {
-                                long long v = 0;
-#pragma unroll
-                                for (int a = 0; a < N; a++) v += (long long) coords[a] * g.vstride[a];
-                                it.elem = v;                                                // :563-564 (vdim == 1)
-                            }
-                        }
-                    }
-                }
                 if (g.small) {
                     int c32 = 0;
 #pragma unroll
-                    for (int a = 0; a < N; a++) c32 += (sup[a] - 1) * g.cstride32[a];
+                    for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; c32 += (idx[a] - 1) * g.cstride32[a]; }
                     cell = c32;
                 } else {
 #pragma unroll
-                    for (int a = 0; a < N; a++) cell += (long long) (sup[a] - 1) * g.cstride[a];
+                    for (int a = 0; a < N; a++) { it.x[a] = nrm[a]; cell += (long long) (idx[a] - 1) * g.cstride[a]; }
                 }
             } else {
                 const int vertex = raw.vertex;
@@ -685,21 +637,13 @@ k_gather_staged(const __grid_constant__ StagedArgs A)
                     for (int j = 0; j < (1 << N) / 2; j++) { double2 p = b2[j]; fv[2 * j] = p.x; fv[2 * j + 1] = p.y; }
                 }, it.x, it.pinmask, it.selbits, bad);
                 fdhc = !bad;
-                if (MODE == 1 || fdhc || it.settled) A.interps[it.i] = val;
+                if (MODE == 1 || fdhc) A.interps[it.i] = val;
             }
             if (MODE == 0) {
-                if (SM >= 0 && it.settled) {
-                    if (!it.issued) A.interps[it.i] = A.grid[it.elem];
-                    A.dists[it.i] = it.dist;
-                }
-                else if (fdhc) A.dists[it.i] = 0.0;
+                if (fdhc) A.dists[it.i] = 0.0;
                 else if (A.method == NDP_M_NONE) { A.interps[it.i] = qnan; A.dists[it.i] = 0.0; }
                 else need_search = true;
             }
-        }
-        if (MODE == 0 && SM >= 0) {
-            const unsigned done = __ballot_sync(0xffffffffu, it.i >= 0 && it.settled);
-            if (done && lane == 0) atomicAdd(&A.ctr->n_inline, __popc(done));
         }
         if (MODE == 0) {
             const unsigned votes = __ballot_sync(0xffffffffu, need_search);

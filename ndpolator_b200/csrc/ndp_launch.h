@@ -13,5 +13,4 @@ cudaError_t ndp_launch_search_fast(const SearchArgs &A, int naxes, int blocks, s
 cudaError_t ndp_launch_search_hard(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st);
 cudaError_t ndp_launch_search_brute(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st);
 // mode 0: k_main work, mode 1: linear-extrapolation finish; picks the grid from the occupancy
-// search_mode >= 0 (mode 0, default staging): settle provable off-grid queries inside the gather kernel
-cudaError_t ndp_launch_staged(const StagedArgs &A, int naxes, int mode, int stages, int search_mode, int sm_count, long long items, size_t smem, cudaStream_t st);
+cudaError_t ndp_launch_staged(const StagedArgs &A, int naxes, int mode, int stages, int sm_count, long long items, size_t smem, cudaStream_t st);
