@@ -239,6 +239,70 @@ NDP_HD double ndp_cell_reduce(Load load, const double *x, unsigned pinmask, unsi
     return result;
 }
 
+// The same reduction for a scalar cell stored contiguously (cell-major layout), evaluated in two
+// halves to halve the live registers: corners are split on the second-to-last axis (the 16-byte
+// chunks of the cell alternate between the halves), each half is reduced over axes 0..N-3 down to
+// its two last-axis values, then the halves meet on axis N-2 and finally on axis N-1.  Every lerp
+// pairs exactly the operands c_ndpolate (:83-96) pairs, in an order that respects all data
+// dependences, so the result is bit-identical to ndp_cell_reduce.
+template <int N>
+NDP_HD double ndp_cell_reduce_halves(const double2 *b2, const double *x, unsigned pinmask, unsigned selbits, bool &nan_used)
+{
+    static_assert(N >= 2, "needs at least two axes");
+    constexpr int HC = 1 << (N - 2);            // 16-byte chunks per half
+    double res[2][2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        double fv[2 * HC];                      // index bits: axes 0..N-3 (MSB first), then the last axis
+#pragma unroll
+        for (int mp = 0; mp < HC; mp++) { const double2 p = b2[2 * mp + h]; fv[2 * mp] = p.x; fv[2 * mp + 1] = p.y; }
+#pragma unroll
+        for (int a = 0; a < N - 2; a++) {
+            const int hb = 1 << (N - 2 - a);
+            const bool pinned = (pinmask >> (N - 1 - a)) & 1u;
+            const bool upper = (selbits >> (N - 1 - a)) & 1u;
+            const double xa = x[a];
+#pragma unroll
+            for (int j = 0; j < HC; j++)        // constant trip count keeps fv[] in registers
+                if (j < hb) {
+                    const double l = ndp_lerp(fv[j], fv[j + hb], xa);
+                    const double sel = upper ? fv[j + hb] : fv[j];
+                    fv[j] = pinned ? sel : l;
+                }
+        }
+        res[h][0] = fv[0]; res[h][1] = fv[1];
+    }
+    double r[2];
+    {
+        const bool pinned = (pinmask >> 1) & 1u, upper = (selbits >> 1) & 1u;
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const double l = ndp_lerp(res[0][b], res[1][b], x[N - 2]);
+            const double sel = upper ? res[1][b] : res[0][b];
+            r[b] = pinned ? sel : l;
+        }
+    }
+    double result;
+    {
+        const bool pinned = pinmask & 1u, upper = selbits & 1u;
+        const double l = ndp_lerp(r[0], r[1], x[N - 1]);
+        const double sel = upper ? r[1] : r[0];
+        result = pinned ? sel : l;
+    }
+    bool bad = false;
+    if (result != result) {                     // see ndp_cell_reduce: only a NaN result needs the corner test
+#pragma unroll
+        for (int m = 0; m < 2 * HC; m++) {
+            const double2 p = b2[m];
+            const bool u0 = (((unsigned) (2 * m) ^ selbits) & pinmask) == 0;
+            const bool u1 = (((unsigned) (2 * m + 1) ^ selbits) & pinmask) == 0;
+            bad |= (u0 && (p.x != p.x)) || (u1 && (p.y != p.y));
+        }
+    }
+    nan_used = bad;
+    return result;
+}
+
 // Runtime-n version (any n <= NDP_MAX_AXES): walks only the used corners in
 // "axis 0 fastest" order and folds them with a carry chain, which performs
 // exactly the lerps of c_ndpolate (:83-96) in an order that respects every data
@@ -1049,6 +1113,10 @@ NDP_HD double ndp_eval_cell(const NdpGeom &g, const double *__restrict__ grid, c
                 for (int a = 0; a < NN; a++) cell += (long long) (sup[a] - 1) * g.cstride[a];
             }
             const double *base = cells + (cell << NN) * V + k;
+            if (V1 && NN >= 2) {
+                constexpr int N2 = NN >= 2 ? NN : 2;
+                return ndp_cell_reduce_halves<N2>(reinterpret_cast<const double2 *>(base), x, pinmask, selbits, nan_used);
+            }
             if (V1) {
                 const double2 *b2 = reinterpret_cast<const double2 *>(base);
                 return ndp_cell_reduce<NN>([&](double *fv) {

@@ -632,10 +632,7 @@ k_gather_staged(const __grid_constant__ StagedArgs A)
             if (it.issued) {
                 const double2 *b2 = reinterpret_cast<const double2 *>(slot_of(st, lane));
                 bool bad = false;
-                const double val = ndp_cell_reduce<N>([&](double *fv) {
-#pragma unroll
-                    for (int j = 0; j < (1 << N) / 2; j++) { double2 p = b2[j]; fv[2 * j] = p.x; fv[2 * j + 1] = p.y; }
-                }, it.x, it.pinmask, it.selbits, bad);
+                const double val = ndp_cell_reduce_halves<N>(b2, it.x, it.pinmask, it.selbits, bad);
                 fdhc = !bad;
                 if (MODE == 1 || fdhc) A.interps[it.i] = val;
             }
