@@ -1078,15 +1078,69 @@ NDP_HD void ndp_make_query(const NdpGeom &g, const int *idx, const double *nrm, 
 // ---------------------------------------------------------------------------
 
 // N > 0: number of axes fixed at compile time; N == 0: read it from the geometry.
+//
+// For N > 0 the guess-and-verify search of ndp_import_axis_guess is laid out in phases over ALL
+// axes -- index guess and tick loads, one corrective tick, verification, then the quotients, then
+// the flags -- as straight-line code, so that the independent per-axis chains interleave in the
+// instruction stream (a warp issues in order: one axis after the other would leave every fp64
+// latency exposed).  Axes whose guess does not verify are redone by the reference bisection.
 template <int N>
 NDP_HD void ndp_import_query(const NdpGeom &g, const double *ticks, const double *qrow,
                              int *idx, int *flg, double *nrm)
 {
-    const int n = N ? N : g.naxes;
+    if (N == 0) {
+        const int n = g.naxes;
+        for (int a = 0; a < n; a++)
+            ndp_import_axis_guess(ticks + g.tickoff[a], g.len[a], g.inv_step[a], g.first[a], g.last[a],
+                                  qrow[a], idx[a], flg[a], nrm[a]);
+        return;
+    }
+    constexpr int M = N ? N : 1;
+    const double rtol = 1e-6;
+    double x[M], xr[M], tl[M], tp[M];
+    int l[M], len[M];
+    const double *tk[M];
+    bool ok[M];
 #pragma unroll
-    for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
-        if (a < n) ndp_import_axis_guess(ticks + g.tickoff[a], g.len[a], g.inv_step[a], g.first[a], g.last[a],
-                                         qrow[a], idx[a], flg[a], nrm[a]);
+    for (int a = 0; a < M; a++) {
+        tk[a] = ticks + g.tickoff[a];
+        len[a] = g.len[a];
+        x[a] = qrow[a];
+        xr[a] = x[a] + rtol;
+        int c = (int) ((xr[a] - g.first[a]) * g.inv_step[a]);
+        c = c < len[a] - 2 ? c : len[a] - 2;
+        l[a] = c > 0 ? c + 1 : 1;
+    }
+#pragma unroll
+    for (int a = 0; a < M; a++) { tl[a] = tk[a][l[a]]; tp[a] = tk[a][l[a] - 1]; }
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+        const bool up = (xr[a] > tl[a]) && (l[a] < len[a] - 1);
+        const bool dn = !up && !(xr[a] > tp[a]) && (l[a] > 1);
+        l[a] += (up ? 1 : 0) - (dn ? 1 : 0);
+    }
+#pragma unroll
+    for (int a = 0; a < M; a++) { tl[a] = tk[a][l[a]]; tp[a] = tk[a][l[a] - 1]; }
+    bool all_ok = true;
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+        ok[a] = g.inv_step[a] > 0.0 && (!(xr[a] > tl[a]) || l[a] == len[a] - 1) && (l[a] == 1 || xr[a] > tp[a]);
+        all_ok &= ok[a];
+    }
+    double t[M];
+#pragma unroll
+    for (int a = 0; a < M; a++) t[a] = (x[a] - tp[a]) / (tl[a] - tp[a]);
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+        int f = (x[a] < g.first[a] || x[a] > g.last[a]) ? NDP_F_OOB : 0;
+        if (fabs(t[a]) < rtol || (l[a] == len[a] - 1 && fabs(t[a] - 1) < rtol)) f |= NDP_F_ON_VERTEX;
+        idx[a] = l[a]; flg[a] = f; nrm[a] = t[a];
+    }
+    if (!all_ok) {
+#pragma unroll
+        for (int a = 0; a < M; a++)
+            if (!ok[a]) ndp_import_axis(tk[a], len[a], x[a], idx[a], flg[a], nrm[a]);
+    }
 }
 
 // Reduced value of component k of the cell whose superior corner is sup[] (:472-498
