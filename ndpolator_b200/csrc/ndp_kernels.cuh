@@ -158,7 +158,22 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_main(const __gr
         double nrm[N ? N : NDP_MAX_AXES];
 
         if (live) {
-            ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
+            if (G > 1 && N > 0 && G >= N) {
+                // the lanes of a group split the axes (one index search each) and exchange the results,
+                // instead of all repeating the whole import
+                int my_idx = 1, my_flg = 0;
+                double my_nrm = 0.0;
+                if (lig < n)
+                    ndp_import_axis_guess(tk + g.tickoff[lig], g.len[lig], g.inv_step[lig], g.first[lig], g.last[lig],
+                                          A.q[i * n + lig], my_idx, my_flg, my_nrm);
+                const int group_base = (int) (lane & ~(unsigned) (G - 1));
+#pragma unroll
+                for (int a = 0; a < (N ? N : 1); a++) {
+                    idx[a] = __shfl_sync(gmask, my_idx, group_base + a);
+                    flg[a] = __shfl_sync(gmask, my_flg, group_base + a);
+                    nrm[a] = __shfl_sync(gmask, my_nrm, group_base + a);
+                }
+            } else ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
             unsigned pinmask, selbits;
             const bool oob = ndp_classify<N>(g, flg, nrm, pinmask, selbits);
 
@@ -257,7 +272,7 @@ __device__ __forceinline__ void ndp_publish(const SearchArgs &A, const NdpQuery 
 // Pass 1: the rounded lattice point, proven optimal by its axis neighbours.  What it
 // cannot settle goes to the hard list so that pass 2 runs with full warps.
 template <int N, int MODE>
-__global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant__ SearchArgs A)
+__global__ void __launch_bounds__(NDP_BLOCK, 3) k_search_fast(const __grid_constant__ SearchArgs A)
 {
     extern __shared__ double s_ticks[];
     const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
