@@ -597,7 +597,9 @@ static int launch_main(ndpb_table *t, const MainArgs &A, cudaStream_t st)
 
 static int launch_finish(ndpb_table *t, const FinishArgs &A, cudaStream_t st)
 {
-    CU(ndp_launch_finish(A, t->g.naxes, A.cells != nullptr, t->sm_count * 8, smem_bytes(t), st));
+    int G = 1;
+    while (G < t->g.vdim && G < 32) G <<= 1;
+    CU(ndp_launch_finish(A, t->g.naxes, G, A.cells != nullptr, t->sm_count * 8, smem_bytes(t), st));
     t->st_launches++;
     return NDPB_OK;
 }

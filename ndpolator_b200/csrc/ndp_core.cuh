@@ -1143,6 +1143,15 @@ NDP_HD void ndp_import_query(const NdpGeom &g, const double *ticks, const double
     }
 }
 
+// The same import behind a real call, for kernels that only import when no record is available
+// (keeps their register budget for the common path).
+template <int N>
+NDP_HD_CALL void ndp_import_query_call(const NdpGeom &g, const double *ticks, const double *qrow,
+                                       int *idx, int *flg, double *nrm)
+{
+    ndp_import_query<N>(g, ticks, qrow, idx, flg, nrm);
+}
+
 // Reduced value of component k of the cell whose superior corner is sup[] (:472-498
 // gather + :78-99 reduction).  CM selects the cell-major copy of the grid
 // (2^n * vdim contiguous doubles per cell, `cells`), else the original strided

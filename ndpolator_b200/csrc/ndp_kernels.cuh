@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NDP_BLOCK, 3) k_search_fast(const __grid_const
 #pragma unroll
                 for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
                     if (a < n) { idx[a] = A.rec_idx[t * n + a]; nrm[a] = A.rec_nrm[t * n + a]; }
-            } else ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
+            } else ndp_import_query_call<N>(g, tk, A.q + i * n, idx, flg, nrm);
             NdpQuery Q;
             ndp_make_query(g, idx, nrm, Q);
             NdpHit hit;
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(NDP_BLOCK, 2) k_search_hard(const __grid_const
         double nrm[NDP_MAX_AXES];
         if (A.list && A.rec_idx) {
             for (int a = 0; a < n; a++) { idx[a] = A.rec_idx[t * n + a]; nrm[a] = A.rec_nrm[t * n + a]; }
-        } else ndp_import_query<0>(g, tk, A.q + i * n, idx, flg, nrm);
+        } else ndp_import_query_call<0>(g, tk, A.q + i * n, idx, flg, nrm);
         NdpQuery Q;
         ndp_make_query(g, idx, nrm, Q);
         NdpHit hit;
@@ -418,7 +418,9 @@ struct FinishArgs {
 };
 
 #if defined(NDP_TU_FINISH)
-template <int N, bool CM>
+// G lanes share a work item when vdim > 1: lane k owns components k, k+G, ... so that a corner
+// vector is one coalesced G*8-byte load (as in k_main).
+template <int N, int G, bool CM>
 __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __grid_constant__ FinishArgs A)
 {
     extern __shared__ double s_ticks[];
@@ -426,8 +428,10 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __
     const NdpGeom &g = A.g;
     const int n = N ? N : g.naxes;
     const int V = g.vdim;
+    const int lig = threadIdx.x % G;
     const long long total = *A.count;
-    for (long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long) gridDim.x * blockDim.x) {
+    const long long groups = ((long long) gridDim.x * blockDim.x) / G;
+    for (long long s = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / G; s < total; s += groups) {
         const long long t = A.sublist ? A.sublist[s] : s;
         const long long i = A.list[t];
         int idx[N ? N : NDP_MAX_AXES], flg[N ? N : NDP_MAX_AXES];
@@ -436,13 +440,13 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __
 #pragma unroll
             for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
                 if (a < n) { idx[a] = A.rec_idx[t * n + a]; nrm[a] = A.rec_nrm[t * n + a]; }
-        } else ndp_import_query<N>(g, tk, A.q + i * n, idx, flg, nrm);
+        } else ndp_import_query_call<N>(g, tk, A.q + i * n, idx, flg, nrm);
         int coords[NDP_MAX_AXES];
         const int vertex = A.chosen[t];
         ndp_decode_vertex(g, vertex, coords);
         for (int a = g.nbasic; a < n; a++)
             coords[a] = ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
-        for (int k = 0; k < V; k++)
+        for (int k = lig; k < V; k += G)
             A.interps[i * V + k] = ndp_finish_component<N, CM, false>(g, A.grid, A.cells, A.method, idx, nrm, coords, k);
     }
 }

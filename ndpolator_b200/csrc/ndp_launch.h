@@ -8,7 +8,7 @@ cudaError_t ndp_launch_import(const ImportArgs &A, int blocks, size_t smem, cuda
 cudaError_t ndp_launch_hypercubes(const HypercubeArgs &A, int blocks, cudaStream_t st);
 cudaError_t ndp_launch_main_strided(const MainArgs &A, int naxes, int G, int blocks, size_t smem, cudaStream_t st);
 cudaError_t ndp_launch_main_cellmajor(const MainArgs &A, int naxes, int G, int blocks, size_t smem, cudaStream_t st);
-cudaError_t ndp_launch_finish(const FinishArgs &A, int naxes, bool cellmajor, int blocks, size_t smem, cudaStream_t st);
+cudaError_t ndp_launch_finish(const FinishArgs &A, int naxes, int G, bool cellmajor, int blocks, size_t smem, cudaStream_t st);
 cudaError_t ndp_launch_search_fast(const SearchArgs &A, int naxes, int blocks, size_t smem, cudaStream_t st);
 cudaError_t ndp_launch_search_hard(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st);
 cudaError_t ndp_launch_search_brute(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st);
