@@ -1143,13 +1143,17 @@ NDP_HD void ndp_import_query(const NdpGeom &g, const double *ticks, const double
     }
 }
 
-// The same import behind a real call, for kernels that only import when no record is available
-// (keeps their register budget for the common path).
+// The plain per-axis form of the same import, for kernels that only import when no record is
+// available: compact code and few registers matter more there than instruction-level parallelism.
 template <int N>
-NDP_HD_CALL void ndp_import_query_call(const NdpGeom &g, const double *ticks, const double *qrow,
-                                       int *idx, int *flg, double *nrm)
+NDP_HD void ndp_import_query_seq(const NdpGeom &g, const double *ticks, const double *qrow,
+                                 int *idx, int *flg, double *nrm)
 {
-    ndp_import_query<N>(g, ticks, qrow, idx, flg, nrm);
+    const int n = N ? N : g.naxes;
+#pragma unroll
+    for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
+        if (a < n) ndp_import_axis_guess(ticks + g.tickoff[a], g.len[a], g.inv_step[a], g.first[a], g.last[a],
+                                         qrow[a], idx[a], flg[a], nrm[a]);
 }
 
 // Reduced value of component k of the cell whose superior corner is sup[] (:472-498

@@ -272,7 +272,7 @@ __device__ __forceinline__ void ndp_publish(const SearchArgs &A, const NdpQuery 
 // Pass 1: the rounded lattice point, proven optimal by its axis neighbours.  What it
 // cannot settle goes to the hard list so that pass 2 runs with full warps.
 template <int N, int MODE>
-__global__ void __launch_bounds__(NDP_BLOCK, 3) k_search_fast(const __grid_constant__ SearchArgs A)
+__global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant__ SearchArgs A)
 {
     extern __shared__ double s_ticks[];
     const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NDP_BLOCK, 3) k_search_fast(const __grid_const
 #pragma unroll
                 for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
                     if (a < n) { idx[a] = A.rec_idx[t * n + a]; nrm[a] = A.rec_nrm[t * n + a]; }
-            } else ndp_import_query_call<N>(g, tk, A.q + i * n, idx, flg, nrm);
+            } else ndp_import_query_seq<N>(g, tk, A.q + i * n, idx, flg, nrm);
             NdpQuery Q;
             ndp_make_query(g, idx, nrm, Q);
             NdpHit hit;
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(NDP_BLOCK, 2) k_search_hard(const __grid_const
         double nrm[NDP_MAX_AXES];
         if (A.list && A.rec_idx) {
             for (int a = 0; a < n; a++) { idx[a] = A.rec_idx[t * n + a]; nrm[a] = A.rec_nrm[t * n + a]; }
-        } else ndp_import_query_call<0>(g, tk, A.q + i * n, idx, flg, nrm);
+        } else ndp_import_query_seq<0>(g, tk, A.q + i * n, idx, flg, nrm);
         NdpQuery Q;
         ndp_make_query(g, idx, nrm, Q);
         NdpHit hit;
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(NDP_BLOCK, (N >= 6 ? 1 : 2)) k_finish(const __
 #pragma unroll
             for (int a = 0; a < (N ? N : NDP_MAX_AXES); a++)
                 if (a < n) { idx[a] = A.rec_idx[t * n + a]; nrm[a] = A.rec_nrm[t * n + a]; }
-        } else ndp_import_query_call<N>(g, tk, A.q + i * n, idx, flg, nrm);
+        } else ndp_import_query_seq<N>(g, tk, A.q + i * n, idx, flg, nrm);
         int coords[NDP_MAX_AXES];
         const int vertex = A.chosen[t];
         ndp_decode_vertex(g, vertex, coords);
