@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--gather', type=int, default=0, help='0 auto, 1 strided, 2 cell-major')
     ap.add_argument('--staged', type=int, default=0, help='0 auto (cp.async ring), 1 off (same results)')
+    ap.add_argument('--opt', action='append', default=[], help='table option key=value (tuning sweeps), repeatable')
     ap.add_argument('--cpu-scale', type=int, default=20, help='ticks per axis of the grid the CPU reference is timed on')
     ap.add_argument('--cpu-queries', type=int, default=20000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -222,6 +223,9 @@ def run_b200(args):
         T.set_option('gather', args.gather)
     if args.staged:
         T.set_option('staged', args.staged)
+    for kv in args.opt:
+        k, v = kv.split('=')
+        T.set_option(k, int(v))
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t_build
 

@@ -111,7 +111,8 @@ int ndpb_table_tree_topology(ndpb_table *t, int method, int32_t *parent, int32_t
 /* Tuning knobs that never change results.  Keys: "gather" = 0 auto | 1 strided
  * (original layout) | 2 cell-major; "linear_search" = 0 auto | 1 brute force |
  * 2 lattice; "chunk" = queries per staged chunk for host buffers; "staged" = 0 auto | 1 never use the cp.async
- * staged gather kernel; "stream" = a
+ * staged gather kernel; "search_fast_blocks_per_sm" / "search_hard_blocks_per_sm" =
+ * grid-stride CTAs per SM of the two search passes (default 64 / 256); "stream" = a
  * cudaStream_t (as integer) to launch the kernels on instead of the table's own
  * stream, 0 to restore it. */
 int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t value);

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libndpb200.so')
+# NDPB_LIB: a tuning variant built by build.build(extra_flags=..., lib_out=...); same ABI, same results
+LIB_PATH = os.environ.get('NDPB_LIB') or os.path.join(HERE, 'libndpb200.so')
 
 # every symbol include/ndpb200.h declares (tests check the export list against the header)
 SYMBOLS = [

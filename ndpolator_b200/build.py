@@ -38,19 +38,21 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), lib_out: str | None = None) -> str:
     """Compiles csrc/*.cu (one object per kernel family, in parallel) and links
-    ndpolator_b200/libndpb200.so, if missing or out of date."""
-    if not force and not stale():
+    ndpolator_b200/libndpb200.so, if missing or out of date.  extra_flags + lib_out build a
+    tuning variant (e.g. -DNDP_HARD_OCC=3) beside it; NDPB_LIB selects it at load time."""
+    if lib_out is None and not force and not stale():
         return LIB
+    out = lib_out or LIB
     from concurrent.futures import ThreadPoolExecutor
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, 'build')
+    objdir = os.path.join(HERE, 'build') if lib_out is None else os.path.splitext(out)[0] + '_obj'
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + '.o')
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', '-o', obj, os.path.join(CSRC, src)]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ['-c', '-o', obj, os.path.join(CSRC, src)]
         if verbose:
             print(' '.join(cmd))
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -60,13 +62,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs
+    cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', out] + objs
     if verbose:
         print(' '.join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('link failed:\n' + res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == '__main__':

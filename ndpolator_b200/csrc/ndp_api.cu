@@ -92,6 +92,7 @@ struct ndpb_table {
     // options
     int opt_gather = 0, opt_linear_search = 0, opt_staged = 0;
     long long opt_chunk = 1 << 22;
+    int opt_fast_blocks = 64, opt_hard_blocks = 256;   // grid-stride CTAs per SM of the two search passes (profiles/r01p_sweep_search.txt)
     // stats of the last call
     long long st_launches = 0, st_offgrid = 0, st_hard = 0, st_ties = 0, st_h2d = 0, st_d2h = 0;
     double st_main_ms = 0, st_search_ms = 0, st_finish_ms = 0;
@@ -396,6 +397,11 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
         t->opt_chunk = value;
         return NDPB_OK;
     }
+    if (k == "search_fast_blocks_per_sm" || k == "search_hard_blocks_per_sm") {
+        if (value < 1 || value > 1024) return fail(NDPB_ERR_INVALID, k + " must be in 1..1024");
+        (k == "search_fast_blocks_per_sm" ? t->opt_fast_blocks : t->opt_hard_blocks) = (int) value;
+        return NDPB_OK;
+    }
     return fail(NDPB_ERR_INVALID, "unknown option " + k);
 }
 
@@ -646,7 +652,7 @@ static int launch_search(ndpb_table *t, SearchArgs &A, long long upper, bool har
     A.topo.parent = t->topo[m].parent; A.topo.depth = t->topo[m].depth;
     A.ticks = t->ticks; A.nticks = t->nticks; A.ticks_in_smem = ticks_in_smem(t);
     const size_t smem = smem_bytes(t);
-    const long long cap = (long long) t->sm_count * 8;
+    const long long cap = (long long) t->sm_count * (hard ? t->opt_hard_blocks : (use_brute(t, A.search) ? 8 : t->opt_fast_blocks));
     if (hard) {
         const int blocks = (int) std::min<long long>((upper + NDP_BLOCK - 1) / NDP_BLOCK, cap);
         CU(ndp_launch_search_hard(A, std::max(blocks, 1), smem, st));

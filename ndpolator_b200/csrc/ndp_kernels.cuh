@@ -18,6 +18,15 @@
 #include "ndp_core.cuh"
 
 #define NDP_BLOCK 256
+// resident CTAs per SM the two search passes are compiled for (register budget = 65536 / (256 * OCC))
+#ifdef NDP_FAST_OCC
+#define NDP_FAST_BOUNDS __launch_bounds__(NDP_BLOCK, NDP_FAST_OCC)
+#else
+#define NDP_FAST_BOUNDS __launch_bounds__(NDP_BLOCK)
+#endif
+#ifndef NDP_HARD_OCC
+#define NDP_HARD_OCC 2
+#endif
 
 struct NdpCounters {      // one per in-flight batch, zeroed before k_main
     int n_off;            // queries not in a fully defined hypercube (search needed)
@@ -272,7 +281,7 @@ __device__ __forceinline__ void ndp_publish(const SearchArgs &A, const NdpQuery 
 // Pass 1: the rounded lattice point, proven optimal by its axis neighbours.  What it
 // cannot settle goes to the hard list so that pass 2 runs with full warps.
 template <int N, int MODE>
-__global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant__ SearchArgs A)
+__global__ void NDP_FAST_BOUNDS k_search_fast(const __grid_constant__ SearchArgs A)
 {
     extern __shared__ double s_ticks[];
     const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
@@ -320,7 +329,7 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_fast(const __grid_constant
 // Pass 2 (and the tie pass): shell search over mask rows, then pyramid descent with an explicit
 // per-thread stack for whatever the shells cannot prove within their budget.
 template <int MODE>
-__global__ void __launch_bounds__(NDP_BLOCK, 2) k_search_hard(const __grid_constant__ SearchArgs A)
+__global__ void __launch_bounds__(NDP_BLOCK, NDP_HARD_OCC) k_search_hard(const __grid_constant__ SearchArgs A)
 {
     extern __shared__ double s_ticks[];
     const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
