@@ -91,7 +91,7 @@ struct ndpb_table {
     int sm_count = 148;
     // options
     int opt_gather = 0, opt_linear_search = 0, opt_staged = 0;
-    long long opt_chunk = 1 << 22;
+    long long opt_chunk = 1 << 20;          // profiles/r01p_sweep_chunk.txt: 1 Mi beats 2, 4 and 8 Mi end to end
     int opt_fast_blocks = 64, opt_hard_blocks = 256;   // grid-stride CTAs per SM of the two search passes (profiles/r01p_sweep_search.txt)
     // stats of the last call
     long long st_launches = 0, st_offgrid = 0, st_hard = 0, st_ties = 0, st_h2d = 0, st_d2h = 0;
