@@ -44,3 +44,39 @@ def test_device_logic_matches_oracle(case):
                 assert_same_bits(a[1], b[1], f'dists {m}/{s} variant {variant}')
     st = H.stats()
     assert st['hard'] > 0 and st['ties'] > 0      # the adversarial set must reach the slow paths
+
+
+@pytest.mark.parametrize('case', build_cases(seed=3), ids=lambda c: c[0])
+def test_non_finite_queries(case):
+    """Non-finite query coordinates.  +-inf is an ordinary out-of-bounds coordinate for the
+    reference (flag 2, normed +-inf: src/ndpolator.c:35,:379-381) and must match bit for bit in
+    every mode.  A NaN coordinate imports as index 1, flag 0, normed NaN (:27-39); with
+    extrapolation 'none' that is fully defined behaviour (NaN interps) and must match too.  NaN
+    together with an extrapolating method is outside the contract: the reference's kd traversal
+    compares against NaN, and round(NaN) indexes out of bounds on associated axes (it segfaults on
+    the 2basic_1assoc case here), so there is nothing to be identical to."""
+    from hostsim.driver import HostSim
+    name, axes, nbasic, grid = case
+    q = adversarial_queries(axes, 300, np.random.default_rng(5))
+    qi = q.copy()
+    qi[::4, -1] = np.inf
+    qi[1::4, 0] = -np.inf
+    qn = q.copy()
+    qn[::3, 0] = np.nan
+    qn[1::7, :] = np.nan
+    O, H = Oracle('port', axes, grid, nbasic), HostSim(axes, grid, nbasic)
+    for a, b, what in zip(O.find(qi), H.find(qi), ('indices', 'flags', 'normed')):
+        assert_same_bits(a, b, what + ' (inf)')
+    for a, b, what in zip(O.find(qn), H.find(qn), ('indices', 'flags', 'normed')):
+        assert_same_bits(a, b, what + ' (nan)')
+    for m in (0, 1, 2):
+        for s in (0, 1):
+            a = O.ndpolate(qi, m, s)
+            for variant in (0, 1, 2):
+                b = H.ndpolate(qi, m, s, variant)
+                assert_same_bits(a[0], b[0], f'interps {m}/{s} variant {variant} (inf)')
+                assert_same_bits(a[1], b[1], f'dists {m}/{s} variant {variant} (inf)')
+    a = O.ndpolate(qn, 0, 0)
+    for variant in (0, 1, 2):
+        b = H.ndpolate(qn, 0, 0, variant)
+        assert_same_bits(a[0], b[0], f'interps none variant {variant} (nan)')
