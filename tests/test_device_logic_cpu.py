@@ -80,3 +80,16 @@ def test_non_finite_queries(case):
     for variant in (0, 1, 2):
         b = H.ndpolate(qn, 0, 0, variant)
         assert_same_bits(a[0], b[0], f'interps none variant {variant} (nan)')
+    # NaN rows that sit in a fully defined hypercube never reach the search: identical in every mode
+    # (all-basic tables only: with associated axes the x86 oracle indexes with (int) NaN and may fault)
+    if nbasic != len(axes):
+        return
+    fo = O.find(qn)
+    _, fdhc, _ = O.hypercubes(*fo)
+    rows = np.nonzero(np.asarray(fdhc).ravel() == 1)[0]
+    assert np.isnan(qn[rows]).any()
+    for m in (1, 2):
+        for s in (0, 1):
+            a, b = O.ndpolate(qn, m, s), H.ndpolate(qn, m, s, 2)
+            assert_same_bits(a[0][rows], b[0][rows], f'interps {m}/{s} (nan, in a fully defined hypercube)')
+            assert_same_bits(a[1][rows], b[1][rows], f'dists {m}/{s} (nan, in a fully defined hypercube)')
