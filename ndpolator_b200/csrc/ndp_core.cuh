@@ -495,11 +495,17 @@ NDP_HD bool ndp_search_fast(const NdpGeom &g, const NdpPyramid &P, int mode_rt, 
     int c[M];
     int flat = 0;
     bool ok = true;
+#ifdef NDP_FAST_MARGIN
+    unsigned clamped = 0;
+#endif
 #pragma unroll
     for (int a = 0; a < M; a++)
         if (a < nb) {
             const double hi = (double) (g.len[a] - 1);
             double p = cells ? floor(Q.qc[a]) + 1.0 : rint(Q.qc[a]);
+#ifdef NDP_FAST_MARGIN
+            if (p < (double) lo || p > hi) clamped |= 1u << a;         // NaN: not clamped, poisons the margin below
+#endif
             p = p < (double) lo ? (double) lo : (p > hi ? hi : p);     // NaN falls through and is rejected below
             c[a] = (int) p;
             ok &= (c[a] >= lo && c[a] <= g.len[a] - 1);
@@ -508,6 +514,44 @@ NDP_HD bool ndp_search_fast(const NdpGeom &g, const NdpPyramid &P, int mode_rt, 
     if (!ok) return false;
     if (!ndp_bit(P.bits[0], flat)) return false;
 
+#ifdef NDP_FAST_MARGIN
+    // Margin shortcut (off by default until measured on a B200; validated on the host build).
+    // Replacing the candidate's term on axis a by a neighbour's raises the exact sum by at least
+    //   point metrics (vertex at c, cell centre at c - 0.5):  1 - 2|q - pos|   (>= 1 where c was clamped)
+    //   box metric of ndp_distance (cell [c-1, c]):           min(f, 1 - f)^2, f = q - (c - 1)   (>= 1 if clamped)
+    // fl-sums are monotone and every rounding error of the terms and of the ordered sums is below
+    // ~50 u (3 d0 + 3), u = 2^-53; a margin above 2^-30 (d0 + 1) therefore proves every neighbour strictly
+    // farther without evaluating the 2 nbasic neighbour sums.  Near-ties (and NaN) take the full proof.
+    {
+        double e0 = 0.0, G = 1.0;
+#pragma unroll
+        for (int a = 0; a < M; a++)
+            if (a < nb) {
+                e0 += ndp_axis_term(mode, Q.qc[a], c[a], c[a]);
+                double ga;
+                if ((clamped >> a) & 1u) ga = 1.0;
+                else if (mode == NDP_MODE_LS_LINEAR) {
+                    const double f = Q.qc[a] - (double) (c[a] - 1);
+                    const double h = f < 1.0 - f ? f : 1.0 - f;
+                    ga = h * h;
+                } else {
+                    const double x = Q.qc[a] - ((double) c[a] - (mode == NDP_MODE_KD_LINEAR ? 0.5 : 0.0));
+                    ga = 1.0 - 2.0 * fabs(x);
+                }
+                G = (ga >= G) ? G : ga;                                 // NaN propagates
+            }
+        e0 = ndp_add_assoc(g, mode, Q, e0);
+        if (!(e0 == e0)) return false;
+        if (G > 0x1p-30 * (e0 + 1.0)) {
+            hit.vertex = flat; hit.dsel = e0; hit.status = NDP_SEARCH_OK; hit.hard = 0;
+#pragma unroll
+            for (int a = 0; a < M; a++)
+                if (a < nb) hit.coords[a] = c[a];
+            hit.has_coords = 1;
+            return true;
+        }
+    }
+#endif
     // per-axis terms of the candidate and of its two axis neighbours, each computed once
     double t0[M], tm[M], tp[M];
     bool hm[M], hp[M];

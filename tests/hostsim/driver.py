@@ -6,7 +6,9 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, 'libhostsim.so')
+# NDPB_HOSTSIM_FLAGS: extra -D switches of ndp_core.cuh under test (e.g. -DNDP_FAST_MARGIN), built beside the default
+FLAGS = os.environ.get('NDPB_HOSTSIM_FLAGS', '').split()
+LIB = os.path.join(HERE, 'libhostsim' + ''.join(f.replace('-D', '_').replace('=', '') for f in FLAGS) + '.so')
 SRC = os.path.join(HERE, 'hostsim.cpp')
 CORE = os.path.join(HERE, '..', '..', 'ndpolator_b200', 'csrc', 'ndp_core.cuh')
 
@@ -16,7 +18,7 @@ _ip = C.POINTER(C.c_int32)
 
 def build():
     if (not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(CORE))):
-        subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC', '-o', LIB, SRC], check=True)
+        subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC'] + FLAGS + ['-o', LIB, SRC], check=True)
     lib = C.CDLL(LIB)
     lib.hs_create.restype = C.c_void_p
     lib.hs_create.argtypes = [C.c_int, C.c_int, _ip, _dp, C.c_int, _dp, C.c_int]

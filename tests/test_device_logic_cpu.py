@@ -93,3 +93,17 @@ def test_non_finite_queries(case):
             a, b = O.ndpolate(qn, m, s), H.ndpolate(qn, m, s, 2)
             assert_same_bits(a[0][rows], b[0][rows], f'interps {m}/{s} (nan, in a fully defined hypercube)')
             assert_same_bits(a[1][rows], b[1][rows], f'dists {m}/{s} (nan, in a fully defined hypercube)')
+
+
+@pytest.mark.skipif(bool(__import__('os').environ.get('NDPB_HOSTSIM_FLAGS')), reason='already inside the variant run')
+def test_margin_shortcut_variant_is_bit_exact_too():
+    """ndp_search_fast's margin shortcut (-DNDP_FAST_MARGIN, off in the shipped library until it has been
+    measured on a B200) must give the same bits: rerun this file against a host build with it on."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, NDPB_HOSTSIM_FLAGS='-DNDP_FAST_MARGIN')
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-x', '-q', '-p', 'no:cacheprovider'],
+                         env=env, cwd=os.path.dirname(here), capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
