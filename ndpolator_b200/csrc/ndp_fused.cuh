@@ -1,0 +1,112 @@
+// ndp_fused.cuh -- the per-query PLAN of the fused ndpolate kernel (k_fused): after the
+// import, everything the reference's driver decides for one query (ndpolate,
+// src/ndpolator.c:510-671) -- is the enclosing hypercube fully defined (:436-505), and if not,
+// which vertex / hypercube the extrapolation uses (:556-635) -- is settled here from two
+// register-time products, the hypercube-mask slice and the nearest-site map (ndp_nsm.cuh),
+// without touching the grid.  What is left for the kernel is ONE gather per query (the
+// query's own cell, or the cell below the found hypercube) and its reduction, so that
+// in-grid and extrapolated queries share one memory pipeline.  Queries the plan cannot
+// settle exactly (see ndp_nsm.cuh) are marked SLOW and redone by the exact generic path.
+#pragma once
+
+#include "ndp_nsm.cuh"
+
+#define NDP_PLAN_IDLE 0
+#define NDP_PLAN_GATHER 1     // interps = reduce(cell `cell`, weights x, pin/sel); dists = dist
+#define NDP_PLAN_VALUE 2      // interps = grid[vflat] (NEAREST extrapolation, :556-567); dists = dist
+#define NDP_PLAN_NAN 3        // interps = NaN, dists = 0 (extrapolation NONE, :551-554)
+#define NDP_PLAN_SLOW 4       // to the slow list
+
+// The slice of the hypercube mask over the axes it depends on: bit set <=> every corner of the
+// cell below that superior corner is defined (ndp_types.c:201-258).
+struct NdpHcSlice {
+    int nvar;
+    int var_axis[NDP_MAX_AXES];
+    int sstride[NDP_MAX_AXES];
+    const uint32_t *bits;
+    int nwords;
+};
+
+template <int N>
+struct NdpPlan {
+    int kind;
+    long long cell;            // GATHER: cell number in the cell-major copy
+    long long vflat;           // VALUE: vertex number in the grid (all axes)
+    double x[N ? N : NDP_MAX_AXES];
+    unsigned pin, sel;
+    double dist;
+};
+
+template <int N>
+NDP_HD long long ndp_cell_of(const NdpGeom &g, const int *sup)
+{
+    constexpr int MM = N ? N : NDP_MAX_AXES;
+    const int n = N ? N : g.naxes;
+    if (g.small) {
+        int c32 = 0;
+#pragma unroll
+        for (int a = 0; a < MM; a++) if (a < n) c32 += (sup[a] - 1) * g.cstride32[a];
+        return c32;
+    }
+    long long c = 0;
+#pragma unroll
+    for (int a = 0; a < MM; a++) if (a < n) c += (long long) (sup[a] - 1) * g.cstride[a];
+    return c;
+}
+
+// METHOD / MODE: compile-time extrapolation method and search mode (MODE is ignored for NONE).
+// `hcbits` is H.bits or a shared-memory copy of it.
+template <int N, int METHOD, int MODE>
+NDP_HD void ndp_fused_plan(const NdpGeom &g, const NdpHcSlice &H, const uint32_t *hcbits, const NdpSiteMap &M,
+                           const int *idx, const int *flg, const double *nrm, NdpPlan<N> &P)
+{
+    constexpr int MM = N ? N : NDP_MAX_AXES;
+    const int n = N ? N : g.naxes;
+    const bool oob = ndp_classify<N>(g, flg, nrm, P.pin, P.sel);
+    P.dist = 0.0;
+    if (!oob) {
+        int h = 0;
+#pragma unroll
+        for (int j = 0; j < MM; j++) if (j < H.nvar) h += idx[H.var_axis[j]] * H.sstride[j];
+        if (ndp_bit(hcbits, h)) {
+            // every corner of the query's cell is defined: the hypercube is fully defined whatever the
+            // on-vertex reduction keeps (:455-505)
+            P.kind = NDP_PLAN_GATHER;
+            P.cell = ndp_cell_of<N>(g, idx);
+#pragma unroll
+            for (int a = 0; a < MM; a++) if (a < n) P.x[a] = nrm[a];
+            return;
+        }
+        // a corner is missing.  With on-vertex axes the reduced hypercube may avoid it: the generic path looks
+        if (P.pin != 0) { P.kind = NDP_PLAN_SLOW; return; }
+    }
+    if (METHOD == NDP_M_NONE) { P.kind = NDP_PLAN_NAN; return; }
+    NdpQuery Q;
+    ndp_make_query(g, idx, nrm, Q);
+    NdpHit hit;
+    if (!ndp_nsm_search<N, MODE>(g, M, Q, hit)) { P.kind = NDP_PLAN_SLOW; return; }
+    int coords[MM];
+#pragma unroll
+    for (int a = 0; a < MM; a++) if (a < n) coords[a] = a < g.nbasic ? hit.coords[a] : Q.acoord[a];
+    P.dist = (MODE >= NDP_MODE_LS_NEAREST) ? hit.dsel : ndp_reported_dist(g, METHOD, Q, coords);
+    if (METHOD == NDP_M_NEAREST) {
+        long long v = 0;
+#pragma unroll
+        for (int a = 0; a < MM; a++) if (a < n) v += (long long) coords[a] * g.vstride[a];
+        P.kind = NDP_PLAN_VALUE;
+        P.vflat = v;
+        return;
+    }
+    // LINEAR: full-dimensional cell below the found corner, clamped at 0 (:601); query shifted into that
+    // cell's unit coordinates (:621-622)
+    int sup[MM];
+#pragma unroll
+    for (int a = 0; a < MM; a++)
+        if (a < n) {
+            sup[a] = coords[a] > 1 ? coords[a] : 1;
+            P.x[a] = nrm[a] + (double) (idx[a] - coords[a]);
+        }
+    P.kind = NDP_PLAN_GATHER;
+    P.cell = ndp_cell_of<N>(g, sup);
+    P.pin = 0; P.sel = 0;
+}

@@ -100,8 +100,8 @@ class Oracle:
         self._fn('table_warm', None, [C.c_void_p, C.c_int])(self.h, int(method))
 
     def tree_topology(self, method):
-        """(parent vertex id, depth) per vertex id of the reference-shaped kd-tree (port only)."""
-        assert self.kind == 'port'
+        """(parent vertex id, depth) per vertex id of the insertion-ordered kd-tree: the port's own
+        index-linked tree, or -- kind 'reference' -- a walk over the reference's real struct kdnode."""
         nv = self.nverts
         parent = np.full(nv, -2, np.int64)
         depth = np.full(nv, -1, np.int32)

@@ -21,7 +21,10 @@
 
 #include "ndpolator.h"
 #include "ndp_types.h"
-#include "kdtree.h"
+/* The reference's kd-tree is compiled as part of THIS translation unit, from where it lies
+ * (-I$(REF)/external/kdtree): struct kdnode / struct kdtree are private to kdtree.c
+ * (external/kdtree/kdtree.c:56-86), and ndpref_tree_topology below has to walk them. */
+#include "kdtree.c"
 
 /* defined in src/ndpolator.c:114 but absent from its header */
 struct kdtree *ndp_kdtree_create(ndp_table *table, ndp_extrapolation_method extrapolation_method);
@@ -71,6 +74,38 @@ void ndpref_table_warm(void *hh, int method)
     ndp_table *t = ((ref_handle *) hh)->table;
     if (method == NDP_METHOD_NEAREST && !t->vtree) t->vtree = ndp_kdtree_create(t, method);
     if (method == NDP_METHOD_LINEAR && !t->hctree) t->hctree = ndp_kdtree_create(t, method);
+}
+
+/* Shape of the reference's own tree (ndp_kdtree_create, src/ndpolator.c:114-136; kd_insert,
+ * external/kdtree/kdtree.c:167-209): parent vertex id (-1 root, -2 not in the tree) and depth
+ * (-1 not in the tree) per basic vertex id.  Iterative walk (the tree is 100s of levels deep);
+ * reads the reference's structs, computes nothing. */
+void ndpref_tree_topology(void *hh, int method, int64_t *parent, int32_t *depth)
+{
+    ndp_table *t = ((ref_handle *) hh)->table;
+    ndpref_table_warm(hh, method);
+    struct kdtree *tree = method == NDP_METHOD_NEAREST ? t->vtree : t->hctree;
+    for (int i = 0; i < t->nverts; i++) { parent[i] = -2; depth[i] = -1; }
+    if (!tree || !tree->root) return;
+    size_t cap = 1024, top = 0;
+    struct kdnode **stack = malloc(cap * sizeof *stack);
+    parent[(uintptr_t) tree->root->data] = -1;
+    depth[(uintptr_t) tree->root->data] = 0;
+    stack[top++] = tree->root;
+    while (top) {
+        struct kdnode *nd = stack[--top];
+        int64_t id = (int64_t) (uintptr_t) nd->data;
+        struct kdnode *kids[2] = {nd->left, nd->right};
+        for (int k = 0; k < 2; k++)
+            if (kids[k]) {
+                int64_t cid = (int64_t) (uintptr_t) kids[k]->data;
+                parent[cid] = id;
+                depth[cid] = depth[id] + 1;
+                if (top == cap) { cap *= 2; stack = realloc(stack, cap * sizeof *stack); }
+                stack[top++] = kids[k];
+            }
+    }
+    free(stack);
 }
 
 void ndpref_import(void *hh, int64_t n, const double *q, int32_t *indices, int32_t *flags, double *normed)

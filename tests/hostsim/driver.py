@@ -10,14 +10,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FLAGS = os.environ.get('NDPB_HOSTSIM_FLAGS', '').split()
 LIB = os.path.join(HERE, 'libhostsim' + ''.join(f.replace('-D', '_').replace('=', '') for f in FLAGS) + '.so')
 SRC = os.path.join(HERE, 'hostsim.cpp')
-CORE = os.path.join(HERE, '..', '..', 'ndpolator_b200', 'csrc', 'ndp_core.cuh')
+CSRC = os.path.join(HERE, '..', '..', 'ndpolator_b200', 'csrc')
+CORE = [os.path.join(CSRC, f) for f in ('ndp_core.cuh', 'ndp_nsm.cuh', 'ndp_fused.cuh')]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 
 
 def build():
-    if (not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(CORE))):
+    if (not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in [SRC] + CORE)):
         subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC'] + FLAGS + ['-o', LIB, SRC], check=True)
     lib = C.CDLL(LIB)
     lib.hs_create.restype = C.c_void_p
@@ -72,7 +73,19 @@ class HostSim:
         self.lib.hs_ndpolate(self.h, C.c_longlong(len(q)), _p(q, _dp), int(method), int(search), int(variant), _p(i, _dp), _p(d, _dp))
         return i, d
 
+    def ndpolate_fused(self, q, method, search):
+        """The fused path's logic (plan from masks + nearest-site map, one gather); None when the
+        table or mode does not qualify for it."""
+        i, d = np.empty((len(q), self.vdim)), np.empty((len(q), 1))
+        ok = self.lib.hs_ndpolate_fused(self.h, C.c_longlong(len(q)), _p(q, _dp), int(method), int(search), _p(i, _dp), _p(d, _dp))
+        return (i, d) if ok else None
+
     def stats(self):
-        o = (C.c_longlong * 3)()
+        o = (C.c_longlong * 5)()
         self.lib.hs_stats(self.h, o)
-        return {'offgrid': o[0], 'hard': o[1], 'ties': o[2]}
+        return {'offgrid': o[0], 'hard': o[1], 'ties': o[2], 'slow': o[3], 'mapped': o[4]}
+
+    def nsm_info(self):
+        o = (C.c_longlong * 12)()
+        self.lib.hs_nsm_info(self.h, o)
+        return [{'valid': o[4 * g], 'S': o[4 * g + 1], 'regions': o[4 * g + 2], 'entries': o[4 * g + 3]} for g in range(3)]

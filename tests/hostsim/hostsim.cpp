@@ -16,6 +16,7 @@
 #include <numeric>
 
 #include "../../ndpolator_b200/csrc/ndp_core.cuh"
+#include "../../ndpolator_b200/csrc/ndp_fused.cuh"
 
 struct HsPyr { NdpPyramid dev; std::vector<std::vector<uint32_t>> levels; std::vector<short> prevv, nextv; };
 
@@ -25,7 +26,12 @@ struct HsTable {
     HsPyr pyr[2], red[2];
     std::vector<int> parent[2], depth[2];
     bool topo_built[2] = {false, false};
-    long long n_hard = 0, n_tie = 0, n_off = 0;
+    long long n_hard = 0, n_tie = 0, n_off = 0, n_slow = 0, n_mapped = 0;
+    NdpSiteMap nsm[3];                       // nearest-site maps per geometry (ndp_nsm.cuh)
+    std::vector<int> nsm_offs[3];
+    std::vector<uint32_t> nsm_ents[3];
+    NdpHcSlice hcs;
+    bool use_hc = false;                     // hypercube-mask bit <=> fully defined hypercube (see build_fused)
 };
 
 static void set_bit(std::vector<uint32_t> &b, long long i) { b[i >> 5] |= 1u << (i & 31); }
@@ -114,6 +120,45 @@ static void build_red(HsTable *t, int m)
     build_pyr(t, t->red[m], level0, nvar, var_axis, dim, false);
 }
 
+// mirrors the register-time part of the fused path in ndp_api.cu: nearest-site maps (k_nsm_count ->
+// exclusive scan -> k_nsm_fill), the hypercube-mask slice and the associated-axes consistency check
+static void build_fused(HsTable *t)
+{
+    const NdpGeom &g = t->g;
+    for (int geo = 0; geo < 3; geo++) {
+        const int m = geo == NSM_GEO_VERTEX ? 0 : 1;
+        NdpSiteMap &M = t->nsm[geo];
+        nsm_setup(g, t->red[m].dev, geo, M);
+        if (!M.valid) continue;
+        std::vector<unsigned long long> cand(NSM_KMAX);
+        std::vector<int> &offs = t->nsm_offs[geo];
+        std::vector<uint32_t> &ents = t->nsm_ents[geo];
+        offs.assign(M.nregions + 1, 0);
+        for (int r = 0; r < M.nregions; r++) {
+            int n = nsm_region_candidates(M, r, cand.data());
+            if (n < 0) n = 0;
+            offs[r + 1] = offs[r] + n;
+            const size_t at = ents.size();
+            ents.resize(at + (size_t) n * M.ew);
+            nsm_write_entries(M, cand.data(), n, ents.data() + at);
+        }
+        if (ents.empty()) ents.push_back(0);
+        M.offs = offs.data(); M.ents = ents.data();
+    }
+    const NdpPyramid &R = t->red[1].dev;
+    t->hcs.nvar = R.nvar;
+    for (int j = 0; j < R.nvar; j++) { t->hcs.var_axis[j] = R.var_axis[j]; t->hcs.sstride[j] = R.stride[0][j]; }
+    t->hcs.bits = R.bits[0];
+    // mirrors k_assoc_consistent: component 0 of a basic vertex is NaN at every associated index or at none
+    bool consistent = true;
+    const long long per = g.vstride[g.nbasic - 1];
+    for (long long v = 0; v < g.nverts && consistent; v++) {
+        const bool first = std::isnan(t->grid[v * per * g.vdim]);
+        for (long long k = 1; k < per; k++) if (std::isnan(t->grid[(v * per + k) * g.vdim]) != first) { consistent = false; break; }
+    }
+    t->use_hc = consistent;
+}
+
 extern "C" void *hs_create(int naxes, int nbasic, const int *axlen, const double *ticks, int vdim, const double *grid, int with_cells)
 {
     HsTable *t = new HsTable();
@@ -163,6 +208,7 @@ extern "C" void *hs_create(int naxes, int nbasic, const int *axlen, const double
     build_pyr(t, t->pyr[1], hb, nbasic, all_axes, g.len, true);
     build_red(t, 0);
     build_red(t, 1);
+    build_fused(t);
     if (with_cells && naxes <= 6) {          // mirrors k_build_cells
         const int n = naxes, V = vdim;
         t->cells.resize((size_t) (ncells << n) * V);
@@ -316,36 +362,101 @@ extern "C" void hs_find_nearest(void *h, long long n, const double *q, int metho
 }
 
 template <int N, bool CM, bool V1>
-static void ndpolate_n(HsTable *t, long long nq, const double *q, int method, int search, double *interps, double *dists)
+static void ndpolate_one(HsTable *t, long long i, const double *q, int method, int search, double *interps, double *dists)
 {
     const NdpGeom &g = t->g;
     const int n = N ? N : g.naxes, V = g.vdim;
     const double *cells = t->cells.empty() ? nullptr : t->cells.data();
-    for (long long i = 0; i < nq; i++) {
-        int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES]; double nrm[NDP_MAX_AXES];
-        ndp_import_query<N>(g, t->ticks.data(), q + i * n, idx, flg, nrm);
-        unsigned pin, sel;
-        const bool oob = ndp_classify<N>(g, flg, nrm, pin, sel);
-        bool fdhc = !oob;
-        if (!oob) {
-            for (int k = 0; k < V; k++) {
-                bool bad = false;
-                double val = ndp_eval_cell<N, CM, V1>(g, t->grid.data(), cells, idx, nrm, pin, sel, k, bad);
-                if (k == 0 && bad) { fdhc = false; break; }
-                interps[i * V + k] = val;
-            }
+    int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES]; double nrm[NDP_MAX_AXES];
+    ndp_import_query<N>(g, t->ticks.data(), q + i * n, idx, flg, nrm);
+    unsigned pin, sel;
+    const bool oob = ndp_classify<N>(g, flg, nrm, pin, sel);
+    bool fdhc = !oob;
+    if (!oob) {
+        for (int k = 0; k < V; k++) {
+            bool bad = false;
+            double val = ndp_eval_cell<N, CM, V1>(g, t->grid.data(), cells, idx, nrm, pin, sel, k, bad);
+            if (k == 0 && bad) { fdhc = false; break; }
+            interps[i * V + k] = val;
         }
-        if (fdhc) { dists[i] = 0.0; continue; }
-        if (method == NDP_M_NONE) { for (int k = 0; k < V; k++) interps[i * V + k] = NAN; dists[i] = 0.0; continue; }
-        t->n_off++;
-        int vertex, coords[NDP_MAX_AXES];
-        search_one(t, q + i * n, method, search, &vertex, &dists[i], coords);
-        // mirrors k_finish: coords are re-derived from the chosen vertex
-        int c2[NDP_MAX_AXES];
-        ndp_decode_vertex(g, vertex, c2);
-        for (int a = g.nbasic; a < n; a++) c2[a] = ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
-        for (int k = 0; k < V; k++)
-            interps[i * V + k] = ndp_finish_component<N, CM, false>(g, t->grid.data(), cells, method, idx, nrm, c2, k);
+    }
+    if (fdhc) { dists[i] = 0.0; return; }
+    if (method == NDP_M_NONE) { for (int k = 0; k < V; k++) interps[i * V + k] = NAN; dists[i] = 0.0; return; }
+    t->n_off++;
+    int vertex, coords[NDP_MAX_AXES];
+    search_one(t, q + i * n, method, search, &vertex, &dists[i], coords);
+    // mirrors k_finish: coords are re-derived from the chosen vertex
+    int c2[NDP_MAX_AXES];
+    ndp_decode_vertex(g, vertex, c2);
+    for (int a = g.nbasic; a < n; a++) c2[a] = ndp_assoc_coord((double) idx[a] + nrm[a] - 1.0, g.len[a]);
+    for (int k = 0; k < V; k++)
+        interps[i * V + k] = ndp_finish_component<N, CM, false>(g, t->grid.data(), cells, method, idx, nrm, c2, k);
+}
+
+template <int N, bool CM, bool V1>
+static void ndpolate_n(HsTable *t, long long nq, const double *q, int method, int search, double *interps, double *dists)
+{
+    for (long long i = 0; i < nq; i++) ndpolate_one<N, CM, V1>(t, i, q, method, search, interps, dists);
+}
+
+// mirrors k_fused + k_slow: the plan settles a query from the masks and the nearest-site map, the gather
+// reduces one cell of the cell-major copy; what the plan cannot settle is redone by the generic path
+template <int N, int METHOD, int MODE>
+static void fused_n(HsTable *t, long long nq, const double *q, int search, double *interps, double *dists)
+{
+    const NdpGeom &g = t->g;
+    const NdpSiteMap &M = t->nsm[nsm_geo_of_mode(MODE)];
+    for (long long i = 0; i < nq; i++) {
+        int idx[N], flg[N]; double nrm[N];
+        ndp_import_query<N>(g, t->ticks.data(), q + i * N, idx, flg, nrm);
+        NdpPlan<N> P;
+        ndp_fused_plan<N, METHOD, MODE>(g, t->hcs, t->hcs.bits, M, idx, flg, nrm, P);
+        switch (P.kind) {
+        case NDP_PLAN_GATHER: {
+            bool bad;
+            const double2 *b2 = reinterpret_cast<const double2 *>(t->cells.data() + (P.cell << N));
+            interps[i] = ndp_cell_reduce_halves<N>(b2, P.x, P.pin, P.sel, bad);
+            dists[i] = P.dist;
+            t->n_mapped += (P.dist != 0.0);
+            break;
+        }
+        case NDP_PLAN_VALUE: interps[i] = t->grid[P.vflat]; dists[i] = P.dist; t->n_mapped++; break;
+        case NDP_PLAN_NAN: interps[i] = NAN; dists[i] = 0.0; break;
+        default:
+            t->n_slow++;
+            ndpolate_one<0, false, false>(t, i, q, METHOD, search, interps, dists);
+        }
+    }
+}
+
+template <int N>
+static bool fused_dispatch(HsTable *t, long long nq, const double *q, int method, int search, double *interps, double *dists)
+{
+    if (method == NDP_M_NONE) { fused_n<N, NDP_M_NONE, 0>(t, nq, q, search, interps, dists); return true; }
+    const int mode = ndp_mode_of(method, search);
+    if (!t->nsm[nsm_geo_of_mode(mode)].valid) return false;
+    switch (mode) {
+    case 0: fused_n<N, NDP_M_NEAREST, 0>(t, nq, q, search, interps, dists); break;
+    case 1: fused_n<N, NDP_M_LINEAR, 1>(t, nq, q, search, interps, dists); break;
+    case 2: fused_n<N, NDP_M_NEAREST, 2>(t, nq, q, search, interps, dists); break;
+    default: fused_n<N, NDP_M_LINEAR, 3>(t, nq, q, search, interps, dists); break;
+    }
+    return true;
+}
+
+// the fused path serves scalar tables with a cell-major copy, 2..6 axes, whose hypercube-mask bit decides
+// "fully defined" (ndp_api.cu: fused_ok); returns 0 when this table / mode does not qualify
+extern "C" int hs_ndpolate_fused(void *h, long long n, const double *q, int method, int search, double *interps, double *dists)
+{
+    HsTable *t = (HsTable *) h;
+    const NdpGeom &g = t->g;
+    if (g.vdim != 1 || t->cells.empty() || g.naxes < 2 || g.naxes > 6 || !t->use_hc) return 0;
+    switch (g.naxes) {
+    case 2: return fused_dispatch<2>(t, n, q, method, search, interps, dists);
+    case 3: return fused_dispatch<3>(t, n, q, method, search, interps, dists);
+    case 4: return fused_dispatch<4>(t, n, q, method, search, interps, dists);
+    case 5: return fused_dispatch<5>(t, n, q, method, search, interps, dists);
+    default: return fused_dispatch<6>(t, n, q, method, search, interps, dists);
     }
 }
 
@@ -373,4 +484,15 @@ extern "C" void hs_ndpolate(void *h, long long n, const double *q, int method, i
 
 extern "C" void hs_variant_axes(void *h, int *out) { HsTable *t = (HsTable *) h; out[0] = t->red[0].dev.nvar; out[1] = t->red[1].dev.nvar; }
 
-extern "C" void hs_stats(void *h, long long *out) { HsTable *t = (HsTable *) h; out[0] = t->n_off; out[1] = t->n_hard; out[2] = t->n_tie; }
+extern "C" void hs_stats(void *h, long long *out) { HsTable *t = (HsTable *) h; out[0] = t->n_off; out[1] = t->n_hard; out[2] = t->n_tie; out[3] = t->n_slow; out[4] = t->n_mapped; }
+
+// nearest-site map summary per geometry: valid, S, regions, entries
+extern "C" void hs_nsm_info(void *h, long long *out)
+{
+    HsTable *t = (HsTable *) h;
+    for (int geo = 0; geo < 3; geo++) {
+        const NdpSiteMap &M = t->nsm[geo];
+        out[4 * geo] = M.valid; out[4 * geo + 1] = M.S; out[4 * geo + 2] = M.nregions;
+        out[4 * geo + 3] = M.valid ? t->nsm_offs[geo].back() : 0;
+    }
+}
