@@ -95,12 +95,26 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def measured_traffic(batch):
-    """DRAM bytes of one launch of the dominant kernel, scaled from the committed ncu capture
-    (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum at its batch size)."""
+def kernel_source_digest():
+    """sha256 over the CUDA sources: an ncu capture is only quoted for the code it was taken on."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'ndpolator_b200', 'csrc')
+    for name in sorted(os.listdir(d)):
+        h.update(name.encode())
+        h.update(open(os.path.join(d, name), 'rb').read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(batch, workload_key):
+    """DRAM bytes of one launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum from
+    an `ncu --set full` capture, tools/traffic_from_ncu.py -> profiles/r02_traffic.json), scaled to this
+    batch.  None unless the capture was taken on exactly these kernel sources and this workload."""
     try:
-        t = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
-        return t['k_gather_staged<5,0,1,4>']['dram_bytes'] * batch / t['batch']
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
+        if t.get('source_digest') != kernel_source_digest() or t.get('workload') != workload_key:
+            return None
+        return t['dram_bytes_per_launch'] * batch / t['queries_per_launch']
     except Exception:
         return None
 
@@ -245,7 +259,7 @@ def run_b200(args):
     for s in range(W):
         T.ndpolate(qs[s % 2], method, search, out=(interps, dists))
 
-    keys = ('launches', 'offgrid', 'hard', 'ties', 'main_ns', 'search_ns', 'finish_ns')
+    keys = ('launches', 'offgrid', 'hard', 'ties', 'slow', 'fused', 'main_ns', 'search_ns', 'finish_ns')
     acc = dict.fromkeys(keys, 0)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -286,7 +300,12 @@ def run_b200(args):
     if ws > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = ws * nb_e2e * args.e2e_steps / float(e2e_s.item())
-    same = bool(torch.equal(ih.view(torch.int64), interps[:nb_e2e].cpu().view(torch.int64))) if (K % 2 == 1) else None
+    # the pipelined host path (chunks, two slots, three streams) against a device-resident run of the same rows
+    ref_i, ref_d = T.ndpolate(qs[0][:nb_e2e], method, search)
+    same = bool(torch.equal(ih.view(torch.int64), ref_i.cpu().view(torch.int64)) and
+                torch.equal(dh.view(torch.int64), ref_d.cpu().view(torch.int64)))
+    if not same:
+        raise SystemExit('bench.py: end-to-end (host buffer) results differ from the device-resident run')
 
     if ws > 1:    # the only collective besides timing: a final gather of per-rank checksums to rank 0
         sums = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(ws)] if rank == 0 else None
@@ -298,11 +317,26 @@ def run_b200(args):
         peak, peak_src = measured_peak()
         n_fdhc = B * K - acc['offgrid']
         main_s = acc['main_ns'] / 1e9 / K
-        # k_main, per launch: every query row read (naxes*8) + for the queries it completes
-        # (fully defined hypercube) the 2^n-corner gather, the interps row and the dist
-        per_fdhc = (1 << w.naxes) * w.vdim * 8 + w.vdim * 8 + 8
-        main_bytes = B * w.naxes * 8 + (n_fdhc / K) * per_fdhc
+        cell_bytes = (1 << w.naxes) * w.vdim * 8
+        out_bytes = w.vdim * 8 + 8
+        fused = acc['fused'] == K
+        if fused:
+            # k_fused, per launch: every query row read (naxes*8), ONE gather per query -- its own cell, or for
+            # an extrapolated query the cell below the found hypercube ('linear') / the found vertex ('nearest')
+            # -- and every interps row and dist written; queries handed to k_slow gather nothing here
+            n_slow = acc['slow'] / K
+            off = acc['offgrid'] / K - n_slow
+            gather = cell_bytes if method == 2 else (w.vdim * 8 if method == 1 else 0)
+            main_bytes = B * w.naxes * 8 + (n_fdhc / K) * cell_bytes + off * gather + (B - n_slow) * out_bytes
+            kernel_name = f'k_fused<{w.naxes},{method},{(0 if search == 0 else 2) + (1 if method == 2 else 0)}>'
+        else:
+            # k_gather_staged / k_main, per launch: every query row read + for the queries it completes (fully
+            # defined hypercube) the 2^n-corner gather, the interps row and the dist
+            main_bytes = B * w.naxes * 8 + (n_fdhc / K) * (cell_bytes + out_bytes)
+            kernel_name = 'k_gather_staged<N,0> / k_main (fused import + cell gather + reduce, first of three passes)'
         achieved = main_bytes / main_s / 1e9 if main_s > 0 else None
+        wl_key = f'{args.workload}@{args.scale}/{args.mix}/{args.method or w.method}/{args.search}'
+        traffic = measured_traffic(B, wl_key) if fused else None
         step_gbs = B * w.bytes_per_query / (ms_total / 1e3 / K) / 1e9
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': ws, 'steps': K, 'warmup': W,
@@ -314,10 +348,12 @@ def run_b200(args):
             'gpu_launches': acc['launches'],
             'clocks': clocks,
             'roofline': {
-                'bound': 'hbm', 'kernel': 'k_gather_staged<N,0> / k_main (fused import + cell gather + reduce)',
+                'bound': 'hbm', 'kernel': kernel_name,
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': (achieved / peak) if achieved else None,
-                'traffic': measured_traffic(B) if (args.workload == 'C4' and args.scale is None and not args.method) else None,
+                'traffic': traffic,
+                'traffic_source': ('profiles/r02_traffic.json (ncu --set full on these sources, scaled to this batch)'
+                                   if traffic else 'no ncu capture of exactly these kernel sources / this workload'),
                 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': main_bytes, 'avg_launch_ms': main_s * 1e3,
                 'whole_step': {'achieved': step_gbs, 'frac': step_gbs / peak,
@@ -326,7 +362,9 @@ def run_b200(args):
                                       'k_finish': acc['finish_ns'] / 1e6 / K},
             },
             'mix_measured': {'in_fully_defined_hypercube': n_fdhc / (B * K), 'offgrid': acc['offgrid'] / (B * K),
-                             'needed_lattice_descent': acc['hard'] / (B * K), 'kd_ties': acc['ties']},
+                             'needed_lattice_descent': acc['hard'] / (B * K), 'kd_ties': acc['ties'],
+                             'left_to_exact_generic_kernel': acc['slow'] / (B * K)},
+            'path': 'fused (k_fused + k_slow)' if fused else 'three-pass (gather, search, finish)',
             'table': {'cellmajor': bool(T.stat('cellmajor')), 'build_s': build_s},
             'checksum': checksum,
         }

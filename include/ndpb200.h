@@ -108,10 +108,22 @@ int ndpb_table_masks(ndpb_table *t, int32_t *vmask, int32_t *hcmask);
  * tree) per basic vertex.  method is NDPB_METHOD_NEAREST or _LINEAR. */
 int ndpb_table_tree_topology(ndpb_table *t, int method, int32_t *parent, int32_t *depth);
 
+/* Stream ordering for DEVICE-resident inputs.  The table launches its kernels on its own non-blocking
+ * stream, which is not ordered against the stream that produced a device query buffer (e.g. torch's
+ * current stream).  Call this with the producer's cudaStream_t (as integer; 0 = the legacy default stream)
+ * before a call that takes device pointers: the table's stream then waits for everything enqueued on the
+ * producer stream so far.  Every entry point returns only after its results are complete, so no ordering
+ * is needed on the output side.  Host pointers need none of this.  (The reference is synchronous host
+ * code, src/ndp_py.c:343-409; this is the price of accepting device pointers.) */
+int ndpb_table_wait_stream(ndpb_table *t, uint64_t producer_stream);
+
 /* Tuning knobs that never change results.  Keys: "gather" = 0 auto | 1 strided
  * (original layout) | 2 cell-major; "linear_search" = 0 auto | 1 brute force |
- * 2 lattice; "chunk" = queries per staged chunk for host buffers; "staged" = 0 auto | 1 never use the cp.async
- * staged gather kernel; "search_fast_blocks_per_sm" / "search_hard_blocks_per_sm" =
+ * 2 lattice; "chunk" = queries per staged chunk for host buffers; "fused" = 0 auto | 1 never use the
+ * fused kernel (import + mask/nearest-site-map plan + one cell gather per query); "staged" = 0 auto: one-stage
+ * cp.async gather, 4 CTAs/SM | 1 never use the staged gather kernels | 2 two-stage ring | 3 one stage,
+ * 5 CTAs/SM (only used when the fused kernel is off or does not apply);
+ * "search_fast_blocks_per_sm" / "search_hard_blocks_per_sm" =
  * grid-stride CTAs per SM of the two search passes (default 64 / 256); "stream" = a
  * cudaStream_t (as integer) to launch the kernels on instead of the table's own
  * stream, 0 to restore it. */
@@ -119,9 +131,14 @@ int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t value);
 
 /* Per-table counters of the last call, for bench.py / tests:
  * "launches" kernels launched, "offgrid" queries sent to the search,
- * "hard" queries that needed the tree/lattice descent, "ties" queries resolved
- * through the kd topology, "h2d_bytes", "d2h_bytes", "cellmajor" (0/1),
- * "kernel_ns" device time of the main gather kernel (CUDA events). */
+ * "hard" queries that needed the lattice descent, "ties" queries resolved
+ * through the kd topology, "slow" queries the fused kernel handed to the exact generic
+ * kernel, "fused" batches that went through the fused kernel, "h2d_bytes", "d2h_bytes",
+ * "cellmajor" (0/1), "use_hc" (0/1: the hypercube-mask bit decides "fully defined"),
+ * "main_ns" / "search_ns" / "finish_ns" device time (CUDA events) of the gather kernel
+ * (fused or staged), of the search / slow-list kernels and of the extrapolation finish,
+ * "nsm_regions_nearest" / "nsm_regions_linear" regions of the nearest-site maps built so
+ * far, "variant_axes_*", "tree_levels_*".  Unknown keys return -1. */
 int64_t ndpb_table_stat(const ndpb_table *t, const char *key);
 
 const char *ndpb_last_error(void);

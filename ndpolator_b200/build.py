@@ -11,9 +11,13 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libndpb200.so')
-SOURCES = ['ndp_api.cu', 'ndp_tu_main_strided.cu', 'ndp_tu_main_cellmajor.cu', 'ndp_tu_finish.cu',
-           'ndp_tu_search.cu', 'ndp_tu_staged.cu']
-HEADERS = ['ndp_core.cuh', 'ndp_kernels.cuh', 'ndp_table.cuh', 'ndp_launch.h', os.path.join('..', '..', 'include', 'ndpb200.h')]
+# (source, object stem, extra defines): ndp_tu_fused.cu is compiled once per axis count
+SOURCES = [('ndp_api.cu', 'ndp_api', []), ('ndp_tu_main_strided.cu', 'ndp_tu_main_strided', []),
+           ('ndp_tu_main_cellmajor.cu', 'ndp_tu_main_cellmajor', []), ('ndp_tu_finish.cu', 'ndp_tu_finish', []),
+           ('ndp_tu_search.cu', 'ndp_tu_search', []), ('ndp_tu_staged.cu', 'ndp_tu_staged', [])] + \
+          [('ndp_tu_fused.cu', f'ndp_tu_fused_{n}', [f'-DNDP_FUSED_N={n}']) for n in (5, 6, 4, 3, 2)]
+HEADERS = ['ndp_core.cuh', 'ndp_nsm.cuh', 'ndp_fused.cuh', 'ndp_kernels.cuh', 'ndp_fused_kernels.cuh', 'ndp_table.cuh',
+           'ndp_launch.h', os.path.join('..', '..', 'include', 'ndpb200.h')]
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
@@ -34,7 +38,7 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     built = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, s) for s in [src for src, _, _ in SOURCES] + HEADERS]
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
 
 
@@ -50,9 +54,10 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), lib_out: s
     objdir = os.path.join(HERE, 'build') if lib_out is None else os.path.splitext(out)[0] + '_obj'
     os.makedirs(objdir, exist_ok=True)
 
-    def compile_one(src):
-        obj = os.path.join(objdir, os.path.splitext(src)[0] + '.o')
-        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ['-c', '-o', obj, os.path.join(CSRC, src)]
+    def compile_one(item):
+        src, stem, defines = item
+        obj = os.path.join(objdir, stem + '.o')
+        cmd = [nvcc] + NVCC_FLAGS + defines + list(extra_flags) + ['-c', '-o', obj, os.path.join(CSRC, src)]
         if verbose:
             print(' '.join(cmd))
         res = subprocess.run(cmd, capture_output=True, text=True)

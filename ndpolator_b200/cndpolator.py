@@ -54,11 +54,13 @@ def _host_f64(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-def _prep_queries(query_pts, naxes):
+def _prep_queries(query_pts, naxes, device_index=None):
     """-> (array kept alive, pointer, n, on_device)"""
     if _is_cuda(query_pts):
         import torch
-        q = query_pts if isinstance(query_pts, torch.Tensor) else torch.as_tensor(query_pts, device='cuda')
+        q = query_pts if isinstance(query_pts, torch.Tensor) else torch.as_tensor(query_pts, device=f'cuda:{device_index or 0}')
+        if device_index is not None and q.device.index != device_index:
+            raise ValueError(f'query_pts lives on {q.device}, the table on cuda:{device_index}')
         if q.dtype != torch.float64 or not q.is_contiguous():
             q = q.to(torch.float64).contiguous()
         if q.dim() == 1:
@@ -142,9 +144,32 @@ class Table:
         _lib.check(_lib.lib().ndpb_table_tree_topology(self._h, int(method), parent.ctypes.data, depth.ctypes.data))
         return parent, depth
 
+    def _order_after_producer(self, on_device):
+        """Device-resident inputs: make the table's stream wait for what the caller's current torch
+        stream has enqueued so far (ndpb_table_wait_stream; host inputs need no ordering)."""
+        if on_device:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib().ndpb_table_wait_stream(self._h, stream))
+
+    def _check_out(self, out, n, on_device):
+        interps, dists = out
+        for arr, shape, what in ((interps, (n, self.vdim), 'interps'), (dists, (n, 1), 'dists')):
+            if _is_cuda(arr) != on_device:
+                raise ValueError(f'out[{what}] must live where query_pts lives (device or host)')
+            if on_device:
+                import torch
+                if arr.device.index != self.device or arr.dtype != torch.float64 or not arr.is_contiguous():
+                    raise ValueError(f'out[{what}] must be a contiguous float64 tensor on cuda:{self.device}')
+            elif arr.dtype != np.float64 or not arr.flags['C_CONTIGUOUS']:
+                raise ValueError(f'out[{what}] must be a C-contiguous float64 array')
+            if tuple(arr.shape) != shape and not (what == 'dists' and tuple(arr.shape) == (n,)):
+                raise ValueError(f'out[{what}] must have shape {shape}')
+
     # -- hot path ----------------------------------------------------------------
     def find(self, query_pts):
-        q, qp, n, dev = _prep_queries(query_pts, self.naxes)
+        q, qp, n, dev = _prep_queries(query_pts, self.naxes, self.device)
+        self._order_after_producer(dev)
         idx = _empty((n, self.naxes), np.int32, dev, self.device)
         flg = _empty((n, self.naxes), np.int32, dev, self.device)
         nrm = _empty((n, self.naxes), np.float64, dev, self.device)
@@ -165,24 +190,28 @@ class Table:
         return dim, fdhc, v
 
     def find_nearest(self, query_pts, method, search):
-        q, qp, n, dev = _prep_queries(query_pts, self.naxes)
+        q, qp, n, dev = _prep_queries(query_pts, self.naxes, self.device)
+        self._order_after_producer(dev)
         coords = _empty((n, self.naxes), np.int32, dev, self.device)
         dist = _empty((n,), np.float64, dev, self.device)
         _lib.check(_lib.lib().ndpb_find_nearest(self._h, qp, n, int(method), int(search), _ptr(coords), _ptr(dist)))
         return coords, dist
 
     def ndpolate(self, query_pts, method=0, search=0, out=None):
-        q, qp, n, dev = _prep_queries(query_pts, self.naxes)
+        q, qp, n, dev = _prep_queries(query_pts, self.naxes, self.device)
+        self._order_after_producer(dev)
         if out is None:
             interps = _empty((n, self.vdim), np.float64, dev, self.device)
             dists = _empty((n, 1), np.float64, dev, self.device)
         else:
+            self._check_out(out, n, dev)
             interps, dists = out
         _lib.check(_lib.lib().ndpb_ndpolate(self._h, qp, n, int(method), int(search), _ptr(interps), _ptr(dists)))
         return interps, dists
 
     def distance(self, query_pts):
-        q, qp, n, dev = _prep_queries(query_pts, self.naxes)
+        q, qp, n, dev = _prep_queries(query_pts, self.naxes, self.device)
+        self._order_after_producer(dev)
         dists = _empty((n, 1), np.float64, dev, self.device)
         _lib.check(_lib.lib().ndpb_distance(self._h, qp, n, _ptr(dists)))
         return dists

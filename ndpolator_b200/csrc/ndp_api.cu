@@ -72,6 +72,7 @@ struct Slot {                               // one in-flight batch
     cudaEvent_t in_done = nullptr, searched = nullptr, out_ready = nullptr, out_done = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;   // phase timing
     bool used = false;
+    bool fused = false;                     // this batch went through k_fused (its tie list holds query ids)
 };
 
 struct ndpb_table {
@@ -84,17 +85,24 @@ struct ndpb_table {
     Pyramid pyr[2];                         // [0] vmask, [1] hcmask: over the whole basic lattice
     Pyramid red[2];                         // the same masks over their variant axes only
     Topology topo[2];
+    // fused path (ndp_fused_kernels.cuh): nearest-site maps per geometry (lazy), hypercube-mask slice
+    NdpSiteMap nsm[3]{};
+    bool nsm_tried[3] = {false, false, false};
+    int *nsm_offs[3] = {nullptr, nullptr, nullptr};
+    uint32_t *nsm_ents[3] = {nullptr, nullptr, nullptr};
+    NdpHcSlice hcs{};
+    bool use_hc = false;                    // hypercube-mask bit <=> hypercube fully defined
     cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
     cudaStream_t s_owned = nullptr;         // the compute stream this table created (s_compute may be a caller's)
     Slot slot[2];
     std::mutex mu;
     int sm_count = 148;
     // options
-    int opt_gather = 0, opt_linear_search = 0, opt_staged = 0;
+    int opt_gather = 0, opt_linear_search = 0, opt_staged = 0, opt_fused = 0;
     long long opt_chunk = 1 << 20;          // profiles/r01p_sweep_chunk.txt: 1 Mi beats 2, 4 and 8 Mi end to end
     int opt_fast_blocks = 64, opt_hard_blocks = 256;   // grid-stride CTAs per SM of the two search passes (profiles/r01p_sweep_search.txt)
     // stats of the last call
-    long long st_launches = 0, st_offgrid = 0, st_hard = 0, st_ties = 0, st_h2d = 0, st_d2h = 0;
+    long long st_launches = 0, st_offgrid = 0, st_hard = 0, st_ties = 0, st_h2d = 0, st_d2h = 0, st_slow = 0, st_fused = 0;
     double st_main_ms = 0, st_search_ms = 0, st_finish_ms = 0;
 };
 
@@ -235,6 +243,7 @@ extern "C" int ndpb_table_destroy(ndpb_table *t)
             cudaFree(set[m].d_desc);
         }
     for (auto &T : t->topo) { cudaFree(T.parent); cudaFree(T.depth); }
+    for (int geo = 0; geo < 3; geo++) { cudaFree(t->nsm_offs[geo]); cudaFree(t->nsm_ents[geo]); }
     for (auto &s : t->slot) free_slot(s);
     if (t->s_owned) cudaStreamDestroy(t->s_owned);
     if (t->s_in) cudaStreamDestroy(t->s_in);
@@ -257,6 +266,67 @@ static int maybe_build_cells(ndpb_table *t)
     k_build_cells<<<t->sm_count * 16, NDP_BLOCK, 0, t->s_compute>>>(g, t->grid, t->cells);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(t->s_compute));
+    return NDPB_OK;
+}
+
+// Register-time products of the fused path that do not depend on the search mode: the hypercube-mask
+// slice, and whether its bit decides "fully defined" -- always when every axis is basic; with associated
+// axes only if component 0 of a basic vertex is NaN at every associated index or at none
+// (ndp_types.c:179-184 looks at associated index 0 only, ndpolator.c:491 at the corner actually used).
+static int setup_fused(ndpb_table *t)
+{
+    const NdpGeom &g = t->g;
+    const NdpPyramid &R = t->red[1].dev;
+    t->hcs = NdpHcSlice{};
+    long long nslice = 1;
+    for (int j = 0; j < R.nvar; j++) { t->hcs.astride[R.var_axis[j]] = R.stride[0][j]; nslice *= g.len[R.var_axis[j]]; }
+    t->hcs.bits = R.bits[0];
+    t->hcs.nwords = (int) ((nslice + 31) / 32);
+    t->use_hc = true;
+    if (g.nbasic < g.naxes) {
+        int *d_flag = nullptr, flag = 1;
+        CU(cudaMalloc(&d_flag, sizeof(int)));
+        CU(cudaMemcpyAsync(d_flag, &flag, sizeof(int), cudaMemcpyHostToDevice, t->s_compute));
+        cudaError_t e = ndp_launch_assoc_consistent(t->grid, g.nverts, g.vstride[g.nbasic - 1], g.vdim, d_flag, t->sm_count * 8, t->s_compute);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, t->s_compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(t->s_compute);
+        cudaFree(d_flag);
+        CU(e);
+        t->use_hc = flag != 0;
+    }
+    return NDPB_OK;
+}
+
+// Lazily builds the nearest-site map of one geometry (k_nsm_count -> exclusive scan -> k_nsm_fill).
+static int ensure_nsm(ndpb_table *t, int geo)
+{
+    if (t->nsm_tried[geo]) return NDPB_OK;
+    t->nsm_tried[geo] = true;
+    NdpSiteMap M;
+    nsm_setup(t->g, t->red[geo == NSM_GEO_VERTEX ? 0 : 1].dev, geo, M);
+    if (!M.valid) return NDPB_OK;
+    cudaStream_t st = t->s_owned;
+    int *counts = nullptr, *offs = nullptr;
+    uint32_t *ents = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int total = 0;
+    cudaError_t e = cudaMalloc(&counts, sizeof(int) * ((size_t) M.nregions + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&offs, sizeof(int) * ((size_t) M.nregions + 1));
+    if (e == cudaSuccess) e = cudaMemsetAsync(counts, 0, sizeof(int) * ((size_t) M.nregions + 1), st);
+    if (e == cudaSuccess) e = ndp_launch_nsm_count(M, counts, st);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, offs, M.nregions + 1, st);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, offs, M.nregions + 1, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&total, offs + M.nregions, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaMalloc(&ents, sizeof(uint32_t) * ((size_t) std::max(total, 1) * M.ew));
+    if (e == cudaSuccess) { M.offs = offs; e = ndp_launch_nsm_fill(M, ents, st); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(counts); cudaFree(tmp);
+    if (e != cudaSuccess) { cudaFree(offs); cudaFree(ents); CU(e); }
+    M.ents = ents;
+    t->nsm[geo] = M; t->nsm_offs[geo] = offs; t->nsm_ents[geo] = ents;
     return NDPB_OK;
 }
 
@@ -353,6 +423,7 @@ extern "C" int ndpb_table_create(const double *const *axes, const int32_t *axlen
         if (rc == NDPB_OK) rc = build_reduced(t, 0);
         if (rc == NDPB_OK) rc = build_reduced(t, 1);
         if (rc == NDPB_OK) rc = maybe_build_cells(t);
+        if (rc == NDPB_OK) rc = setup_fused(t);
         if (rc != NDPB_OK) return bail(rc);
     }
 #undef CUT
@@ -392,6 +463,11 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
         t->opt_staged = (int) value;
         return NDPB_OK;
     }
+    if (k == "fused") {
+        if (value < 0 || value > 1) return fail(NDPB_ERR_INVALID, "fused must be 0 (auto) or 1 (never use the fused kernel)");
+        t->opt_fused = (int) value;
+        return NDPB_OK;
+    }
     if (k == "chunk") {
         if (value < 1024) return fail(NDPB_ERR_INVALID, "chunk must be >= 1024");
         t->opt_chunk = value;
@@ -405,6 +481,22 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
     return fail(NDPB_ERR_INVALID, "unknown option " + k);
 }
 
+extern "C" int ndpb_table_wait_stream(ndpb_table *t, uint64_t producer_stream)
+{
+    if (!t) return fail(NDPB_ERR_INVALID, "table is NULL");
+    std::lock_guard<std::mutex> lk(t->mu);
+    CU(cudaSetDevice(t->device));
+    cudaStream_t src = (cudaStream_t) (uintptr_t) producer_stream;
+    if (src == t->s_compute) return NDPB_OK;
+    cudaEvent_t ev = nullptr;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, src);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(t->s_compute, ev, 0);
+    cudaEventDestroy(ev);
+    CU(e);
+    return NDPB_OK;
+}
+
 extern "C" int64_t ndpb_table_stat(const ndpb_table *t, const char *key)
 {
     if (!t || !key) return -1;
@@ -416,6 +508,11 @@ extern "C" int64_t ndpb_table_stat(const ndpb_table *t, const char *key)
     if (k == "h2d_bytes") return t->st_h2d;
     if (k == "d2h_bytes") return t->st_d2h;
     if (k == "cellmajor") return t->cells ? 1 : 0;
+    if (k == "slow") return t->st_slow;
+    if (k == "fused") return t->st_fused;
+    if (k == "use_hc") return t->use_hc ? 1 : 0;
+    if (k == "nsm_regions_nearest") return t->nsm[NSM_GEO_VERTEX].valid ? t->nsm[NSM_GEO_VERTEX].nregions : 0;
+    if (k == "nsm_regions_linear") return t->nsm[NSM_GEO_CENTRE].valid ? t->nsm[NSM_GEO_CENTRE].nregions : 0;
     if (k == "main_ns") return (int64_t) (t->st_main_ms * 1e6);
     if (k == "search_ns") return (int64_t) (t->st_search_ms * 1e6);
     if (k == "finish_ns") return (int64_t) (t->st_finish_ms * 1e6);
@@ -670,6 +767,64 @@ static int launch_search(ndpb_table *t, SearchArgs &A, long long upper, bool har
 
 enum Task { TASK_NDPOLATE, TASK_NEAREST, TASK_DISTANCE };
 
+// The fused kernel serves scalar tables with a cell-major copy, 2..6 axes, whose hypercube-mask bit decides
+// "fully defined", and -- when extrapolating -- a search mode that has a nearest-site map.
+static bool fused_ok(ndpb_table *t, int method, int search)
+{
+    if (t->opt_fused == 1 || !t->cells || t->g.vdim != 1 || t->g.naxes < 2 || t->g.naxes > 6 || !t->use_hc) return false;
+    if ((size_t) t->nticks * sizeof(double) > 16 * 1024) return false;
+    if (method == NDPB_METHOD_NONE) return true;
+    if (use_brute(t, search)) return false;
+    const int geo = nsm_geo_of_mode(ndp_mode_of(method, search));
+    if (ensure_nsm(t, geo) != NDPB_OK) return false;
+    return t->nsm[geo].valid != 0;
+}
+
+static int launch_fused(ndpb_table *t, Slot &s, const double *q, long long n, int method, int search,
+                        double *interps, double *dists, cudaStream_t st)
+{
+    const NdpGeom &g = t->g;
+    const int mode = ndp_mode_of(method, search);
+    FusedArgs A{};
+    A.g = g; A.ticks = t->ticks; A.nticks = t->nticks; A.cells = t->cells; A.grid = t->grid;
+    A.q = q; A.n = n; A.interps = interps; A.dists = dists;
+    A.H = t->hcs; A.hc_in_smem = t->hcs.nwords * sizeof(uint32_t) <= 8 * 1024;
+    if (method != NDPB_METHOD_NONE) A.M = t->nsm[nsm_geo_of_mode(mode)];
+    A.slowlist = s.list; A.ctr = s.ctr;
+    const size_t fixed = (((size_t) t->nticks * 8 + 127) & ~(size_t) 127) +
+                         (A.hc_in_smem ? (((size_t) t->hcs.nwords * 4 + 127) & ~(size_t) 127) : 0);
+    cudaError_t e;
+    switch (g.naxes) {
+    case 2: e = ndp_launch_fused_2(A, method, mode, t->sm_count, fixed, st); break;
+    case 3: e = ndp_launch_fused_3(A, method, mode, t->sm_count, fixed, st); break;
+    case 4: e = ndp_launch_fused_4(A, method, mode, t->sm_count, fixed, st); break;
+    case 5: e = ndp_launch_fused_5(A, method, mode, t->sm_count, fixed, st); break;
+    default: e = ndp_launch_fused_6(A, method, mode, t->sm_count, fixed, st); break;
+    }
+    CU(e);
+    t->st_launches++;
+    return NDPB_OK;
+}
+
+// k_slow over a device list of query ids: the slow list of the fused kernel, or (tie == true) the tie list
+static int launch_slow(ndpb_table *t, Slot &s, const double *q, int method, int search, double *interps, double *dists,
+                       bool tie, cudaStream_t st)
+{
+    const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;
+    SlowArgs A{};
+    A.g = t->g; A.F = t->pyr[m].d_desc; A.R = t->red[m].d_desc;
+    A.have_topo = t->topo[m].built ? 1 : 0;
+    A.topo.parent = t->topo[m].parent; A.topo.depth = t->topo[m].depth;
+    A.ticks = t->ticks; A.nticks = t->nticks; A.ticks_in_smem = ticks_in_smem(t);
+    A.grid = t->grid; A.q = q; A.method = method; A.search = search;
+    A.list = tie ? s.tielist : s.list;
+    A.count = tie ? &s.ctr->n_tie : &s.ctr->n_slow;
+    A.interps = interps; A.dists = dists; A.tielist = s.tielist; A.count_searched = tie ? 0 : 1; A.ctr = s.ctr;
+    CU(ndp_launch_slow(A, t->sm_count * 2, smem_bytes(t), st));
+    t->st_launches++;
+    return NDPB_OK;
+}
+
 // Enqueues everything that needs no host decision for one batch resident on the device.
 static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, long long n, int method, int search,
                          double *interps, double *dists, int *coords)
@@ -677,6 +832,21 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
     cudaStream_t st = t->s_compute;
     CU(cudaMemsetAsync(s.ctr, 0, sizeof(NdpCounters), st));
     CU(cudaEventRecord(s.t0, st));
+    s.fused = (task == TASK_NDPOLATE) && fused_ok(t, method, search);
+    if (s.fused) {
+        int rc = launch_fused(t, s, q, n, method, search, interps, dists, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(s.t1, st));
+        rc = launch_slow(t, s, q, method, search, interps, dists, false, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(s.t2, st));
+        CU(cudaEventRecord(s.t3, st));
+        CU(cudaMemcpyAsync(s.ctr_host, s.ctr, sizeof(NdpCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(s.searched, st));
+        s.used = true;
+        t->st_fused++;
+        return NDPB_OK;
+    }
     StagedArgs G{};
     G.g = t->g; G.ticks = t->ticks; G.nticks = t->nticks; G.cells = t->cells; G.q = q; G.n = n;
     G.interps = interps; G.dists = dists; G.method = method; G.offlist = s.list; G.chosen = s.chosen; G.ctr = s.ctr;
@@ -743,7 +913,16 @@ static int batch_complete(ndpb_table *t, Slot &s, Task task, const double *q, lo
     const NdpCounters c = *s.ctr_host;
     t->st_offgrid += (task == TASK_NDPOLATE) ? c.n_off : (method == NDPB_METHOD_NONE ? 0 : n);
     t->st_hard += c.n_hard;
-    if (c.n_tie > 0) {
+    t->st_slow += c.n_slow;
+    if (s.fused && c.n_tie > 0) {
+        // kd distance ties met by k_slow before the reference-shaped topology existed: build it, redo them
+        const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;
+        int rc = ensure_topology(t, m);
+        if (rc) return rc;
+        rc = launch_slow(t, s, q, method, search, interps, dists, true, st);
+        if (rc) return rc;
+        t->st_ties += c.n_tie;
+    } else if (c.n_tie > 0) {
         const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;
         int rc = ensure_topology(t, m);
         if (rc) return rc;
@@ -771,7 +950,7 @@ static int batch_complete(ndpb_table *t, Slot &s, Task task, const double *q, lo
 
 static void reset_stats(ndpb_table *t)
 {
-    t->st_launches = t->st_offgrid = t->st_hard = t->st_ties = t->st_h2d = t->st_d2h = 0;
+    t->st_launches = t->st_offgrid = t->st_hard = t->st_ties = t->st_h2d = t->st_d2h = t->st_slow = t->st_fused = 0;
     t->st_main_ms = t->st_search_ms = t->st_finish_ms = 0;
 }
 

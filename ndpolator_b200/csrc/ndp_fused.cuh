@@ -20,9 +20,7 @@
 // The slice of the hypercube mask over the axes it depends on: bit set <=> every corner of the
 // cell below that superior corner is defined (ndp_types.c:201-258).
 struct NdpHcSlice {
-    int nvar;
-    int var_axis[NDP_MAX_AXES];
-    int sstride[NDP_MAX_AXES];
+    int astride[NDP_MAX_AXES];     // per basic axis: its stride in the slice, 0 when the mask does not depend on it
     const uint32_t *bits;
     int nwords;
 };
@@ -35,6 +33,7 @@ struct NdpPlan {
     double x[N ? N : NDP_MAX_AXES];
     unsigned pin, sel;
     double dist;
+    int searched;              // 1: the query went to the nearest search (map or slow path)
 };
 
 template <int N>
@@ -64,10 +63,11 @@ NDP_HD void ndp_fused_plan(const NdpGeom &g, const NdpHcSlice &H, const uint32_t
     const int n = N ? N : g.naxes;
     const bool oob = ndp_classify<N>(g, flg, nrm, P.pin, P.sel);
     P.dist = 0.0;
+    P.searched = 0;
     if (!oob) {
         int h = 0;
 #pragma unroll
-        for (int j = 0; j < MM; j++) if (j < H.nvar) h += idx[H.var_axis[j]] * H.sstride[j];
+        for (int a = 0; a < MM; a++) if (a < g.nbasic) h += idx[a] * H.astride[a];
         if (ndp_bit(hcbits, h)) {
             // every corner of the query's cell is defined: the hypercube is fully defined whatever the
             // on-vertex reduction keeps (:455-505)
@@ -81,14 +81,15 @@ NDP_HD void ndp_fused_plan(const NdpGeom &g, const NdpHcSlice &H, const uint32_t
         if (P.pin != 0) { P.kind = NDP_PLAN_SLOW; return; }
     }
     if (METHOD == NDP_M_NONE) { P.kind = NDP_PLAN_NAN; return; }
+    P.searched = 1;
     NdpQuery Q;
-    ndp_make_query(g, idx, nrm, Q);
+    ndp_make_query_n<N>(g, idx, nrm, Q);
     NdpHit hit;
     if (!ndp_nsm_search<N, MODE>(g, M, Q, hit)) { P.kind = NDP_PLAN_SLOW; return; }
     int coords[MM];
 #pragma unroll
     for (int a = 0; a < MM; a++) if (a < n) coords[a] = a < g.nbasic ? hit.coords[a] : Q.acoord[a];
-    P.dist = (MODE >= NDP_MODE_LS_NEAREST) ? hit.dsel : ndp_reported_dist(g, METHOD, Q, coords);
+    P.dist = (MODE >= NDP_MODE_LS_NEAREST) ? hit.dsel : ndp_reported_dist_n<N, METHOD>(g, Q, coords);
     if (METHOD == NDP_M_NEAREST) {
         long long v = 0;
 #pragma unroll

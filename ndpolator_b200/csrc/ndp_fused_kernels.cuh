@@ -1,0 +1,294 @@
+// ndp_fused_kernels.cuh -- the fused ndpolate kernel and its companions.
+//
+//   k_fused      import + plan + ONE cell gather + reduce for every query, in-grid and
+//                extrapolated alike (ndp_query_pts_import + ndp_find_hypercubes + ndpolate,
+//                src/ndpolator.c:354-414, :416-508, :510-671; the nearest search of :188-352
+//                is a lookup in the nearest-site map, ndp_nsm.cuh)
+//   k_slow       the exact generic path, per query, for the few the plan cannot settle
+//                (kd distance ties, on-vertex queries beside a void, far-out points, NaN)
+//   k_nsm_count / k_nsm_fill   register time: the nearest-site map
+//   k_assoc_consistent         register time: is "vertex defined" independent of the associated index?
+//
+// Scalar tables (vdim 1) with a cell-major copy, 2..6 axes.  Per query the kernel moves
+// naxes*8 bytes of query, one contiguous (8 << naxes)-byte cell and 16 bytes of results --
+// exactly the algorithmic bytes of SURVEY 8(d) -- and nothing else touches HBM: no off-grid
+// records, no second pass, no fetch of cells that turn out to be incomplete.
+#pragma once
+
+#include <cuda_runtime.h>
+#include "ndp_fused.cuh"
+#include "ndp_kernels.cuh"
+
+#define NDP_FUSED_WARPS 4
+
+struct FusedArgs {
+    NdpGeom g;
+    const double *ticks; int nticks;
+    const double *cells; const double *grid;
+    const double *q; long long n;
+    double *interps; double *dists;
+    NdpHcSlice H; int hc_in_smem;
+    NdpSiteMap M;
+    int *slowlist;
+    NdpCounters *ctr;
+};
+
+#if defined(NDP_TU_FUSED)
+__device__ __forceinline__ unsigned ndpf_smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ndpf_cp_async16(unsigned dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ndpf_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ndpf_cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// c_ndpolate (:78-99) on a contiguous scalar cell without on-vertex axes: the common case, no selects.
+// Same pairing and order of operations as ndp_cell_reduce_halves, hence the same bits.
+template <int N>
+__device__ __forceinline__ double ndpf_reduce_plain(const double2 *b2, const double *x)
+{
+    constexpr int HC = 1 << (N - 2);
+    double res[2][2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        double fv[2 * HC];
+#pragma unroll
+        for (int mp = 0; mp < HC; mp++) { const double2 p = b2[2 * mp + h]; fv[2 * mp] = p.x; fv[2 * mp + 1] = p.y; }
+#pragma unroll
+        for (int a = 0; a < N - 2; a++) {
+            const int hb = 1 << (N - 2 - a);
+            const double xa = x[a];
+#pragma unroll
+            for (int j = 0; j < HC; j++)
+                if (j < hb) fv[j] = ndp_lerp(fv[j], fv[j + hb], xa);
+        }
+        res[h][0] = fv[0]; res[h][1] = fv[1];
+    }
+    const double r0 = ndp_lerp(res[0][0], res[1][0], x[N - 2]);
+    const double r1 = ndp_lerp(res[0][1], res[1][1], x[N - 2]);
+    return ndp_lerp(r0, r1, x[N - 1]);
+}
+
+template <int N, int METHOD, int MODE, int OCC>
+__global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __grid_constant__ FusedArgs A)
+{
+    constexpr unsigned CELL_BYTES = 8u << N;
+    constexpr unsigned SLOT = CELL_BYTES + 16u;           // +16: the 128-bit shared loads of a quarter warp hit distinct bank groups
+    constexpr int CHUNKS = (int) (CELL_BYTES / 16u);
+    constexpr int LPB = CHUNKS < 32 ? CHUNKS : 32;        // lanes per cell
+    constexpr int BPI = 32 / LPB;                         // cells per copy instruction
+    extern __shared__ __align__(128) unsigned char ndp_smem[];
+    const NdpGeom &g = A.g;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // shared layout: ticks | hypercube-mask slice (when small) | copy slots
+    double *s_ticks = reinterpret_cast<double *>(ndp_smem);
+    const unsigned ticks_bytes = ((unsigned) A.nticks * 8u + 127u) & ~127u;
+    uint32_t *s_hc = reinterpret_cast<uint32_t *>(ndp_smem + ticks_bytes);
+    const unsigned hc_bytes = A.hc_in_smem ? (((unsigned) A.H.nwords * 4u + 127u) & ~127u) : 0u;
+    unsigned char *s_slots = ndp_smem + ticks_bytes + hc_bytes;
+    for (int i = threadIdx.x; i < A.nticks; i += blockDim.x) s_ticks[i] = A.ticks[i];
+    if (A.hc_in_smem)
+        for (int i = threadIdx.x; i < A.H.nwords; i += blockDim.x) s_hc[i] = A.H.bits[i];
+    __syncthreads();
+    const uint32_t *hcbits = A.hc_in_smem ? s_hc : A.H.bits;
+
+    unsigned char *my_slot = s_slots + ((size_t) warp * 32 + lane) * SLOT;
+    const unsigned sub = lane % LPB, grp = lane / LPB;
+    const unsigned dst0 = ndpf_smem_u32(s_slots + ((size_t) warp * 32 + grp) * SLOT) + sub * 16u;
+    const unsigned char *src0 = reinterpret_cast<const unsigned char *>(A.cells) + sub * 16u;
+
+    const long long ntiles = (A.n + 31) / 32;
+    const long long tile_stride = (long long) gridDim.x * NDP_FUSED_WARPS;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    int n_searched = 0;
+
+    for (long long tile = (long long) blockIdx.x * NDP_FUSED_WARPS + warp; tile < ntiles; tile += tile_stride) {
+        const long long w = tile * 32 + lane;
+        NdpPlan<N> P;
+        P.kind = NDP_PLAN_IDLE; P.cell = 0; P.vflat = 0; P.pin = 0; P.sel = 0; P.dist = 0.0; P.searched = 0;
+        if (w < A.n) {
+            double qv[N];
+#pragma unroll
+            for (int a = 0; a < N; a++) qv[a] = A.q[w * N + a];
+            int idx[N], flg[N];
+            double nrm[N];
+            ndp_import_query<N>(g, s_ticks, qv, idx, flg, nrm);
+            ndp_fused_plan<N, METHOD, MODE>(g, A.H, hcbits, A.M, idx, flg, nrm, P);
+        }
+        // cooperative copy: a cell is fetched by LPB consecutive lanes, 16 bytes each, i.e. as ONE contiguous
+        // (8 << N)-byte request (measured on B200, tools/probe_gather.cu: 5.5x the rate of per-thread walks)
+        if (g.small) {
+            const int mine = P.kind == NDP_PLAN_GATHER ? (int) P.cell : -1;
+#pragma unroll
+            for (int k = 0; k < 32 / BPI; k++) {
+                const int oc = __shfl_sync(0xffffffffu, mine, k * BPI + (int) grp);
+                if (oc >= 0) {
+#pragma unroll
+                    for (int c = 0; c < CHUNKS / LPB; c++)
+                        ndpf_cp_async16(dst0 + (unsigned) (k * BPI) * SLOT + (unsigned) (c * LPB) * 16u,
+                                        src0 + (long long) oc * (long long) CELL_BYTES + (long long) (c * LPB) * 16);
+                }
+            }
+        } else {
+            const long long mine = P.kind == NDP_PLAN_GATHER ? P.cell : -1;
+#pragma unroll
+            for (int k = 0; k < 32 / BPI; k++) {
+                const long long oc = __shfl_sync(0xffffffffu, mine, k * BPI + (int) grp);
+                if (oc >= 0) {
+#pragma unroll
+                    for (int c = 0; c < CHUNKS / LPB; c++)
+                        ndpf_cp_async16(dst0 + (unsigned) (k * BPI) * SLOT + (unsigned) (c * LPB) * 16u,
+                                        src0 + oc * (long long) CELL_BYTES + (long long) (c * LPB) * 16);
+                }
+            }
+        }
+        ndpf_cp_async_commit();
+        double val = qnan;
+        if (METHOD == NDP_M_NEAREST && P.kind == NDP_PLAN_VALUE) val = A.grid[P.vflat];
+        ndpf_cp_async_wait0();
+        __syncwarp();                          // the other lanes' copies into my slot are visible
+        if (P.kind == NDP_PLAN_GATHER) {
+            const double2 *b2 = reinterpret_cast<const double2 *>(my_slot);
+            if (P.pin == 0) val = ndpf_reduce_plain<N>(b2, P.x);
+            else { bool unused; val = ndp_cell_reduce_halves<N>(b2, P.x, P.pin, P.sel, unused); }
+        }
+        if (P.kind != NDP_PLAN_IDLE && P.kind != NDP_PLAN_SLOW) { A.interps[w] = val; A.dists[w] = P.dist; }
+        __syncwarp();                          // the slots may be overwritten by the next tile's copies
+        if (METHOD != NDP_M_NONE) n_searched += P.searched;
+        const unsigned slow = __ballot_sync(0xffffffffu, P.kind == NDP_PLAN_SLOW);
+        if (slow) {                            // rare: warp-aggregated append to the slow list
+            int base = 0;
+            const int leader = __ffs(slow) - 1;
+            if ((int) lane == leader) base = atomicAdd(&A.ctr->n_slow, __popc(slow));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (P.kind == NDP_PLAN_SLOW) A.slowlist[base + __popc(slow & ((1u << lane) - 1u))] = (int) w;
+        }
+    }
+    if (METHOD != NDP_M_NONE) {
+        for (int off = 16; off; off >>= 1) n_searched += __shfl_xor_sync(0xffffffffu, n_searched, off);
+        if (lane == 0 && n_searched) atomicAdd(&A.ctr->n_off, n_searched);
+    }
+}
+#endif  // NDP_TU_FUSED
+
+// ---------------------------------------------------------------------------
+// k_slow: one thread per listed query, the whole reference pipeline with the exact
+// lattice search (import, hypercube with NaN test, search, publish, finish).
+// ---------------------------------------------------------------------------
+struct SlowArgs {
+    NdpGeom g;
+    const NdpPyramid *F; const NdpPyramid *R;
+    NdpTopo topo; int have_topo;
+    const double *ticks; int nticks; int ticks_in_smem;
+    const double *grid;
+    const double *q;
+    int method, search;
+    const int *list; const int *count;     // query ids to do, device count
+    double *interps; double *dists;
+    int *tielist;                          // out: query ids whose kd tie needs the topology (have_topo == 0)
+    int count_searched;                    // 1: add the searched queries to ctr->n_off (slow pass), 0: tie pass
+    NdpCounters *ctr;
+};
+
+#if defined(NDP_TU_SEARCH)
+template <int MODE>
+__global__ void __launch_bounds__(NDP_BLOCK, 2) k_slow(const __grid_constant__ SlowArgs A)
+{
+    extern __shared__ double s_ticks[];
+    const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
+    const NdpGeom &g = A.g;
+    const int n = g.naxes, V = g.vdim;
+    const int mode = ndp_mode_of(A.method, A.search);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const long long total = *A.count;
+    for (long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long) gridDim.x * blockDim.x) {
+        const long long i = A.list[s];
+        int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES];
+        double nrm[NDP_MAX_AXES];
+        ndp_import_query_seq<0>(g, tk, A.q + i * n, idx, flg, nrm);
+        unsigned pin, sel;
+        const bool oob = ndp_classify<0>(g, flg, nrm, pin, sel);
+        bool fdhc = !oob;
+        if (!oob) {
+            for (int k = 0; k < V; k++) {
+                bool bad = false;
+                const double val = ndp_eval_cell<0, false, false>(g, A.grid, nullptr, idx, nrm, pin, sel, k, bad);
+                if (k == 0 && bad) { fdhc = false; break; }
+                A.interps[i * V + k] = val;
+            }
+        }
+        if (fdhc) { A.dists[i] = 0.0; continue; }
+        if (A.method == NDP_M_NONE) {
+            for (int k = 0; k < V; k++) A.interps[i * V + k] = qnan;
+            A.dists[i] = 0.0;
+            continue;
+        }
+        if (A.count_searched) atomicAdd(&A.ctr->n_hard, 1);
+        NdpQuery Q;
+        ndp_make_query(g, idx, nrm, Q);
+        NdpHit hit;
+        hit.has_coords = 0;
+        if (!ndp_search_fast<0, MODE>(g, *A.F, mode, Q, hit))
+            ndp_search_descend<MODE>(g, *A.F, *A.R, mode, Q, A.have_topo ? &A.topo : nullptr, hit);
+        if (hit.status == NDP_SEARCH_TIE) {
+            A.tielist[atomicAdd(&A.ctr->n_tie, 1)] = (int) i;
+            continue;                                       // redone once the topology exists
+        }
+        if (A.have_topo && !A.count_searched) atomicAdd(&A.ctr->n_tie_resolved, 1);
+        ndp_scan_sentinel(*A.F, mode, hit);
+        int coords[NDP_MAX_AXES];
+        double dist;
+        if (hit.status == NDP_SEARCH_EMPTY) {               // empty kd-tree: see ndp_publish
+            hit.vertex = 0;
+            ndp_coords_of(g, Q, 0, coords);
+            dist = 1e10;
+        } else {
+            ndp_coords_of(g, Q, hit.vertex, coords);
+            dist = (mode >= NDP_MODE_LS_NEAREST) ? hit.dsel : ndp_reported_dist(g, A.method, Q, coords);
+        }
+        A.dists[i] = dist;
+        for (int k = 0; k < V; k++)
+            A.interps[i * V + k] = ndp_finish_component<0, false, false>(g, A.grid, nullptr, A.method, idx, nrm, coords, k);
+    }
+}
+#endif  // NDP_TU_SEARCH
+
+// ---------------------------------------------------------------------------
+// register time
+// ---------------------------------------------------------------------------
+#if defined(NDP_TU_TAPS)
+// pass 1: candidates per region (counts[region]; overflowing regions count 0 and keep the lattice search)
+__global__ void __launch_bounds__(128) k_nsm_count(const __grid_constant__ NdpSiteMap M, int *counts)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M.nregions) return;
+    unsigned long long cand[NSM_KMAX];
+    const int n = nsm_region_candidates(M, r, cand);
+    counts[r] = n < 0 ? 0 : n;
+}
+
+// pass 2: M.offs holds the exclusive scan of the counts; the candidates are recomputed and written
+__global__ void __launch_bounds__(128) k_nsm_fill(const __grid_constant__ NdpSiteMap M, uint32_t *ents)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M.nregions) return;
+    const int beg = M.offs[r], n = M.offs[r + 1] - beg;
+    if (n == 0) return;
+    unsigned long long cand[NSM_KMAX];
+    const int got = nsm_region_candidates(M, r, cand);
+    if (got == n) nsm_write_entries(M, cand, n, ents + (long long) beg * M.ew);
+}
+
+// *flag is cleared when component 0 of some basic vertex is NaN at one associated index but not at another
+// (then the hypercube-mask bit does not decide "fully defined" and the fused path is not used)
+__global__ void k_assoc_consistent(const double *__restrict__ grid, int nverts, long long per_vertex, int vdim, int *flag)
+{
+    const long long total = (long long) nverts * per_vertex;
+    for (long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long) gridDim.x * blockDim.x) {
+        const long long v = e / per_vertex;
+        const double first = grid[v * per_vertex * vdim], mine = grid[e * vdim];
+        if ((first != first) != (mine != mine)) *flag = 0;
+    }
+}
+#endif  // NDP_TU_TAPS

@@ -33,6 +33,7 @@ struct NdpCounters {      // one per in-flight batch, zeroed before k_main
     int n_tie;            // kd-mode ties met without topology
     int n_hard;           // queries that needed the pyramid descent
     int n_tie_resolved;   // ties settled through the kd topology
+    int n_slow;           // fused path: queries the plan could not settle (redone by k_slow)
 };
 
 // ---------------------------------------------------------------------------

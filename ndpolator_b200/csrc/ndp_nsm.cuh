@@ -125,8 +125,12 @@ NDP_HD int nsm_region_of(int S, int L, double q)
     double t = low ? -q : q - top;
     if (!(t < 64.0)) return -1;
     const int it = (int) t;
-    int band = 0;
-    for (int x = it; x; x >>= 1) band++;           // 0 -> 0, 1 -> 1, 2..3 -> 2, 4..7 -> 3, ...
+    // 0 -> 0, 1 -> 1, 2..3 -> 2, 4..7 -> 3, ...
+#if defined(__CUDA_ARCH__)
+    const int band = 32 - __clz(it);
+#else
+    const int band = it ? 32 - __builtin_clz((unsigned) it) : 0;
+#endif
     if (band >= NSM_BANDS) return -1;
     return low ? NSM_BANDS - 1 - band : NSM_BANDS + S * (L - 1) + band;
 }
@@ -256,6 +260,49 @@ NDP_HD void nsm_write_entries(const NdpSiteMap &M, const unsigned long long *can
         for (int w = 0; w < M.ew; w++) dst[i * M.ew + w] = (uint32_t) (cand[i] >> (32 * w));
 }
 
+// Compile-time-unrolled twins of ndp_make_query / ndp_add_assoc / ndp_reported_dist (ndp_core.cuh): every
+// array index is a constant, so the per-query state stays in registers inside the fused kernel.
+template <int N>
+NDP_HD void ndp_make_query_n(const NdpGeom &g, const int *idx, const double *nrm, NdpQuery &Q)
+{
+    if (N == 0) { ndp_make_query(g, idx, nrm, Q); return; }
+#pragma unroll
+    for (int a = 0; a < (N ? N : 1); a++) {
+        Q.qc[a] = (double) idx[a] + nrm[a] - 1.0;
+        Q.acoord[a] = (a >= g.nbasic) ? ndp_assoc_coord(Q.qc[a], g.len[a]) : 0;
+    }
+}
+
+template <int N, int MODE>
+NDP_HD double ndp_add_assoc_n(const NdpGeom &g, const NdpQuery &Q, double acc)
+{
+    if (N == 0) return ndp_add_assoc(g, MODE, Q, acc);
+    if (MODE >= NDP_MODE_LS_NEAREST) {
+#pragma unroll
+        for (int a = 0; a < (N ? N : 1); a++)
+            if (a >= g.nbasic) {
+                const double diff = Q.qc[a] - (double) Q.acoord[a];
+                acc += diff * diff;
+            }
+    }
+    return acc;
+}
+
+template <int N, int METHOD>
+NDP_HD double ndp_reported_dist_n(const NdpGeom &g, const NdpQuery &Q, const int *coords)
+{
+    if (N == 0) return ndp_reported_dist(g, METHOD, Q, coords);
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < (N ? N : 1); a++) {
+        if (METHOD == NDP_M_NEAREST || a >= g.nbasic) {
+            const double diff = Q.qc[a] - (double) coords[a];
+            acc += diff * diff;
+        } else acc += ndp_axis_term(NDP_MODE_LS_LINEAR, Q.qc[a], coords[a], coords[a]);
+    }
+    return acc;
+}
+
 // ---------------------------------------------------------------------------
 // Query time.  N: compile-time axis count (0 = run time); MODE: search mode.
 // Returns true when the map settles the query: hit.vertex / coords / dsel are then
@@ -322,7 +369,7 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
                     vid += c * g.bstride[a];
                 }
             }
-        d = ndp_add_assoc(g, mode, Q, d);
+        d = ndp_add_assoc_n<N, MODE>(g, Q, d);
         if (best < 0 || d < bestd) { best = vid; bestd = d; bestp = p; tie = false; }
         else if (d == bestd) {
             if (kd) tie = true;                                     // the reference's traversal order decides

@@ -56,3 +56,32 @@ cudaError_t ndp_launch_search_brute(const SearchArgs &A, int blocks, size_t smem
     k_search_brute<<<blocks, NDP_BLOCK, smem, st>>>(A);
     return cudaGetLastError();
 }
+
+cudaError_t ndp_launch_slow(const SlowArgs &A, int blocks, size_t smem, cudaStream_t st)
+{
+    switch (ndp_mode_of(A.method, A.search)) {
+    case NDP_MODE_KD_NEAREST: k_slow<NDP_MODE_KD_NEAREST><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case NDP_MODE_KD_LINEAR: k_slow<NDP_MODE_KD_LINEAR><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case NDP_MODE_LS_NEAREST: k_slow<NDP_MODE_LS_NEAREST><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    default: k_slow<NDP_MODE_LS_LINEAR><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t ndp_launch_nsm_count(const NdpSiteMap &M, int *counts, cudaStream_t st)
+{
+    k_nsm_count<<<(M.nregions + 127) / 128, 128, 0, st>>>(M, counts);
+    return cudaGetLastError();
+}
+
+cudaError_t ndp_launch_nsm_fill(const NdpSiteMap &M, uint32_t *ents, cudaStream_t st)
+{
+    k_nsm_fill<<<(M.nregions + 127) / 128, 128, 0, st>>>(M, ents);
+    return cudaGetLastError();
+}
+
+cudaError_t ndp_launch_assoc_consistent(const double *grid, int nverts, long long per_vertex, int vdim, int *flag, int blocks, cudaStream_t st)
+{
+    k_assoc_consistent<<<blocks, NDP_BLOCK, 0, st>>>(grid, nverts, per_vertex, vdim, flag);
+    return cudaGetLastError();
+}

@@ -89,6 +89,15 @@ def build_cases(seed=2):
     i0, i1 = np.meshgrid(np.arange(12), np.arange(6), indexing='ij')
     g[(i0 / 11 + (1 - i1 / 5)) > 1.2254] = np.nan
     cases.append(('c3_like_v16', ax, 3, g))
+    # scalar tables with associated axes: voids are whole basic vertices (the fused CUDA path applies) ...
+    ax = (np.linspace(0, 7, 8), np.linspace(0, 5, 6), np.linspace(0, 1, 5), np.linspace(-1, 1, 4))
+    g = rng.random((8, 6, 5, 4, 1)); g[rng.random((8, 6)) < 0.25] = np.nan
+    cases.append(('2basic_2assoc_v1', ax, 2, g))
+    # ... and a grid whose NaNs depend on the associated index too (ndp_types.c:179-184 looks at associated
+    # index 0 only, ndpolator.c:491 at the corners actually used): the mask bit does not decide "fully defined"
+    ax = (np.linspace(0, 6, 7), np.linspace(0, 4, 5), np.linspace(0, 1, 4))
+    g = rng.random((7, 5, 4, 1)); g[rng.random((7, 5)) < 0.2] = np.nan; g[rng.random((7, 5, 4)) < 0.05] = np.nan
+    cases.append(('assoc_dependent_nan_v1', ax, 2, g))
     return cases
 
 

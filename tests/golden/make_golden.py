@@ -22,10 +22,12 @@ from cases import adversarial_queries, build_cases  # noqa: E402
 from oracle.oracle import Oracle, have  # noqa: E402
 
 
-def main():
+def main(only=()):
     if not have('reference'):
         raise SystemExit('oracle/_ref/libndp_ref.so missing: run `make -C oracle` where /root/reference is mounted')
     for ci, (name, axes, nbasic, grid) in enumerate(build_cases()):
+        if only and name not in only:
+            continue
         rng = np.random.default_rng(1000 + ci)
         q = adversarial_queries(axes, 400, rng)
         R = Oracle('reference', axes, grid, nbasic)
@@ -55,4 +57,4 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    main(sys.argv[1:])      # optional: case names to (re)generate; default all

@@ -146,8 +146,8 @@ static void build_fused(HsTable *t)
         M.offs = offs.data(); M.ents = ents.data();
     }
     const NdpPyramid &R = t->red[1].dev;
-    t->hcs.nvar = R.nvar;
-    for (int j = 0; j < R.nvar; j++) { t->hcs.var_axis[j] = R.var_axis[j]; t->hcs.sstride[j] = R.stride[0][j]; }
+    t->hcs = NdpHcSlice{};
+    for (int j = 0; j < R.nvar; j++) t->hcs.astride[R.var_axis[j]] = R.stride[0][j];
     t->hcs.bits = R.bits[0];
     // mirrors k_assoc_consistent: component 0 of a basic vertex is NaN at every associated index or at none
     bool consistent = true;

@@ -107,3 +107,65 @@ def test_margin_shortcut_variant_is_bit_exact_too():
     res = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-x', '-q', '-p', 'no:cacheprovider'],
                          env=env, cwd=os.path.dirname(here), capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+
+
+def _far_queries(axes, n, rng):
+    """Points far outside the box: beyond the nearest-site map's outermost band (32 cells) and beyond
+    its total-distance guard (2^20), mixed with ordinary ones."""
+    lo = np.array([a[0] for a in axes]); hi = np.array([a[-1] for a in axes])
+    step = (hi - lo) / np.array([len(a) - 1 for a in axes])
+    q = lo + (hi - lo) * rng.random((n, len(axes)))
+    k = rng.integers(0, len(axes), n)
+    far = rng.choice([3.0, 17.0, 31.5, 33.0, 70.0, 2000.0, 1e7], n) * rng.choice([-1.0, 1.0], n)
+    q[np.arange(n), k] = np.where(far > 0, hi[k], lo[k]) + far * step[k]
+    return q
+
+
+@pytest.mark.parametrize('case', build_cases(seed=3), ids=lambda c: c[0])
+def test_fused_plan_matches_oracle(case):
+    """The fused path's per-query logic (ndp_fused.cuh: hypercube-mask slice + nearest-site map, one cell
+    gather; what it cannot settle goes through the generic path) against the oracle, bit for bit, all
+    methods and both search algorithms -- on the tables that qualify for it (scalar, 2..6 axes, mask bit
+    decides 'fully defined')."""
+    from hostsim.driver import HostSim
+    name, axes, nbasic, grid = case
+    rng = np.random.default_rng(31)
+    q = np.concatenate([adversarial_queries(axes, 1500, rng), _far_queries(axes, 600, rng)])
+    O, H = Oracle('port', axes, grid, nbasic), HostSim(axes, grid, nbasic)
+    qualifies = grid.shape[-1] == 1 and 2 <= len(axes) <= 6 and name != 'assoc_dependent_nan_v1'
+    for m in (0, 1, 2):
+        for s in (0, 1):
+            b = H.ndpolate_fused(q, m, s)
+            assert (b is not None) == qualifies, f'{name}: fused path eligibility'
+            if b is None:
+                continue
+            a = O.ndpolate(q, m, s)
+            assert_same_bits(a[0], b[0], f'interps {m}/{s}')
+            assert_same_bits(a[1], b[1], f'dists {m}/{s}')
+    if qualifies:
+        st = H.stats()
+        assert st['mapped'] > 0 and st['slow'] > 0      # both the map and the exact fall-back were exercised
+
+
+@pytest.mark.parametrize('spec', [('C4', 12, 'near'), ('C4', 12, 'deep'), ('C5', 6, 'near'), ('C2', 12, 'near'), ('C1', None, 'near')],
+                         ids=lambda s: f'{s[0]}@{s[1]}-{s[2]}')
+def test_fused_plan_on_baseline_mixes(spec):
+    """The same on scaled BASELINE.json configurations with their own query mixes: the map must settle
+    practically everything there (that is the point of it), still bit for bit."""
+    from hostsim.driver import HostSim
+    from ndpolator_b200 import synth
+    name, scale, mix = spec
+    n = 60000
+    w = synth.workload(name, scale, mix=mix, n_queries=n)
+    grid, q = w.grid(), w.queries(0, n)
+    nb = len(w.basic_axes)
+    O, H = Oracle('port', w.axes, grid, nb), HostSim(w.axes, grid, nb)
+    for m in (0, 1, 2):
+        for s in (0, 1):
+            qq = q if s == 0 else q[:1500]
+            a, b = O.ndpolate(qq, m, s, threads=4), H.ndpolate_fused(qq, m, s)
+            assert b is not None
+            assert_same_bits(a[0], b[0], f'interps {m}/{s}')
+            assert_same_bits(a[1], b[1], f'dists {m}/{s}')
+    st = H.stats()
+    assert st['slow'] < 1e-3 * st['mapped']

@@ -1,19 +1,18 @@
 """GPU twin of tests/test_device_logic_cpu.py::test_non_finite_queries: +-inf query coordinates
 bit-exact in every mode, NaN with extrapolation 'none' (src/ndpolator.c:27-39, :379-381, :551-554).
-Written after round 1's GPU minutes were spent, so it has not run on a B200 yet: enable it (drop
-the skip) together with its first GPU run."""
+Runs through the fused kernel where the table qualifies and through the two-pass path otherwise."""
 import numpy as np
 import pytest
 
 from cases import adversarial_queries, assert_same_bits, build_cases
 from oracle.oracle import Oracle
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skip(reason='not yet run on a GPU (round 1 budget spent); the host build of the same logic is tested on CPU')]
+pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize('fused_off', [0, 1], ids=['fused', 'two-pass'])
 @pytest.mark.parametrize('case', build_cases(seed=3), ids=lambda c: c[0])
-def test_non_finite_queries_gpu(case):
+def test_non_finite_queries_gpu(case, fused_off):
     from ndpolator_b200.cndpolator import Table
     name, axes, nbasic, grid = case
     q = adversarial_queries(axes, 5000, np.random.default_rng(5))
@@ -24,6 +23,7 @@ def test_non_finite_queries_gpu(case):
     qn[::3, 0] = np.nan
     qn[1::7, :] = np.nan
     O, T = Oracle('port', axes, grid, nbasic), Table(axes, grid, nbasic)
+    T.set_option('fused', fused_off)
     for a, b, what in zip(O.find(qi), T.find(qi), ('indices', 'flags', 'normed')):
         assert_same_bits(a, b, what + ' (inf)')
     for a, b, what in zip(O.find(qn), T.find(qn), ('indices', 'flags', 'normed')):

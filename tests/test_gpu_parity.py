@@ -11,6 +11,7 @@ import pytest
 
 from cases import adversarial_queries, assert_same_bits, build_cases
 from oracle.oracle import Oracle
+from fullsize import FULL, check_full, load_full
 from test_oracle_cpu import GOLDEN, check_engine_against_golden, load_golden
 
 pytestmark = pytest.mark.gpu
@@ -32,16 +33,95 @@ def test_extension_is_loaded_and_gpu_present():
 
 
 @pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[4:-4] for p in GOLDEN])
-@pytest.mark.parametrize('variant', [(1, 0), (2, 0), (2, 1)], ids=['strided', 'cellmajor-staged', 'cellmajor-direct'])
+@pytest.mark.parametrize('variant', [(1, 0, 0), (2, 0, 0), (2, 0, 1), (2, 1, 1)],
+                         ids=['strided', 'cellmajor-fused', 'cellmajor-staged', 'cellmajor-direct'])
 def test_cuda_matches_reference_golden(path, variant):
-    gather, staged_off = variant
+    gather, staged_off, fused_off = variant
     z, axes, nbasic = load_golden(path)
-    T = _table(axes, z['grid'], nbasic, gather=gather, staged=staged_off)
+    T = _table(axes, z['grid'], nbasic, gather=gather, staged=staged_off, fused=fused_off)
     check_engine_against_golden(
         z, T.find, lambda idx, flg, nrm: T.hypercubes_raw(nrm, idx, flg), T.ndpolate,
         lambda q, idx, flg, nrm, m, s: T.find_nearest(q, m, s), T.distance, T.masks)
     if gather == 2 and len(axes) <= 6 and z['grid'].shape[-1] * 8 < 128:
         assert T.stat('cellmajor') == 1
+    scalar = z['grid'].shape[-1] == 1 and 2 <= len(axes) <= 6
+    if gather == 2 and not fused_off and scalar:
+        # the last call was distance(); run one ndpolate to read which path served it
+        T.ndpolate(z['q'], 2, 0)
+        assert T.stat('fused') == (0 if 'assoc_dependent_nan' in path else 1)
+        assert T.stat('use_hc') == (0 if 'assoc_dependent_nan' in path else 1)
+    T.close()
+
+
+@pytest.mark.parametrize('path', FULL, ids=[os.path.basename(p)[5:-4] for p in FULL])
+def test_cuda_matches_reference_golden_fullsize(path):
+    """BASELINE.json's configurations AT FULL GRID SIZE (C4 40^5 with both query mixes, C5 16^6, C3
+    80x20x10x50 v16) against outputs of the reference itself on sub-ranges of the very batches bench.py
+    times (tests/golden/make_golden_fullsize.py; the reference needed ~20 min of kd-tree building for C4)."""
+    import torch
+    z, w, first, count = load_full(path)
+    dev = 'cuda'
+    from ndpolator_b200.cndpolator import Table
+    T = Table(w.axes, w.grid(dev), len(w.basic_axes))
+    q = w.queries(first, count, dev)
+
+    def ndp(m):
+        gi, gd = T.ndpolate(q, m, 0)
+        return gi.cpu().numpy(), gd.cpu().numpy()
+
+    def near(m):
+        c, d = T.find_nearest(q, m, 0)
+        return c.cpu().numpy(), d.cpu().numpy()
+
+    check_full(z, ndp, near)
+    if w.vdim == 1:
+        assert T.stat('fused') == 1 and T.stat('slow') < 100      # the benchmarked path is the one checked
+        T.set_option('fused', 1)                                   # and the staged / two-pass path as well
+        check_full(z, ndp, None, methods=(1, 2))
+    # host buffers through the chunked H2D / D2H pipeline give the same bits
+    T.set_option('fused', 0)
+    qh = q.cpu().numpy()
+    check_full(z, lambda m: T.ndpolate(qh, m, 0), None, methods=(2,))
+    T.close()
+
+
+def test_device_inputs_are_ordered_after_their_producer():
+    """A query tensor produced on torch's current stream immediately before the call (here behind a long
+    fill kernel) must be complete when the table's own stream reads it (ndpb_table_wait_stream)."""
+    import torch
+    from ndpolator_b200 import synth
+    w = synth.workload('C4', 12)
+    T = _table(w.axes, w.grid('cuda'), 5)
+    n = 1 << 20
+    q_ready = w.queries(0, n, 'cuda')
+    want = T.ndpolate(q_ready, 2, 0)
+    want = (want[0].clone(), want[1].clone())
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(side):
+            junk = torch.empty(1 << 28, dtype=torch.float64, device='cuda')
+            junk.fill_(1.0)                                   # ~2 GB of writes ahead of the producer on this stream
+            q = torch.full((n, 5), float('nan'), dtype=torch.float64, device='cuda')
+            q.copy_(q_ready)                                   # the producer: still queued when ndpolate is called
+            got = T.ndpolate(q, 2, 0)
+        assert torch.equal(got[0].view(torch.int64), want[0].view(torch.int64))
+        assert torch.equal(got[1].view(torch.int64), want[1].view(torch.int64))
+        del junk
+    T.close()
+
+
+def test_bad_device_arguments_raise():
+    import torch
+    name, axes, nbasic, grid = build_cases()[1]
+    T = _table(axes, grid, nbasic)
+    q = torch.zeros((8, 3), dtype=torch.float64, device='cuda')
+    with pytest.raises(ValueError):
+        T.ndpolate(q, 0, 0, out=(torch.zeros((8, 1), dtype=torch.float32, device='cuda'), torch.zeros((8, 1), dtype=torch.float64, device='cuda')))
+    with pytest.raises(ValueError):
+        T.ndpolate(q, 0, 0, out=(np.zeros((8, 1)), np.zeros((8, 1))))
+    with pytest.raises(ValueError):
+        T.ndpolate(q, 0, 0, out=(torch.zeros((7, 1), dtype=torch.float64, device='cuda'), torch.zeros((8, 1), dtype=torch.float64, device='cuda')))
     T.close()
 
 
@@ -127,18 +207,19 @@ def test_host_chunking_device_tensors_and_search_variants_agree():
     T.close()
 
 
+@pytest.mark.parametrize('fused_off', [0, 1], ids=['fused', 'two-pass'])
 @pytest.mark.parametrize('spec', [('C1', None, 200000), ('C2', 50, 200000), ('C3', 24, 60000),
-                                  ('C4', 12, 100000), ('C5', 6, 100000)], ids=lambda s: f'{s[0]}@{s[1]}')
-def test_baseline_configs_scaled_vs_oracle(spec):
+                                  ('C4', 12, 100000), ('C4deep', 12, 100000), ('C5', 6, 100000)], ids=lambda s: f'{s[0]}@{s[1]}')
+def test_baseline_configs_scaled_vs_oracle(spec, fused_off):
     """The BASELINE.json configurations (C1/C2 at full grid size, C3-C5 scaled so that the
     oracle's O(N*depth) tree build finishes in seconds), every extrapolation method."""
     from ndpolator_b200 import synth
     name, scale, n = spec
-    w = synth.workload(name, scale, n_queries=n)
+    w = synth.workload(name[:2], scale, mix='deep' if name.endswith('deep') else 'near', n_queries=n)
     grid, q = w.grid(), w.queries(0, n)
     nb = len(w.basic_axes)
     O = Oracle('port', w.axes, grid, nb)
-    T = _table(w.axes, grid, nb)
+    T = _table(w.axes, grid, nb, fused=fused_off)
     for m in (0, 1, 2):
         a, b = O.ndpolate(q, m, 0, threads=os.cpu_count() or 1), T.ndpolate(q, m, 0)
         assert_same_bits(a[0], b[0], f'{name} interps method {m}')

@@ -102,3 +102,32 @@ def test_threaded_oracle_equals_serial():
     b = O.ndpolate(q, 2, 0, threads=4)
     assert_same_bits(a[0], b[0])
     assert_same_bits(a[1], b[1])
+
+
+def test_port_matches_reference_golden_fullsize_c3():
+    """C3 at BASELINE.json's full size (80x20x10x50, vdim 16): the port against outputs of the reference
+    itself (the C4 / C5 full-size fixtures are checked on the GPU only: the port's insertion-built tree for
+    them takes minutes, like the reference's)."""
+    import fullsize
+    path = [p for p in fullsize.FULL if p.endswith('full_c3.npz')]
+    assert path, 'tests/golden/full_c3.npz missing'
+    z, w, first, count = fullsize.load_full(path[0])
+    q = w.queries(first, count)
+    O = Oracle('port', w.axes, w.grid(), len(w.basic_axes))
+    idx, flg, nrm = O.find(q)
+    fullsize.check_full(z, lambda m: O.ndpolate(q, m, 0, threads=os.cpu_count() or 1),
+                        lambda m: O.find_nearest(idx, flg, nrm, m, 0))
+
+
+@pytest.mark.skipif(not have('reference'), reason='oracle/_ref/libndp_ref.so not built (needs /root/reference)')
+@pytest.mark.parametrize('case', build_cases(seed=11), ids=lambda c: c[0])
+def test_port_tree_shape_is_the_references(case):
+    """parent / depth of the port's index-linked kd-tree against a walk over the reference's own
+    struct kdnode (oracle/ref_shim.c: ndpref_tree_topology)."""
+    name, axes, nbasic, grid = case
+    P, R = Oracle('port', axes, grid, nbasic), Oracle('reference', axes, grid, nbasic)
+    for m in (1, 2):
+        pp, dp = P.tree_topology(m)
+        pr, dr = R.tree_topology(m)
+        assert np.array_equal(pp, pr), f'kd parent, method {m}'
+        assert np.array_equal(dp, dr), f'kd depth, method {m}'
