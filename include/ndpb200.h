@@ -141,6 +141,29 @@ int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t value);
  * far, "variant_axes_*", "tree_levels_*".  Unknown keys return -1. */
 int64_t ndpb_table_stat(const ndpb_table *t, const char *key);
 
+/* ---- one call, several GPUs -------------------------------------------------------------------
+ * The reference's ndpolate is ONE call in one process (ndpolator/ndpolator.py:253-349).  A group
+ * holds one replicated table per listed device (grid, masks, cell-major copy and
+ * search structures replicated at create time, one host thread per device) and serves a HOST
+ * batch by contiguous query ranges [g N / G, (g + 1) N / G), one host thread + stream set per
+ * device; each device copies its results into its own slice of the caller's output arrays, which
+ * is the "final result gather" -- there is no collective on the path.  Results are identical to
+ * a single table's.  Device buffers are rejected (they belong to one GPU: use ndpb_group_table). */
+typedef struct ndpb_group ndpb_group;
+int ndpb_group_create(const double *const *axes, const int32_t *axlen, int naxes, int nbasic,
+                      const double *grid, int vdim, const int32_t *devices, int ndev, ndpb_group **out);
+int ndpb_group_destroy(ndpb_group *g);
+int ndpb_group_size(const ndpb_group *g);
+ndpb_table *ndpb_group_table(ndpb_group *g, int i);               /* borrowed; owned by the group */
+int ndpb_group_ndpolate(ndpb_group *g, const double *query_pts, int64_t n, int method, int search,
+                        double *interps, double *dists);
+int ndpb_group_distance(ndpb_group *g, const double *query_pts, int64_t n, double *dists);
+/* table options applied to every member; plus "min_queries_per_device" (default 65536: smaller batches
+ * use fewer devices) */
+int ndpb_group_set_option(ndpb_group *g, const char *key, int64_t value);
+/* sum of a table stat over the members; "used_devices" = devices the last call ran on */
+int64_t ndpb_group_stat(const ndpb_group *g, const char *key);
+
 const char *ndpb_last_error(void);
 const char *ndpb_version(void);
 

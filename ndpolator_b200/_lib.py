@@ -16,6 +16,8 @@ SYMBOLS = [
     'ndpb_table_create', 'ndpb_table_destroy', 'ndpb_find', 'ndpb_hypercubes', 'ndpb_find_nearest',
     'ndpb_ndpolate', 'ndpb_distance', 'ndpb_table_nverts', 'ndpb_table_masks', 'ndpb_table_tree_topology',
     'ndpb_table_set_option', 'ndpb_table_stat', 'ndpb_table_wait_stream', 'ndpb_last_error', 'ndpb_version',
+    'ndpb_group_create', 'ndpb_group_destroy', 'ndpb_group_size', 'ndpb_group_table', 'ndpb_group_ndpolate',
+    'ndpb_group_distance', 'ndpb_group_set_option', 'ndpb_group_stat',
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -66,6 +68,22 @@ def lib():
     L.ndpb_table_wait_stream.argtypes = [_vp, C.c_uint64]
     L.ndpb_table_stat.restype = C.c_int64
     L.ndpb_table_stat.argtypes = [_vp, C.c_char_p]
+    L.ndpb_group_create.restype = C.c_int
+    L.ndpb_group_create.argtypes = [C.POINTER(_vp), _ip, C.c_int, C.c_int, _vp, C.c_int, _ip, C.c_int, C.POINTER(_vp)]
+    L.ndpb_group_destroy.restype = C.c_int
+    L.ndpb_group_destroy.argtypes = [_vp]
+    L.ndpb_group_size.restype = C.c_int
+    L.ndpb_group_size.argtypes = [_vp]
+    L.ndpb_group_table.restype = _vp
+    L.ndpb_group_table.argtypes = [_vp, C.c_int]
+    L.ndpb_group_ndpolate.restype = C.c_int
+    L.ndpb_group_ndpolate.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp]
+    L.ndpb_group_distance.restype = C.c_int
+    L.ndpb_group_distance.argtypes = [_vp, _vp, C.c_int64, _vp]
+    L.ndpb_group_set_option.restype = C.c_int
+    L.ndpb_group_set_option.argtypes = [_vp, C.c_char_p, C.c_int64]
+    L.ndpb_group_stat.restype = C.c_int64
+    L.ndpb_group_stat.argtypes = [_vp, C.c_char_p]
     L.ndpb_last_error.restype = C.c_char_p
     L.ndpb_version.restype = C.c_char_p
     _lib = L

@@ -217,6 +217,84 @@ class Table:
         return dists
 
 
+class Group:
+    """One registered table replicated on several GPUs of this process (ndpb_group): a host batch is
+    cut into contiguous query ranges, one per device, and every device copies its results into its
+    slice of the output arrays -- no collective.  Same results as a single :class:`Table`.
+    Stands where the reference keeps its PyCapsule, like Table; host (numpy) buffers only."""
+
+    def __init__(self, axes, grid, nbasic=0, devices=(0,)):
+        L = _lib.lib()
+        self.devices = [int(d) for d in devices]
+        self.device = self.devices[0]
+        self.axes = tuple(_host_f64(a) for a in axes)
+        self.naxes = len(self.axes)
+        self.nbasic = int(nbasic) if nbasic else self.naxes
+        g = _host_f64(grid)
+        self.vdim = int(g.shape[-1])
+        want = int(np.prod([len(a) for a in self.axes])) * self.vdim
+        if want != g.size:
+            raise ValueError(f'grid has {g.size} elements, axes x vdim need {want}')
+        axlen = (C.c_int32 * self.naxes)(*[len(a) for a in self.axes])
+        axptr = (C.c_void_p * self.naxes)(*[a.ctypes.data for a in self.axes])
+        devs = (C.c_int32 * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        _lib.check(L.ndpb_group_create(axptr, axlen, self.naxes, self.nbasic, g.ctypes.data, self.vdim,
+                                       devs, len(self.devices), C.byref(h)))
+        self._h = h
+        self._finalizer = weakref.finalize(self, L.ndpb_group_destroy, h)
+
+    def close(self):
+        self._finalizer()
+
+    def set_option(self, key: str, value: int):
+        _lib.check(_lib.lib().ndpb_group_set_option(self._h, key.encode(), int(value)))
+
+    def stat(self, key: str) -> int:
+        return int(_lib.lib().ndpb_group_stat(self._h, key.encode()))
+
+    def _host_queries(self, query_pts):
+        if _is_cuda(query_pts):
+            raise ValueError('a multi-GPU table takes host (numpy) query arrays; a device tensor belongs to one GPU')
+        return _prep_queries(query_pts, self.naxes)
+
+    def ndpolate(self, query_pts, method=0, search=0, out=None):
+        q, qp, n, _ = self._host_queries(query_pts)
+        if out is None:
+            interps, dists = np.empty((n, self.vdim), np.float64), np.empty((n, 1), np.float64)
+        else:
+            interps, dists = out
+            for arr, what in ((interps, 'interps'), (dists, 'dists')):
+                if not isinstance(arr, np.ndarray) or arr.dtype != np.float64 or not arr.flags['C_CONTIGUOUS']:
+                    raise ValueError(f'out[{what}] must be a C-contiguous float64 numpy array')
+            if interps.size != n * self.vdim or dists.size != n:
+                raise ValueError('out arrays have the wrong size')
+        _lib.check(_lib.lib().ndpb_group_ndpolate(self._h, qp, n, int(method), int(search), _ptr(interps), _ptr(dists)))
+        return interps, dists
+
+    def distance(self, query_pts):
+        q, qp, n, _ = self._host_queries(query_pts)
+        dists = np.empty((n, 1), np.float64)
+        _lib.check(_lib.lib().ndpb_group_distance(self._h, qp, n, _ptr(dists)))
+        return dists
+
+    def member(self, i=0):
+        """Borrowed :class:`Table` view of member i (taps such as find / masks / find_nearest)."""
+        t = Table.__new__(Table)
+        t.device, t.axes, t.naxes, t.nbasic, t.vdim = self.devices[i], self.axes, self.naxes, self.nbasic, self.vdim
+        t._h = C.c_void_p(_lib.lib().ndpb_group_table(self._h, i))
+        t._grid = None
+        t._owner = self                       # keeps the group alive; the member is not destroyed separately
+        t._finalizer = lambda: None
+        return t
+
+    def find(self, query_pts):
+        return self.member(0).find(query_pts)
+
+    def hypercubes_raw(self, normed, indices, flags):
+        return self.member(0).hypercubes_raw(normed, indices, flags)
+
+
 # ---------------------------------------------------------------------------
 # module-level functions with the reference's signatures
 # ---------------------------------------------------------------------------
@@ -224,7 +302,7 @@ class Table:
 def ndpolate(capsule=None, query_pts=None, axes=None, grid=None, nbasic=0,
              extrapolation_method=0, search_algorithm=0):
     """-> (interps, dists) with a valid capsule, else (interps, dists, capsule)."""
-    if isinstance(capsule, Table):
+    if isinstance(capsule, (Table, Group)):
         interps, dists = capsule.ndpolate(query_pts, extrapolation_method, search_algorithm)
         return interps, dists
     if query_pts is not None and axes is not None and grid is not None:
@@ -246,7 +324,7 @@ def find(axes, query_pts, nbasic):
 
 def hypercubes(normed_query_pts, indices, axes, flags, grid, nbasic=0, capsule=None):
     """-> tuple of N arrays of shape (2,)*dim + (vdim,)."""
-    table = capsule if isinstance(capsule, Table) else Table(axes, grid, nbasic)
+    table = capsule if isinstance(capsule, (Table, Group)) else Table(axes, grid, nbasic)
     try:
         dim, fdhc, v = table.hypercubes_raw(normed_query_pts, indices, flags)
     finally:
@@ -258,7 +336,7 @@ def hypercubes(normed_query_pts, indices, axes, flags, grid, nbasic=0, capsule=N
 
 def distance(query_pts, capsule=None, axes=None, grid=None, nbasic=0):
     """-> (N, 1) squared index-space distances to the nearest fully defined hypercube."""
-    if isinstance(capsule, Table):
+    if isinstance(capsule, (Table, Group)):
         return capsule.distance(query_pts)
     if axes is None or grid is None:
         raise ValueError('Either capsule must be valid or axes and grid must be provided')   # src/ndp_py.c:212-216

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -390,14 +391,7 @@ extern "C" int ndpb_table_create(const double *const *axes, const int32_t *axlen
         if (is_device_ptr(axes[a])) CUT(cudaMemcpy(flat.data() + g.tickoff[a], axes[a], sizeof(double) * axlen[a], cudaMemcpyDeviceToHost));
         else memcpy(flat.data() + g.tickoff[a], axes[a], sizeof(double) * axlen[a]);
     }
-    for (int a = 0; a < naxes; a++) {
-        const double *tk = flat.data() + g.tickoff[a];
-        bool ascending = true;
-        for (int i = 1; i < axlen[a]; i++) if (!(tk[i] > tk[i - 1])) ascending = false;
-        const double span = tk[axlen[a] - 1] - tk[0];
-        g.inv_step[a] = (ascending && span > 0 && span < 1e300) ? (double) (axlen[a] - 1) / span : 0.0;
-        g.first[a] = tk[0]; g.last[a] = tk[axlen[a] - 1];
-    }
+    ndp_geom_axes(g, flat.data());
     g.small = (nall < (1LL << 31) - 64) ? 1 : 0;
     for (int a = 0; a < naxes; a++) { g.vstride32[a] = g.small ? (int) g.vstride[a] : 0; g.cstride32[a] = g.small ? (int) g.cstride[a] : 0; }
     for (int a = 0; a < nbasic; a++) g.inv_bstride[a] = 1.0 / (double) g.bstride[a];
@@ -1141,4 +1135,125 @@ extern "C" int ndpb_hypercubes(ndpb_table *t, const double *normed, const int32_
     CU(cudaStreamSynchronize(t->s_compute));
     if ((rc = dm.back()) || (rc = fd.back()) || (rc = vv.back())) return rc;
     return NDPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// ndpb_group: ONE call, several GPUs.  The reference's ndpolate is one call on one process
+// (ndpolator/ndpolator.py:253-349); the batch is embarrassingly parallel over queries, so a group
+// holds one replicated table per device and cuts a host batch into contiguous ranges, one host
+// thread + stream set per device.  Every device copies its results straight into its own slice of
+// the caller's output arrays -- that IS the final gather; there is no collective.
+// ---------------------------------------------------------------------------
+struct ndpb_group {
+    std::vector<ndpb_table *> tables;
+    std::mutex mu;
+    long long min_per_device = 1 << 16;     // below this a device is not worth waking up
+    long long st_used_devices = 0;
+};
+
+extern "C" int ndpb_group_destroy(ndpb_group *g)
+{
+    if (!g) return NDPB_OK;
+    for (auto t : g->tables) ndpb_table_destroy(t);
+    delete g;
+    return NDPB_OK;
+}
+
+extern "C" int ndpb_group_create(const double *const *axes, const int32_t *axlen, int naxes, int nbasic,
+                                 const double *grid, int vdim, const int32_t *devices, int ndev, ndpb_group **out)
+{
+    if (!out) return fail(NDPB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!devices || ndev < 1 || ndev > 64) return fail(NDPB_ERR_INVALID, "devices must list 1..64 device ordinals");
+    for (int i = 0; i < ndev; i++)
+        for (int j = 0; j < i; j++)
+            if (devices[i] == devices[j]) return fail(NDPB_ERR_INVALID, "a device is listed twice");
+    ndpb_group *g = new ndpb_group();
+    g->tables.assign(ndev, nullptr);
+    std::vector<int> rcs(ndev, NDPB_OK);
+    std::vector<std::string> errs(ndev);
+    // replicate the table: one host thread per device uploads the grid and builds masks, pyramids and the
+    // cell-major copy on its own GPU (per-device H2D)
+    std::vector<std::thread> th;
+    for (int i = 0; i < ndev; i++)
+        th.emplace_back([&, i] {
+            rcs[i] = ndpb_table_create(axes, axlen, naxes, nbasic, grid, vdim, devices[i], &g->tables[i]);
+            if (rcs[i]) errs[i] = ndpb_last_error();
+        });
+    for (auto &x : th) x.join();
+    for (int i = 0; i < ndev; i++)
+        if (rcs[i]) { const int rc = rcs[i]; const std::string msg = errs[i]; ndpb_group_destroy(g); return fail(rc, msg); }
+    *out = g;
+    return NDPB_OK;
+}
+
+extern "C" int ndpb_group_size(const ndpb_group *g) { return g ? (int) g->tables.size() : 0; }
+extern "C" ndpb_table *ndpb_group_table(ndpb_group *g, int i)
+{
+    return (g && i >= 0 && i < (int) g->tables.size()) ? g->tables[i] : nullptr;
+}
+
+extern "C" int ndpb_group_set_option(ndpb_group *g, const char *key, int64_t value)
+{
+    if (!g || !key) return fail(NDPB_ERR_INVALID, "NULL argument");
+    if (std::string(key) == "min_queries_per_device") {
+        if (value < 1) return fail(NDPB_ERR_INVALID, "min_queries_per_device must be >= 1");
+        g->min_per_device = value;
+        return NDPB_OK;
+    }
+    for (auto t : g->tables) { int rc = ndpb_table_set_option(t, key, value); if (rc) return rc; }
+    return NDPB_OK;
+}
+
+extern "C" int64_t ndpb_group_stat(const ndpb_group *g, const char *key)
+{
+    if (!g || !key) return -1;
+    if (std::string(key) == "used_devices") return g->st_used_devices;
+    int64_t sum = 0;
+    for (auto t : g->tables) { const int64_t v = ndpb_table_stat(t, key); if (v < 0) return v; sum += v; }
+    return sum;
+}
+
+// task: 0 ndpolate, 1 distance
+static int group_call(ndpb_group *g, int task, const double *q, int64_t n, int method, int search, double *interps, double *dists)
+{
+    if (!g) return fail(NDPB_ERR_INVALID, "group is NULL");
+    if (n < 0) return fail(NDPB_ERR_INVALID, "negative query count");
+    if (n > 0 && (!q || !dists || (task == 0 && !interps))) return fail(NDPB_ERR_INVALID, "NULL argument");
+    if (is_device_ptr(q) || is_device_ptr(interps) || is_device_ptr(dists))
+        return fail(NDPB_ERR_INVALID, "ndpb_group takes host buffers (a device buffer belongs to one GPU: use that GPU's table)");
+    std::lock_guard<std::mutex> lk(g->mu);
+    const int ndev = (int) g->tables.size();
+    int use = (int) std::min<long long>(ndev, std::max<long long>(1, n / g->min_per_device));
+    g->st_used_devices = use;
+    const int na = g->tables[0]->g.naxes, V = g->tables[0]->g.vdim;
+    std::vector<int> rcs(use, NDPB_OK);
+    std::vector<std::string> errs(use);
+    auto work = [&](int i) {
+        const long long lo = (n * i) / use, hi = (n * (i + 1)) / use;      // contiguous range [g N / G, (g + 1) N / G)
+        ndpb_table *t = g->tables[i];
+        if (task == 0) rcs[i] = ndpb_ndpolate(t, q + lo * na, hi - lo, method, search, interps + lo * V, dists + lo);
+        else rcs[i] = ndpb_distance(t, q + lo * na, hi - lo, dists + lo);
+        if (rcs[i]) errs[i] = ndpb_last_error();
+    };
+    if (use == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < use; i++) th.emplace_back(work, i);
+        for (auto &x : th) x.join();
+    }
+    for (int i = 0; i < use; i++)
+        if (rcs[i]) return fail(rcs[i], errs[i]);
+    return NDPB_OK;
+}
+
+extern "C" int ndpb_group_ndpolate(ndpb_group *g, const double *query_pts, int64_t n, int method, int search,
+                                   double *interps, double *dists)
+{
+    return group_call(g, 0, query_pts, n, method, search, interps, dists);
+}
+
+extern "C" int ndpb_group_distance(ndpb_group *g, const double *query_pts, int64_t n, double *dists)
+{
+    return group_call(g, 1, query_pts, n, NDPB_METHOD_LINEAR, NDPB_SEARCH_KDTREE, nullptr, dists);
 }

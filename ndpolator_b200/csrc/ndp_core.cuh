@@ -63,7 +63,37 @@ struct NdpGeom {
     int cstride32[NDP_MAX_AXES];
     int small;                        // every vertex and cell index fits in 31 bits
     double inv_bstride[NDP_MAX_AXES]; // 1.0 / bstride: first guess of the vertex-id decode (then fixed up exactly)
+    int easy;                         // every axis is evenly spaced by an exact power of two (see ndp_geom_axes)
+    double inv_pow2[NDP_MAX_AXES];    // 1 / spacing of such an axis (exact)
 };
+
+// Per-axis facts the import uses, from the concatenated tick array (host side, at table creation):
+//   inv_step / first / last  index guess of ndp_import_axis_guess (0 = always bisect);
+//   easy                     every axis has tick[i+1] - tick[i] == s_a for all i IN FLOATING POINT, with s_a an
+//                            exact power of two.  Then the quotient (x - t[l-1]) / (t[l] - t[l-1]) of :37 / :381
+//                            equals (x - t[l-1]) * (1 / s_a) bit for bit (scaling by a power of two is exact,
+//                            under- and overflow included), and the index guess needs no corrective step.
+inline void ndp_geom_axes(NdpGeom &g, const double *ticks)
+{
+    g.easy = 1;
+    for (int a = 0; a < g.naxes; a++) {
+        const double *tk = ticks + g.tickoff[a];
+        const int len = g.len[a];
+        bool ascending = true;
+        for (int i = 1; i < len; i++) if (!(tk[i] > tk[i - 1])) ascending = false;
+        const double span = tk[len - 1] - tk[0];
+        g.inv_step[a] = (ascending && span > 0 && span < 1e300) ? (double) (len - 1) / span : 0.0;
+        g.first[a] = tk[0]; g.last[a] = tk[len - 1];
+        const double s = tk[1] - tk[0];
+        int e = 0;
+        bool pow2 = ascending && s > 0 && s < 1e300 && frexp(s, &e) == 0.5 && e > -1000 && e < 1000;
+        for (int i = 1; i < len && pow2; i++) if (tk[i] - tk[i - 1] != s) pow2 = false;
+        g.inv_pow2[a] = pow2 ? 1.0 / s : 0.0;
+        if (!pow2) g.easy = 0;
+    }
+}
+
+
 
 // Bit-packed occupancy pyramid over the basic lattice.  Level 0 = one bit per
 // basic vertex (vmask or hcmask); level L = one bit per 2^L-wide block, set when
@@ -1141,6 +1171,34 @@ NDP_HD void ndp_import_query(const NdpGeom &g, const double *ticks, const double
     }
     constexpr int M = N ? N : 1;
     const double rtol = 1e-6;
+    if (g.easy) {
+        // evenly spaced axes with power-of-two spacing (ndp_geom_axes): guess, verify, scale -- no corrective
+        // step, no division; an unverified guess (a query within an ulp of a tick) takes the bisection
+        bool all_ok = true;
+#pragma unroll
+        for (int a = 0; a < M; a++) {
+            const double *tka = ticks + g.tickoff[a];
+            const int lena = g.len[a];
+            const double xa = qrow[a], xra = xa + rtol;
+            int c = (int) ((xra - g.first[a]) * g.inv_pow2[a]);
+            c = c < lena - 2 ? c : lena - 2;
+            const int la = c > 0 ? c + 1 : 1;
+            const double tla = tka[la], tpa = tka[la - 1];
+            const bool oka = (!(xra > tla) || la == lena - 1) && (la == 1 || xra > tpa);
+            const double ta = (xa - tpa) * g.inv_pow2[a];
+            int f = (xa < g.first[a] || xa > g.last[a]) ? NDP_F_OOB : 0;
+            if (fabs(ta) < rtol || (la == lena - 1 && fabs(ta - 1) < rtol)) f |= NDP_F_ON_VERTEX;
+            idx[a] = la; flg[a] = f; nrm[a] = ta;
+            all_ok &= oka;
+            if (!oka) idx[a] = -1;
+        }
+        if (!all_ok) {
+#pragma unroll
+            for (int a = 0; a < M; a++)
+                if (idx[a] < 0) ndp_import_axis(ticks + g.tickoff[a], g.len[a], qrow[a], idx[a], flg[a], nrm[a]);
+        }
+        return;
+    }
     double x[M], xr[M], tl[M], tp[M];
     int l[M], len[M];
     const double *tk[M];

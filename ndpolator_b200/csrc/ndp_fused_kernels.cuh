@@ -39,6 +39,11 @@ __device__ __forceinline__ void ndpf_cp_async16(unsigned dst, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// the copy is issued only when `flag` is non-negative (a lane without a cell passes -1)
+__device__ __forceinline__ void ndpf_cp_async16_if(unsigned dst, const void *src, int flag)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst), "l"(src), "r"(flag) : "memory");
+}
 __device__ __forceinline__ void ndpf_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void ndpf_cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -117,30 +122,27 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
             ndp_fused_plan<N, METHOD, MODE>(g, A.H, hcbits, A.M, idx, flg, nrm, P);
         }
         // cooperative copy: a cell is fetched by LPB consecutive lanes, 16 bytes each, i.e. as ONE contiguous
-        // (8 << N)-byte request (measured on B200, tools/probe_gather.cu: 5.5x the rate of per-thread walks)
+        // (8 << N)-byte request (measured on B200, tools/probe_gather.cu: 5.5x the rate of per-thread walks).
+        // The copy is predicated, not branched around: four instructions per sweep (shuffle, address, test, LDGSTS).
         if (g.small) {
             const int mine = P.kind == NDP_PLAN_GATHER ? (int) P.cell : -1;
 #pragma unroll
             for (int k = 0; k < 32 / BPI; k++) {
                 const int oc = __shfl_sync(0xffffffffu, mine, k * BPI + (int) grp);
-                if (oc >= 0) {
+                const unsigned char *src = src0 + (unsigned long long) (unsigned) oc * CELL_BYTES;
 #pragma unroll
-                    for (int c = 0; c < CHUNKS / LPB; c++)
-                        ndpf_cp_async16(dst0 + (unsigned) (k * BPI) * SLOT + (unsigned) (c * LPB) * 16u,
-                                        src0 + (long long) oc * (long long) CELL_BYTES + (long long) (c * LPB) * 16);
-                }
+                for (int c = 0; c < CHUNKS / LPB; c++)
+                    ndpf_cp_async16_if(dst0 + (unsigned) (k * BPI) * SLOT + (unsigned) (c * LPB) * 16u, src + (c * LPB) * 16, oc);
             }
         } else {
             const long long mine = P.kind == NDP_PLAN_GATHER ? P.cell : -1;
 #pragma unroll
             for (int k = 0; k < 32 / BPI; k++) {
                 const long long oc = __shfl_sync(0xffffffffu, mine, k * BPI + (int) grp);
-                if (oc >= 0) {
+                const unsigned char *src = src0 + (unsigned long long) oc * CELL_BYTES;
 #pragma unroll
-                    for (int c = 0; c < CHUNKS / LPB; c++)
-                        ndpf_cp_async16(dst0 + (unsigned) (k * BPI) * SLOT + (unsigned) (c * LPB) * 16u,
-                                        src0 + oc * (long long) CELL_BYTES + (long long) (c * LPB) * 16);
-                }
+                for (int c = 0; c < CHUNKS / LPB; c++)
+                    ndpf_cp_async16_if(dst0 + (unsigned) (k * BPI) * SLOT + (unsigned) (c * LPB) * 16u, src + (c * LPB) * 16, (int) (oc >> 32));
             }
         }
         ndpf_cp_async_commit();

@@ -260,6 +260,39 @@ NDP_HD void nsm_write_entries(const NdpSiteMap &M, const unsigned long long *can
         for (int w = 0; w < M.ew; w++) dst[i * M.ew + w] = (uint32_t) (cand[i] >> (32 * w));
 }
 
+// int in [0, 2^31) -> double, exactly.  On the device: a bit pattern + one DADD instead of I2F.F64
+// (which runs on the slow conversion pipe); both give the same value.
+NDP_HD double nsm_i2d(int c)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(0x43300000, c) - 4503599627370496.0;               // (2^52 + c) - 2^52
+#else
+    return (double) c;
+#endif
+}
+
+// position of site coordinate c on a point-metric axis: c (vertex) or c - 0.5 (cell centre); exact
+template <bool CENTRE>
+NDP_HD double nsm_pos(int c)
+{
+#if defined(__CUDA_ARCH__)
+    return CENTRE ? __hiloint2double(0x43200000, c << 1) - 2251799813685248.5  // (2^51 + c) - (2^51 + 0.5)
+                  : __hiloint2double(0x43300000, c) - 4503599627370496.0;
+#else
+    return CENTRE ? (double) c - 0.5 : (double) c;
+#endif
+}
+
+// ndp_axis_term(mode, q, c, c) for a non-NaN q, without its branches where the metric is a point metric:
+// all three of its cases are (pos - q)^2 there (pos - q is +0 when they are equal).
+template <int MODE>
+NDP_HD double nsm_term(double q, int c)
+{
+    if (MODE == NDP_MODE_LS_LINEAR) return ndp_axis_term(MODE, q, c, c);
+    const double d = nsm_pos<MODE == NDP_MODE_KD_LINEAR>(c) - q;
+    return d * d;
+}
+
 // Compile-time-unrolled twins of ndp_make_query / ndp_add_assoc / ndp_reported_dist (ndp_core.cuh): every
 // array index is a constant, so the per-query state stays in registers inside the fused kernel.
 template <int N>
@@ -268,7 +301,7 @@ NDP_HD void ndp_make_query_n(const NdpGeom &g, const int *idx, const double *nrm
     if (N == 0) { ndp_make_query(g, idx, nrm, Q); return; }
 #pragma unroll
     for (int a = 0; a < (N ? N : 1); a++) {
-        Q.qc[a] = (double) idx[a] + nrm[a] - 1.0;
+        Q.qc[a] = nsm_i2d(idx[a]) + nrm[a] - 1.0;             // idx >= 1 (:226, :250)
         Q.acoord[a] = (a >= g.nbasic) ? ndp_assoc_coord(Q.qc[a], g.len[a]) : 0;
     }
 }
@@ -281,13 +314,14 @@ NDP_HD double ndp_add_assoc_n(const NdpGeom &g, const NdpQuery &Q, double acc)
 #pragma unroll
         for (int a = 0; a < (N ? N : 1); a++)
             if (a >= g.nbasic) {
-                const double diff = Q.qc[a] - (double) Q.acoord[a];
+                const double diff = Q.qc[a] - nsm_i2d(Q.acoord[a]);
                 acc += diff * diff;
             }
     }
     return acc;
 }
 
+// coords[] are valid lattice coordinates (>= 0; >= 1 on the basic axes for LINEAR)
 template <int N, int METHOD>
 NDP_HD double ndp_reported_dist_n(const NdpGeom &g, const NdpQuery &Q, const int *coords)
 {
@@ -295,18 +329,23 @@ NDP_HD double ndp_reported_dist_n(const NdpGeom &g, const NdpQuery &Q, const int
     double acc = 0.0;
 #pragma unroll
     for (int a = 0; a < (N ? N : 1); a++) {
-        if (METHOD == NDP_M_NEAREST || a >= g.nbasic) {
-            const double diff = Q.qc[a] - (double) coords[a];
-            acc += diff * diff;
-        } else acc += ndp_axis_term(NDP_MODE_LS_LINEAR, Q.qc[a], coords[a], coords[a]);
+        const double q = Q.qc[a], hi = nsm_i2d(coords[a]);
+        double diff;
+        if (METHOD == NDP_M_NEAREST || a >= g.nbasic) diff = q - hi;            // :245-254, :179-183
+        else {                                                                  // ndp_distance, :158-176: cell [c-1, c]
+            const double lo = hi - 1.0;
+            diff = q < lo ? lo - q : (q > hi ? q - hi : 0.0);
+        }
+        acc += diff * diff;
     }
     return acc;
 }
 
 // ---------------------------------------------------------------------------
 // Query time.  N: compile-time axis count (0 = run time); MODE: search mode.
-// Returns true when the map settles the query: hit.vertex / coords / dsel are then
-// exactly what the reference's search returns.  false: take the lattice search.
+// Returns true when the map settles the query: hit.coords (basic axes) and hit.dsel are then exactly
+// what the reference's search returns (hit.vertex is filled for the full-scan modes only, whose tie rule
+// needs it).  false: take the lattice search.
 // ---------------------------------------------------------------------------
 template <int N, int MODE>
 NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery &Q, NdpHit &hit)
@@ -315,16 +354,20 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
     constexpr int mode = MODE;
     constexpr bool cells = (mode == NDP_MODE_KD_LINEAR || mode == NDP_MODE_LS_LINEAR);
     constexpr bool kd = mode < NDP_MODE_LS_NEAREST;
+    constexpr bool point = mode != NDP_MODE_LS_LINEAR;
     constexpr int lo = cells ? 1 : 0;
     const int nb = g.nbasic;
-    double t0[MM];                     // closed-form axes: the term of the chosen coordinate
+    double t0[MM];                     // closed-form axes: the term of the chosen coordinate (0 elsewhere)
     int fix[MM];
     int region = 0, base = 0;
     bool ok = true;
 #pragma unroll
-    for (int a = 0; a < MM; a++)
+    for (int a = 0; a < MM; a++) {
+        t0[a] = 0.0; fix[a] = 0;
         if (a < nb) {
-            const double q = Q.qc[a];
+            const bool nan = !(Q.qc[a] == Q.qc[a]);
+            const double q = nan ? 0.0 : Q.qc[a];
+            ok &= !nan;
             const int j = M.jof[a];
             if (j < 0) {
                 // the mask does not depend on this axis: the winner takes the coordinate that minimises the
@@ -332,52 +375,60 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
                 const double hi = (double) (g.len[a] - 1);
                 double p = cells ? floor(q) + 1.0 : rint(q);
                 p = p < (double) lo ? (double) lo : (p > hi ? hi : p);
-                if (!(q == q)) { ok = false; p = (double) lo; }
                 const int c = (int) p;
-                const double t = ndp_axis_term(mode, q, c, c);
-                const double tm = (c - 1 >= lo) ? ndp_axis_term(mode, q, c - 1, c - 1) : 4.0 * NSM_TMAX;
-                const double tp = (c + 1 <= g.len[a] - 1) ? ndp_axis_term(mode, q, c + 1, c + 1) : 4.0 * NSM_TMAX;
-                ok &= (tm - t > NSM_EPS) && (tp - t > NSM_EPS);
-                t0[a] = t; fix[a] = c;
-                base += c * g.bstride[a];
+                if (point) {
+                    // (pos - q)^2 with pos = p or p - 0.5; the neighbours at pos -+ 1 score 1 -+ 2 d0 more
+                    const double d0 = (cells ? p - 0.5 : p) - q;
+                    t0[a] = d0 * d0;
+                    ok &= (!(p > (double) lo) || 1.0 - 2.0 * d0 > 2.0 * NSM_EPS) && (!(p < hi) || 1.0 + 2.0 * d0 > 2.0 * NSM_EPS);
+                } else {
+                    const double t = ndp_axis_term(mode, q, c, c);
+                    const double tm = (c - 1 >= lo) ? ndp_axis_term(mode, q, c - 1, c - 1) : 4.0 * NSM_TMAX;
+                    const double tp = (c + 1 <= g.len[a] - 1) ? ndp_axis_term(mode, q, c + 1, c + 1) : 4.0 * NSM_TMAX;
+                    ok &= (tm - t > NSM_EPS) && (tp - t > NSM_EPS);
+                    t0[a] = t;
+                }
+                fix[a] = c;
+                if (!kd) base += c * g.bstride[a];
             } else {
                 const int r = nsm_region_of(M.S, g.len[a], q);
                 ok &= r >= 0;
                 region += (r < 0 ? 0 : r) * M.rstride[j];
-                t0[a] = 0.0; fix[a] = 0;
             }
         }
+    }
     if (!ok) return false;
     const int beg = M.offs[region], end = M.offs[region + 1];
-    int best = -1;
-    double bestd = 0.0;
+    int best = 0x7fffffff;
+    double bestd = 8.0 * NSM_TMAX;
     unsigned long long bestp = 0;
     bool tie = false;
     for (int e = beg; e < end; e++) {
         unsigned long long p = M.ents[(long long) e * M.ew];
         if (M.ew > 1) p |= (unsigned long long) M.ents[(long long) e * M.ew + 1] << 32;
+        // the reference's sum, in its axis order: closed-form axes contribute their fixed term (associated axes
+        // and axes beyond nbasic add +0.0, which changes nothing)
         double d = 0.0;
         int vid = base;
 #pragma unroll
-        for (int a = 0; a < MM; a++)
-            if (a < nb) {
-                const int j = M.jof[a];
-                if (j < 0) d += t0[a];
-                else {
-                    const int c = nsm_coord(p, j);
-                    d += ndp_axis_term(mode, Q.qc[a], c, c);
-                    vid += c * g.bstride[a];
-                }
+        for (int a = 0; a < MM; a++) {
+            const int j = M.jof[a];
+            if (j < 0) d += t0[a];
+            else {
+                const int c = nsm_coord(p, j);
+                d += nsm_term<MODE>(Q.qc[a], c);
+                if (!kd) vid += c * g.bstride[a];
             }
+        }
         d = ndp_add_assoc_n<N, MODE>(g, Q, d);
-        if (best < 0 || d < bestd) { best = vid; bestd = d; bestp = p; tie = false; }
+        if (d < bestd) { best = vid; bestd = d; bestp = p; tie = false; }
         else if (d == bestd) {
             if (kd) tie = true;                                     // the reference's traversal order decides
             else if (vid < best) { best = vid; bestp = p; }         // _compare_indexed_dists, :101-112
         }
     }
-    if (best < 0 || tie || !(bestd < NSM_TMAX)) return false;
-    hit.vertex = best; hit.dsel = bestd; hit.status = NDP_SEARCH_OK; hit.hard = 0; hit.has_coords = 1;
+    if (tie || !(bestd < NSM_TMAX)) return false;                   // also: no candidate stored for this region
+    hit.vertex = kd ? -1 : best; hit.dsel = bestd; hit.status = NDP_SEARCH_OK; hit.hard = 0; hit.has_coords = 1;
 #pragma unroll
     for (int a = 0; a < MM; a++)
         if (a < nb) { const int j = M.jof[a]; hit.coords[a] = j < 0 ? fix[a] : nsm_coord(bestp, j); }

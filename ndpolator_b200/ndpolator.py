@@ -21,7 +21,11 @@ class Ndpolator():
         * table : dict            name -> {'associated_axes', 'grid', 'capsule'}
     """
 
-    def __init__(self, basic_axes: tuple, device: int | None = None) -> None:
+    def __init__(self, basic_axes: tuple, device: int | None = None, devices=None) -> None:
+        """`device`: GPU ordinal of this process' tables (default: NDPB_DEVICE / LOCAL_RANK / 0).
+        `devices`: list of GPU ordinals -- every registered table is replicated on all of them and each
+        ndpolate() call on a host array is split across them by contiguous query ranges (one call, several
+        GPUs; see cndpolator.Group).  Both are extensions: the reference's constructor takes basic_axes only."""
         # reference ndpolator/ndpolator.py:35-44
         if not isinstance(basic_axes, tuple):
             raise TypeError('parameter `basic_axes` must be a tuple of ndarrays')
@@ -34,6 +38,7 @@ class Ndpolator():
         self.axes = basic_axes
         self.table = dict()
         self.device = device
+        self.devices = list(devices) if devices is not None else None
 
     def __repr__(self) -> str:
         return f'<Ndpolator N={len(self.axes)}, {len(self.table)} tables>'
@@ -75,7 +80,11 @@ class Ndpolator():
         reference caches its PyCapsule (ndpolator/ndpolator.py:317-339)."""
         entry = self.table[name]
         if entry['capsule'] is None:
-            entry['capsule'] = cndpolator.Table(self._all_axes(name), entry['grid'], len(self.axes), device=self.device)
+            if self.devices is not None and len(self.devices) > 1:
+                entry['capsule'] = cndpolator.Group(self._all_axes(name), entry['grid'], len(self.axes), devices=self.devices)
+            else:
+                device = self.devices[0] if self.devices else self.device
+                entry['capsule'] = cndpolator.Table(self._all_axes(name), entry['grid'], len(self.axes), device=device)
         return entry['capsule']
 
     def import_query_pts(self, name: str, query_pts: np.ndarray) -> tuple:

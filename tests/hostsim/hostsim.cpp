@@ -174,14 +174,7 @@ extern "C" void *hs_create(int naxes, int nbasic, const int *axlen, const double
     for (int a = nbasic - 1; a >= 0; a--) g.bstride[a] = (a == nbasic - 1) ? 1 : g.bstride[a + 1] * g.len[a + 1];
     g.nverts = (int) nverts; g.ncells = ncells;
     t->ticks.assign(ticks, ticks + nt);
-    for (int a = 0; a < naxes; a++) {       // mirrors ndpb_table_create
-        const double *tk = ticks + g.tickoff[a];
-        bool ascending = true;
-        for (int i = 1; i < axlen[a]; i++) if (!(tk[i] > tk[i - 1])) ascending = false;
-        const double span = tk[axlen[a] - 1] - tk[0];
-        g.inv_step[a] = (ascending && span > 0 && span < 1e300) ? (double) (axlen[a] - 1) / span : 0.0;
-        g.first[a] = tk[0]; g.last[a] = tk[axlen[a] - 1];
-    }
+    ndp_geom_axes(g, ticks);                // the same helper ndpb_table_create uses
     g.small = (nall < (1LL << 31) - 64) ? 1 : 0;
     for (int a = 0; a < naxes; a++) { g.vstride32[a] = g.small ? (int) g.vstride[a] : 0; g.cstride32[a] = g.small ? (int) g.cstride[a] : 0; }
     for (int a = 0; a < nbasic; a++) g.inv_bstride[a] = 1.0 / (double) g.bstride[a];
@@ -494,5 +487,26 @@ extern "C" void hs_nsm_info(void *h, long long *out)
         const NdpSiteMap &M = t->nsm[geo];
         out[4 * geo] = M.valid; out[4 * geo + 1] = M.S; out[4 * geo + 2] = M.nregions;
         out[4 * geo + 3] = M.valid ? t->nsm_offs[geo].back() : 0;
+    }
+}
+
+// analysis helper: candidates of the region a query falls into (geometry geo), -1 when not mapped
+extern "C" void hs_nsm_counts(void *h, long long n, const double *q, int geo, int32_t *out)
+{
+    HsTable *t = (HsTable *) h;
+    const NdpGeom &g = t->g;
+    const NdpSiteMap &M = t->nsm[geo];
+    for (long long i = 0; i < n; i++) {
+        int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES]; double nrm[NDP_MAX_AXES];
+        ndp_import_query<0>(g, t->ticks.data(), q + i * g.naxes, idx, flg, nrm);
+        NdpQuery Q; ndp_make_query(g, idx, nrm, Q);
+        int region = 0; bool ok = M.valid;
+        for (int a = 0; a < g.nbasic && ok; a++) {
+            const int j = M.jof[a];
+            if (j < 0) continue;
+            const int r = nsm_region_of(M.S, g.len[a], Q.qc[a]);
+            if (r < 0) ok = false; else region += r * M.rstride[j];
+        }
+        out[i] = ok ? M.offs[region + 1] - M.offs[region] : -1;
     }
 }

@@ -75,6 +75,7 @@ def test_cuda_matches_reference_golden_fullsize(path):
 
     check_full(z, ndp, near)
     if w.vdim == 1:
+        ndp(2)
         assert T.stat('fused') == 1 and T.stat('slow') < 100      # the benchmarked path is the one checked
         T.set_option('fused', 1)                                   # and the staged / two-pass path as well
         check_full(z, ndp, None, methods=(1, 2))
