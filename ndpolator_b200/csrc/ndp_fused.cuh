@@ -55,7 +55,7 @@ NDP_HD long long ndp_cell_of(const NdpGeom &g, const int *sup)
 
 // METHOD / MODE: compile-time extrapolation method and search mode (MODE is ignored for NONE).
 // `hcbits` is H.bits or a shared-memory copy of it.
-template <int N, int METHOD, int MODE>
+template <int N, int METHOD, int MODE, int VS = 0>
 NDP_HD void ndp_fused_plan(const NdpGeom &g, const NdpHcSlice &H, const uint32_t *hcbits, const NdpSiteMap &M,
                            const int *idx, const int *flg, const double *nrm, NdpPlan<N> &P)
 {
@@ -85,7 +85,7 @@ NDP_HD void ndp_fused_plan(const NdpGeom &g, const NdpHcSlice &H, const uint32_t
     NdpQuery Q;
     ndp_make_query_n<N>(g, idx, nrm, Q);
     NdpHit hit;
-    if (!ndp_nsm_search<N, MODE>(g, M, Q, hit)) { P.kind = NDP_PLAN_SLOW; return; }
+    if (!ndp_nsm_search<N, MODE, VS>(g, M, Q, hit)) { P.kind = NDP_PLAN_SLOW; return; }
     int coords[MM];
 #pragma unroll
     for (int a = 0; a < MM; a++) if (a < n) coords[a] = a < g.nbasic ? hit.coords[a] : Q.acoord[a];

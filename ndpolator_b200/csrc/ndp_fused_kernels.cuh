@@ -74,97 +74,258 @@ __device__ __forceinline__ double ndpf_reduce_plain(const double2 *b2, const dou
     return ndp_lerp(r0, r1, x[N - 1]);
 }
 
-template <int N, int METHOD, int MODE, int OCC>
+// src = base + cell * bytes as ONE instruction (IMAD.WIDE.U32 with a 64-bit addend)
+__device__ __forceinline__ const unsigned char *ndpf_cell_ptr(const unsigned char *base, unsigned cell, unsigned bytes)
+{
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(cell), "r"(bytes), "l"((unsigned long long) base));
+    return reinterpret_cast<const unsigned char *>(r);
+}
+
+// 16-byte copy of which only the first `bytes` (0, 8 or 16) are read from global memory, the rest zero-filled
+__device__ __forceinline__ void ndpf_cp_async16_part(unsigned dst, const void *src, unsigned bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ndpf_cp_async8(unsigned dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ndpf_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// shared memory per warp: 32 copy slots; PIPE: + 2 query tiles + 2 tiles of saved plans (x[N], dist, 4 ints per lane)
+__host__ __device__ constexpr unsigned ndpf_warp_bytes(int n, int pipe)
+{
+    return 32u * ((8u << n) + 16u) + (pipe ? 2u * 32u * 8u * (unsigned) n : 0u) +
+           (pipe == 1 ? 2u * 32u * (8u * ((unsigned) n + 1u) + 16u) : 0u);
+}
+
+// What a lane keeps of its plan between issuing a tile's copies and reducing it.
+template <int N>
+struct NdpFusedItem {
+    double x[N];
+    double dist;
+    unsigned pin, sel;
+    int kind, searched;
+};
+
+// PIPE 0: per warp and tile  import -> plan -> copy -> wait -> reduce  (latency hidden by the other warps only).
+// PIPE 1: software pipeline -- the queries of tile t+2 are prefetched into shared memory, and the import + plan
+//         of tile t+1 run while the cell copies of tile t are in flight; the plan of the tile in flight waits in
+//         shared memory, so the long plan section has the whole register file.
+// PIPE 2: the same pipeline with the waiting plan kept in registers (less shared memory, one more CTA per SM).
+// VS: see ndp_nsm_search.
+template <int N, int METHOD, int MODE, int OCC, int VS, int PIPE>
 __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __grid_constant__ FusedArgs A)
 {
     constexpr unsigned CELL_BYTES = 8u << N;
     constexpr unsigned SLOT = CELL_BYTES + 16u;           // +16: the 128-bit shared loads of a quarter warp hit distinct bank groups
     constexpr int CHUNKS = (int) (CELL_BYTES / 16u);
     constexpr int LPB = CHUNKS < 32 ? CHUNKS : 32;        // lanes per cell
-    constexpr int BPI = 32 / LPB;                         // cells per copy instruction
+    constexpr unsigned QROW = 8u * N;                     // bytes of one query row
+    constexpr unsigned QTILE = 32u * QROW;                // one tile of queries, laid out as in global memory
+    constexpr unsigned QCHUNKS = QTILE / 16u;
+    constexpr unsigned WARP_BYTES = ndpf_warp_bytes(N, PIPE);
     extern __shared__ __align__(128) unsigned char ndp_smem[];
     const NdpGeom &g = A.g;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // shared layout: ticks | hypercube-mask slice (when small) | copy slots
+    // shared layout: ticks | hypercube-mask slice (when small) | per warp: copy slots [| 2 query tiles | 2 plan tiles]
     double *s_ticks = reinterpret_cast<double *>(ndp_smem);
     const unsigned ticks_bytes = ((unsigned) A.nticks * 8u + 127u) & ~127u;
     uint32_t *s_hc = reinterpret_cast<uint32_t *>(ndp_smem + ticks_bytes);
     const unsigned hc_bytes = A.hc_in_smem ? (((unsigned) A.H.nwords * 4u + 127u) & ~127u) : 0u;
-    unsigned char *s_slots = ndp_smem + ticks_bytes + hc_bytes;
+    unsigned char *s_warp = ndp_smem + ticks_bytes + hc_bytes + (size_t) warp * WARP_BYTES;
     for (int i = threadIdx.x; i < A.nticks; i += blockDim.x) s_ticks[i] = A.ticks[i];
     if (A.hc_in_smem)
         for (int i = threadIdx.x; i < A.H.nwords; i += blockDim.x) s_hc[i] = A.H.bits[i];
     __syncthreads();
     const uint32_t *hcbits = A.hc_in_smem ? s_hc : A.H.bits;
 
-    unsigned char *my_slot = s_slots + ((size_t) warp * 32 + lane) * SLOT;
+    unsigned char *s_slots = s_warp;
+    unsigned char *s_q = s_warp + 32u * SLOT;                       // PIPE: [2][32][N] doubles
+    unsigned char *s_item = s_q + 2u * QTILE;                       // PIPE: [2][N + 1][32] doubles + [2][32] uint4
+    const unsigned char *my_slot = s_slots + (size_t) lane * SLOT;
+    // cooperative copy: a cell is fetched by LPB consecutive lanes, 16 bytes each, i.e. as ONE contiguous (8 << N)-
+    // byte request (measured on B200, tools/probe_gather.cu: 5.5x the rate of per-thread walks).  In sweep k the
+    // LPB lanes of group `grp` fetch the cell of lane grp * LPB + k: a width-LPB shuffle with a constant lane.
     const unsigned sub = lane % LPB, grp = lane / LPB;
-    const unsigned dst0 = ndpf_smem_u32(s_slots + ((size_t) warp * 32 + grp) * SLOT) + sub * 16u;
+    const unsigned dst0 = ndpf_smem_u32(s_slots + (size_t) (grp * LPB) * SLOT) + sub * 16u;
     const unsigned char *src0 = reinterpret_cast<const unsigned char *>(A.cells) + sub * 16u;
 
     const long long ntiles = (A.n + 31) / 32;
     const long long tile_stride = (long long) gridDim.x * NDP_FUSED_WARPS;
+    const long long tile0 = (long long) blockIdx.x * NDP_FUSED_WARPS + warp;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const bool q_aligned = (reinterpret_cast<unsigned long long>(A.q) & 15ull) == 0;
     int n_searched = 0;
 
-    for (long long tile = (long long) blockIdx.x * NDP_FUSED_WARPS + warp; tile < ntiles; tile += tile_stride) {
-        const long long w = tile * 32 + lane;
-        NdpPlan<N> P;
+    // import + plan of this lane's query of `tile`; qrow: its N coordinates (registers or shared memory)
+    auto make_plan = [&](long long tile, const double *qrow, NdpPlan<N> &P) {
         P.kind = NDP_PLAN_IDLE; P.cell = 0; P.vflat = 0; P.pin = 0; P.sel = 0; P.dist = 0.0; P.searched = 0;
-        if (w < A.n) {
-            double qv[N];
-#pragma unroll
-            for (int a = 0; a < N; a++) qv[a] = A.q[w * N + a];
+        if (tile * 32 + lane < A.n) {
             int idx[N], flg[N];
             double nrm[N];
-            ndp_import_query<N>(g, s_ticks, qv, idx, flg, nrm);
-            ndp_fused_plan<N, METHOD, MODE>(g, A.H, hcbits, A.M, idx, flg, nrm, P);
+            ndp_import_query<N>(g, s_ticks, qrow, idx, flg, nrm);
+            ndp_fused_plan<N, METHOD, MODE, VS>(g, A.H, hcbits, A.M, idx, flg, nrm, P);
         }
-        // cooperative copy: a cell is fetched by LPB consecutive lanes, 16 bytes each, i.e. as ONE contiguous
-        // (8 << N)-byte request (measured on B200, tools/probe_gather.cu: 5.5x the rate of per-thread walks).
-        // The copy is predicated, not branched around: four instructions per sweep (shuffle, address, test, LDGSTS).
+    };
+    // starts the copies of a tile's cells (no commit); a NEAREST-extrapolated lane fetches its vertex value instead
+    auto issue_cells = [&](const NdpPlan<N> &P) {
+        if (METHOD == NDP_M_NEAREST && P.kind == NDP_PLAN_VALUE) ndpf_cp_async8(ndpf_smem_u32(my_slot), A.grid + P.vflat);
         if (g.small) {
             const int mine = P.kind == NDP_PLAN_GATHER ? (int) P.cell : -1;
 #pragma unroll
-            for (int k = 0; k < 32 / BPI; k++) {
-                const int oc = __shfl_sync(0xffffffffu, mine, k * BPI + (int) grp);
-                const unsigned char *src = src0 + (unsigned long long) (unsigned) oc * CELL_BYTES;
+            for (int k = 0; k < LPB; k++) {
+                const int oc = __shfl_sync(0xffffffffu, mine, k, LPB);
+                const unsigned char *src = ndpf_cell_ptr(src0, (unsigned) oc, CELL_BYTES);
 #pragma unroll
                 for (int c = 0; c < CHUNKS / LPB; c++)
-                    ndpf_cp_async16_if(dst0 + (unsigned) (k * BPI) * SLOT + (unsigned) (c * LPB) * 16u, src + (c * LPB) * 16, oc);
+                    ndpf_cp_async16_if(dst0 + (unsigned) k * SLOT + (unsigned) (c * LPB) * 16u, src + (c * LPB) * 16, oc);
             }
         } else {
             const long long mine = P.kind == NDP_PLAN_GATHER ? P.cell : -1;
 #pragma unroll
-            for (int k = 0; k < 32 / BPI; k++) {
-                const long long oc = __shfl_sync(0xffffffffu, mine, k * BPI + (int) grp);
+            for (int k = 0; k < LPB; k++) {
+                const long long oc = __shfl_sync(0xffffffffu, mine, k, LPB);
                 const unsigned char *src = src0 + (unsigned long long) oc * CELL_BYTES;
 #pragma unroll
                 for (int c = 0; c < CHUNKS / LPB; c++)
-                    ndpf_cp_async16_if(dst0 + (unsigned) (k * BPI) * SLOT + (unsigned) (c * LPB) * 16u, src + (c * LPB) * 16, (int) (oc >> 32));
+                    ndpf_cp_async16_if(dst0 + (unsigned) k * SLOT + (unsigned) (c * LPB) * 16u, src + (c * LPB) * 16, (int) (oc >> 32));
             }
         }
-        ndpf_cp_async_commit();
+    };
+    // reduces / finishes this lane's query of `tile` once its cell has landed, writes the results
+    auto finish = [&](long long tile, const NdpFusedItem<N> &it) {
+        const long long w = tile * 32 + lane;
         double val = qnan;
-        if (METHOD == NDP_M_NEAREST && P.kind == NDP_PLAN_VALUE) val = A.grid[P.vflat];
-        ndpf_cp_async_wait0();
-        __syncwarp();                          // the other lanes' copies into my slot are visible
-        if (P.kind == NDP_PLAN_GATHER) {
+        if (METHOD == NDP_M_NEAREST && it.kind == NDP_PLAN_VALUE) val = *reinterpret_cast<const double *>(my_slot);
+        if (it.kind == NDP_PLAN_GATHER) {
             const double2 *b2 = reinterpret_cast<const double2 *>(my_slot);
-            if (P.pin == 0) val = ndpf_reduce_plain<N>(b2, P.x);
-            else { bool unused; val = ndp_cell_reduce_halves<N>(b2, P.x, P.pin, P.sel, unused); }
+            if (it.pin == 0) val = ndpf_reduce_plain<N>(b2, it.x);
+            else { bool unused; val = ndp_cell_reduce_halves<N>(b2, it.x, it.pin, it.sel, unused); }
         }
-        if (P.kind != NDP_PLAN_IDLE && P.kind != NDP_PLAN_SLOW) { A.interps[w] = val; A.dists[w] = P.dist; }
-        __syncwarp();                          // the slots may be overwritten by the next tile's copies
-        if (METHOD != NDP_M_NONE) n_searched += P.searched;
-        const unsigned slow = __ballot_sync(0xffffffffu, P.kind == NDP_PLAN_SLOW);
+        if (it.kind != NDP_PLAN_IDLE && it.kind != NDP_PLAN_SLOW) { A.interps[w] = val; A.dists[w] = it.dist; }
+        if (METHOD != NDP_M_NONE) n_searched += it.searched;
+        const unsigned slow = __ballot_sync(0xffffffffu, it.kind == NDP_PLAN_SLOW);
         if (slow) {                            // rare: warp-aggregated append to the slow list
             int base = 0;
             const int leader = __ffs(slow) - 1;
             if ((int) lane == leader) base = atomicAdd(&A.ctr->n_slow, __popc(slow));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (P.kind == NDP_PLAN_SLOW) A.slowlist[base + __popc(slow & ((1u << lane) - 1u))] = (int) w;
+            if (it.kind == NDP_PLAN_SLOW) A.slowlist[base + __popc(slow & ((1u << lane) - 1u))] = (int) w;
+        }
+    };
+    auto item_of = [&](const NdpPlan<N> &P, NdpFusedItem<N> &it) {
+#pragma unroll
+        for (int a = 0; a < N; a++) it.x[a] = P.x[a];
+        it.dist = P.dist; it.pin = P.pin; it.sel = P.sel; it.kind = P.kind; it.searched = P.searched;
+    };
+
+    if (!PIPE) {
+        for (long long tile = tile0; tile < ntiles; tile += tile_stride) {
+            const long long w = tile * 32 + lane;
+            double qv[N];
+            if (w < A.n) {
+#pragma unroll
+                for (int a = 0; a < N; a++) qv[a] = A.q[w * N + a];
+            }
+            NdpPlan<N> P;
+            make_plan(tile, qv, P);
+            issue_cells(P);
+            ndpf_cp_async_commit();
+            NdpFusedItem<N> it;
+            item_of(P, it);
+            ndpf_cp_async_wait0();
+            __syncwarp();                          // the other lanes' copies into my slot are visible
+            finish(tile, it);
+            __syncwarp();                          // the slots may be overwritten by the next tile's copies
+        }
+    } else {
+        // query prefetch: the tile's 32 rows are contiguous in global memory; 16-byte pieces, coalesced
+        auto prefetch_q = [&](long long tile, int buf) {
+            if (tile >= ntiles) return;
+            const unsigned dst = ndpf_smem_u32(s_q + (unsigned) buf * QTILE);
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(A.q) + tile * (long long) QTILE;
+            const long long left = (A.n - tile * 32) * (long long) QROW;            // bytes of this tile that exist
+            if (q_aligned) {
+#pragma unroll
+                for (unsigned c = 0; c < (QCHUNKS + 31u) / 32u; c++) {
+                    const unsigned piece = c * 32u + lane;
+                    const long long off = (long long) piece * 16;
+                    if (piece < QCHUNKS && off < left)
+                        ndpf_cp_async16_part(dst + piece * 16u, src + off, left - off >= 16 ? 16u : 8u);
+                }
+            } else {
+#pragma unroll
+                for (unsigned c = 0; c < N; c++) {
+                    const long long off = (long long) (c * 32u + lane) * 8;
+                    if (off < left) ndpf_cp_async8(dst + (c * 32u + lane) * 8u, src + off);
+                }
+            }
+        };
+        double *itemd = reinterpret_cast<double *>(s_item);                         // [2][N + 1][32]
+        uint4 *itemu = reinterpret_cast<uint4 *>(s_item + 2u * (N + 1) * 32u * 8u);  // [2][32]
+        auto save_item = [&](int buf, const NdpFusedItem<N> &it) {
+            double *d = itemd + (size_t) buf * (N + 1) * 32 + lane;
+#pragma unroll
+            for (int a = 0; a < N; a++) d[a * 32] = it.x[a];
+            d[N * 32] = it.dist;
+            itemu[buf * 32 + lane] = make_uint4(it.pin, it.sel, (unsigned) it.kind, (unsigned) it.searched);
+        };
+        auto load_item = [&](int buf, NdpFusedItem<N> &it) {
+            const double *d = itemd + (size_t) buf * (N + 1) * 32 + lane;
+#pragma unroll
+            for (int a = 0; a < N; a++) it.x[a] = d[a * 32];
+            it.dist = d[N * 32];
+            const uint4 u = itemu[buf * 32 + lane];
+            it.pin = u.x; it.sel = u.y; it.kind = (int) u.z; it.searched = (int) u.w;
+        };
+        if (tile0 < ntiles) {
+            // groups: {q(t0)} {q(t1)} {cells(t0), q(t2)} | per iteration {cells(t+1), q(t+3)}
+            prefetch_q(tile0, 0);
+            ndpf_cp_async_commit();
+            prefetch_q(tile0 + tile_stride, 1);
+            ndpf_cp_async_commit();
+            ndpf_cp_async_wait1();
+            __syncwarp();
+            NdpPlan<N> P;
+            make_plan(tile0, reinterpret_cast<const double *>(s_q) + lane * N, P);
+            __syncwarp();                          // every lane has read its row of query buffer 0
+            issue_cells(P);
+            prefetch_q(tile0 + 2 * tile_stride, 0);
+            ndpf_cp_async_commit();
+            NdpFusedItem<N> it_cur;
+            item_of(P, it_cur);
+            if (PIPE == 1) save_item(0, it_cur);
+            int cur = 0;
+            for (long long tile = tile0; tile < ntiles; tile += tile_stride) {
+                const long long next = tile + tile_stride;
+                NdpPlan<N> Pn;
+                Pn.kind = NDP_PLAN_IDLE; Pn.cell = 0; Pn.vflat = 0;
+                NdpFusedItem<N> itn;
+                itn.kind = NDP_PLAN_IDLE; itn.pin = 0; itn.sel = 0; itn.searched = 0; itn.dist = 0.0;
+                if (next < ntiles) {
+                    // q(next) sits in the group before the newest one; the cells of `tile` stay in flight meanwhile
+                    ndpf_cp_async_wait1();
+                    __syncwarp();
+                    make_plan(next, reinterpret_cast<const double *>(s_q + (unsigned) (cur ^ 1) * QTILE) + lane * N, Pn);
+                    item_of(Pn, itn);
+                    if (PIPE == 1) save_item(cur ^ 1, itn);
+                }
+                ndpf_cp_async_wait0();
+                __syncwarp();                      // the cells of `tile` have landed, for every lane
+                if (PIPE == 1) load_item(cur, it_cur);
+                finish(tile, it_cur);
+                if (PIPE == 2) it_cur = itn;
+                __syncwarp();                      // slots and query buffer cur^1 are free again
+                if (next < ntiles) {
+                    issue_cells(Pn);
+                    prefetch_q(next + 2 * tile_stride, cur ^ 1);
+                    ndpf_cp_async_commit();
+                }
+                cur ^= 1;
+            }
         }
     }
     if (METHOD != NDP_M_NONE) {

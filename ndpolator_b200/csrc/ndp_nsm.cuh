@@ -342,12 +342,14 @@ NDP_HD double ndp_reported_dist_n(const NdpGeom &g, const NdpQuery &Q, const int
 }
 
 // ---------------------------------------------------------------------------
-// Query time.  N: compile-time axis count (0 = run time); MODE: search mode.
+// Query time.  N: compile-time axis count (0 = run time); MODE: search mode; VS: 0 = the variant axes are
+// read from the map at run time, 1 = the caller guarantees they are exactly axes {0, 1} with one-word entries
+// (the usual shape of tables whose voids depend on their two leading axes: no per-axis tests in the loop).
 // Returns true when the map settles the query: hit.coords (basic axes) and hit.dsel are then exactly
 // what the reference's search returns (hit.vertex is filled for the full-scan modes only, whose tie rule
 // needs it).  false: take the lattice search.
 // ---------------------------------------------------------------------------
-template <int N, int MODE>
+template <int N, int MODE, int VS = 0>
 NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery &Q, NdpHit &hit)
 {
     constexpr int MM = N ? N : NDP_MAX_AXES;
@@ -368,7 +370,7 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
             const bool nan = !(Q.qc[a] == Q.qc[a]);
             const double q = nan ? 0.0 : Q.qc[a];
             ok &= !nan;
-            const int j = M.jof[a];
+            const int j = VS ? (a < 2 ? a : -1) : M.jof[a];
             if (j < 0) {
                 // the mask does not depend on this axis: the winner takes the coordinate that minimises the
                 // axis' own term, provided both neighbours lose by a margin no rounding can bridge
@@ -377,10 +379,12 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
                 p = p < (double) lo ? (double) lo : (p > hi ? hi : p);
                 const int c = (int) p;
                 if (point) {
-                    // (pos - q)^2 with pos = p or p - 0.5; the neighbours at pos -+ 1 score 1 -+ 2 d0 more
+                    // (pos - q)^2 with pos = p or p - 0.5.  The neighbours at pos -+ 1 score 1 -+ 2 d0 more: a
+                    // margin unless |d0| is within NSM_EPS of 1/2.  (|d0| > 1/2 only where p was clamped to the end
+                    // of the axis, and then the one neighbour that exists lies on the far side.)
                     const double d0 = (cells ? p - 0.5 : p) - q;
                     t0[a] = d0 * d0;
-                    ok &= (!(p > (double) lo) || 1.0 - 2.0 * d0 > 2.0 * NSM_EPS) && (!(p < hi) || 1.0 + 2.0 * d0 > 2.0 * NSM_EPS);
+                    ok &= fabs(fabs(d0) - 0.5) > NSM_EPS;
                 } else {
                     const double t = ndp_axis_term(mode, q, c, c);
                     const double tm = (c - 1 >= lo) ? ndp_axis_term(mode, q, c - 1, c - 1) : 4.0 * NSM_TMAX;
@@ -403,16 +407,18 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
     double bestd = 8.0 * NSM_TMAX;
     unsigned long long bestp = 0;
     bool tie = false;
+    const uint32_t *ep = M.ents + (long long) beg * (VS ? 1 : M.ew);
     for (int e = beg; e < end; e++) {
-        unsigned long long p = M.ents[(long long) e * M.ew];
-        if (M.ew > 1) p |= (unsigned long long) M.ents[(long long) e * M.ew + 1] << 32;
+        unsigned long long p = ep[0];
+        if (!VS && M.ew > 1) p |= (unsigned long long) ep[1] << 32;
+        ep += VS ? 1 : M.ew;
         // the reference's sum, in its axis order: closed-form axes contribute their fixed term (associated axes
         // and axes beyond nbasic add +0.0, which changes nothing)
         double d = 0.0;
         int vid = base;
 #pragma unroll
         for (int a = 0; a < MM; a++) {
-            const int j = M.jof[a];
+            const int j = VS ? (a < 2 ? a : -1) : M.jof[a];
             if (j < 0) d += t0[a];
             else {
                 const int c = nsm_coord(p, j);
@@ -431,6 +437,12 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
     hit.vertex = kd ? -1 : best; hit.dsel = bestd; hit.status = NDP_SEARCH_OK; hit.hard = 0; hit.has_coords = 1;
 #pragma unroll
     for (int a = 0; a < MM; a++)
-        if (a < nb) { const int j = M.jof[a]; hit.coords[a] = j < 0 ? fix[a] : nsm_coord(bestp, j); }
+        if (a < nb) { const int j = VS ? (a < 2 ? a : -1) : M.jof[a]; hit.coords[a] = j < 0 ? fix[a] : nsm_coord(bestp, j); }
     return true;
+}
+
+// true when a map qualifies for the VS = 1 specialisation of ndp_nsm_search
+inline bool nsm_leading_pair(const NdpSiteMap &M)
+{
+    return M.valid && M.nvar == 2 && M.var_axis[0] == 0 && M.var_axis[1] == 1 && M.ew == 1;
 }

@@ -6,24 +6,28 @@
 #ifndef NDP_FUSED_N
 #error "compile with -DNDP_FUSED_N=<axes>"
 #endif
-// resident CTAs per SM the kernel is compiled for (register budget 65536 / (128 * OCC); shared memory:
-// 4 warps x 32 slots x ((8 << N) + 16) bytes per CTA)
+// software pipeline inside a warp (plan of the next tile while this tile's cells are in flight): see k_fused
+#ifndef NDP_FUSED_PIPE
+#define NDP_FUSED_PIPE 1
+#endif
+// resident CTAs per SM the kernel is compiled for (register budget 65536 / (128 * OCC); shared memory per
+// CTA: 4 warps x ndpf_warp_bytes)
 #ifndef NDP_FUSED_OCC
 #if NDP_FUSED_N <= 4
 #define NDP_FUSED_OCC 6
 #elif NDP_FUSED_N == 5
-#define NDP_FUSED_OCC 5
+#define NDP_FUSED_OCC (NDP_FUSED_PIPE ? 3 : 5)
 #else
-#define NDP_FUSED_OCC 3
+#define NDP_FUSED_OCC (NDP_FUSED_PIPE ? 2 : 3)
 #endif
 #endif
 
-template <int METHOD, int MODE>
+template <int METHOD, int MODE, int VS>
 static cudaError_t go(const FusedArgs &A, int sm_count, size_t smem_fixed, cudaStream_t st)
 {
     constexpr int N = NDP_FUSED_N;
-    auto kern = k_fused<N, METHOD, MODE, NDP_FUSED_OCC>;
-    const size_t smem = smem_fixed + (size_t) NDP_FUSED_WARPS * 32 * (((size_t) 8 << N) + 16);
+    auto kern = k_fused<N, METHOD, MODE, NDP_FUSED_OCC, VS, NDP_FUSED_PIPE>;
+    const size_t smem = smem_fixed + (size_t) NDP_FUSED_WARPS * ndpf_warp_bytes(N, NDP_FUSED_PIPE);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
@@ -37,15 +41,23 @@ static cudaError_t go(const FusedArgs &A, int sm_count, size_t smem_fixed, cudaS
     return cudaGetLastError();
 }
 
+template <int VS>
+static cudaError_t by_mode(const FusedArgs &A, int method, int mode, int sm_count, size_t smem_fixed, cudaStream_t st)
+{
+    switch (mode) {
+    case NDP_MODE_KD_NEAREST: return go<NDP_M_NEAREST, NDP_MODE_KD_NEAREST, VS>(A, sm_count, smem_fixed, st);
+    case NDP_MODE_KD_LINEAR: return go<NDP_M_LINEAR, NDP_MODE_KD_LINEAR, VS>(A, sm_count, smem_fixed, st);
+    case NDP_MODE_LS_NEAREST: return go<NDP_M_NEAREST, NDP_MODE_LS_NEAREST, VS>(A, sm_count, smem_fixed, st);
+    default: return go<NDP_M_LINEAR, NDP_MODE_LS_LINEAR, VS>(A, sm_count, smem_fixed, st);
+    }
+}
+
 #define NDP_CAT2(a, b) a##b
 #define NDP_CAT(a, b) NDP_CAT2(a, b)
 cudaError_t NDP_CAT(ndp_launch_fused_, NDP_FUSED_N)(const FusedArgs &A, int method, int mode, int sm_count, size_t smem_fixed, cudaStream_t st)
 {
-    if (method == NDP_M_NONE) return go<NDP_M_NONE, 0>(A, sm_count, smem_fixed, st);
-    switch (mode) {
-    case NDP_MODE_KD_NEAREST: return go<NDP_M_NEAREST, NDP_MODE_KD_NEAREST>(A, sm_count, smem_fixed, st);
-    case NDP_MODE_KD_LINEAR: return go<NDP_M_LINEAR, NDP_MODE_KD_LINEAR>(A, sm_count, smem_fixed, st);
-    case NDP_MODE_LS_NEAREST: return go<NDP_M_NEAREST, NDP_MODE_LS_NEAREST>(A, sm_count, smem_fixed, st);
-    default: return go<NDP_M_LINEAR, NDP_MODE_LS_LINEAR>(A, sm_count, smem_fixed, st);
-    }
+    if (method == NDP_M_NONE) return go<NDP_M_NONE, 0, 0>(A, sm_count, smem_fixed, st);
+    // tables whose voids depend on exactly their two leading axes take the specialised candidate loop
+    return nsm_leading_pair(A.M) ? by_mode<1>(A, method, mode, sm_count, smem_fixed, st)
+                                 : by_mode<0>(A, method, mode, sm_count, smem_fixed, st);
 }
