@@ -7,10 +7,10 @@
 Workload (BASELINE.json metric / config): C4 = 5-D 40^5 sparse grid (30 % structured
 void, 819 MB fp64, exceeds L2), vdim 1, 'near' query mix (56 % in a fully defined
 hypercube, 44 % off-grid within ~3 cells), extrapolation_method='linear',
-search_algorithm='kdtree'.  A step = one ndpolate pass over one batch of `--batch`
-synthetic queries per GPU (device-resident, > L2, two alternating batches); N GPUs run
-N query shards against replicated tables with no collective on the data path
-(weak scaling).  One JSON line on stdout (rank 0)."""
+search_algorithm='kdtree'.  A step = one ndpolate pass over the configuration's 10^9
+synthetic queries (device-resident, 40 GB >> L2), query-sharded over the N GPUs of the
+run against replicated tables with no collective on the data path (strong scaling: the
+total is fixed, each GPU takes 10^9 / N).  One JSON line on stdout (rank 0)."""
 from __future__ import annotations
 
 import argparse
@@ -39,13 +39,16 @@ def parse():
     ap.add_argument('--mix', default='near', choices=['near', 'deep'])
     ap.add_argument('--method', default=None, choices=[None, 'none', 'nearest', 'linear'])
     ap.add_argument('--search', default='kdtree', choices=['kdtree', 'linear'])
-    ap.add_argument('--batch', type=int, default=1 << 27, help='queries per GPU per step')
-    ap.add_argument('--e2e-batch', type=int, default=1 << 24, help='queries per GPU per end-to-end (host buffer) step')
-    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--total', type=int, default=None,
+                    help='queries per step over ALL GPUs (default: the number BASELINE.json names for the workload, 10^9 for C4)')
+    ap.add_argument('--batch', type=int, default=None, help='queries per GPU per step (overrides --total: weak scaling)')
+    ap.add_argument('--e2e-batch', type=int, default=1 << 26, help='queries per GPU per end-to-end (host buffer) step')
+    ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--gather', type=int, default=0, help='0 auto, 1 strided, 2 cell-major')
     ap.add_argument('--staged', type=int, default=0, help='0 auto (cp.async ring), 1 off (same results)')
     ap.add_argument('--opt', action='append', default=[], help='table option key=value (tuning sweeps), repeatable')
-    ap.add_argument('--cpu-scale', type=int, default=20, help='ticks per axis of the grid the CPU reference is timed on')
+    ap.add_argument('--cpu-scale', type=int, default=None,
+                    help='ticks per axis of the grid the CPU reference is timed on (default: 24 for C4 -- BASELINE.md 4.5 -- else full size)')
     ap.add_argument('--cpu-queries', type=int, default=20000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -130,41 +133,95 @@ def measured_peak():
 # ---------------------------------------------------------------------------
 # the reference's CPU path (oracle/_ref when it was compiled here, else the oracle port)
 # ---------------------------------------------------------------------------
+def _pool_worker(args):
+    """Process-pool worker (fork): the parent's warm table is shared copy-on-write, as BASELINE.md 4.5 allows."""
+    lo, hi = args
+    O, q, method, search = _POOL_STATE
+    i, d = O.ndpolate(q[lo:hi], method, search)
+    return float(i[~(i != i)].sum())
+
+
+_POOL_STATE = None
+
+
+def cpu_scale_of(args):
+    if args.cpu_scale is not None:
+        return args.cpu_scale
+    return 24 if (args.workload == 'C4' and args.scale is None) else args.scale
+
+
 def cpu_reference_run(args, steps, warmup):
-    """Times the reference C implementation of this path on the host cores, on a bounded
-    sample: the same query mix on a `cpu_scale`^5 version of the grid (its insertion-built
-    kd-tree for the full 40^5 grid needs ~15 min and 6.6 GB per process),
-    tree warm (like the GPU table), all host threads sharing one table."""
+    """Times the reference C implementation of this path (oracle/_ref = the unmodified reference sources; the
+    oracle port only where they could not be compiled) on the host cores, on a bounded sample of the workload:
+    the same query mix, for C4 on a 24^5 version of the grid (the reference's insertion-built kd-tree for the
+    full 40^5 grid takes ~12 min and ~8 GB per process to build; BASELINE.md 4.5 names this substitution).
+    Reported: cold first call (masks + kd-tree build inside), warm single thread as shipped, all host threads
+    sharing one warm table, and a fork()ed process pool sharing it copy-on-write."""
+    global _POOL_STATE
+    import multiprocessing as mp
     import numpy as np
     from ndpolator_b200 import synth
     from oracle import oracle as orc
     kind = 'reference' if orc.have('reference') else 'port'
-    w = synth.workload(args.workload, args.cpu_scale, mix=args.mix, n_queries=args.cpu_queries)
+    scale = cpu_scale_of(args)
+    w = synth.workload(args.workload, scale, mix=args.mix, n_queries=args.cpu_queries)
     method = METHODS[args.method or w.method]
     search = SEARCHES[args.search]
-    O = orc.Oracle(kind, w.axes, w.grid(), len(w.basic_axes))
-    if method and search == 0:
-        O.warm(method)
     cores = os.cpu_count() or 1
     n = args.cpu_queries
     batches = [np.ascontiguousarray(w.queries(s * n, n)) for s in range(2)]
+    t0 = time.perf_counter()
+    O = orc.Oracle(kind, w.axes, w.grid(), len(w.basic_axes))
+    register_s = time.perf_counter() - t0
+    n_cold = max(1, n // 8)
+    t0 = time.perf_counter()
+    O.ndpolate(batches[1][:n_cold], method, search, threads=1)          # lazy kd-tree build happens here
+    cold_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.ndpolate(batches[0][: max(1, n // 4)], method, search, threads=1)
+    single = max(1, n // 4) / (time.perf_counter() - t0)
     for s in range(warmup):
         O.ndpolate(batches[s % 2], method, search, threads=cores)
     t0 = time.perf_counter()
     for s in range(steps):
         O.ndpolate(batches[s % 2], method, search, threads=cores)
     dt = time.perf_counter() - t0
-    t1 = time.perf_counter()
-    O.ndpolate(batches[0][: max(1, n // 4)], method, search, threads=1)
-    single = max(1, n // 4) / (time.perf_counter() - t1)
+    threads_value = steps * n / dt
+    pool_value = None
+    try:
+        _POOL_STATE = (O, batches[0], method, search)
+        cuts = np.linspace(0, n, cores + 1).astype(int)
+        with mp.get_context('fork').Pool(cores) as pool:
+            pool.map(_pool_worker, [(int(cuts[k]), int(cuts[k + 1])) for k in range(cores)])       # warm the workers
+            t0 = time.perf_counter()
+            reps = max(1, min(steps, 4))
+            for _ in range(reps):
+                pool.map(_pool_worker, [(int(cuts[k]), int(cuts[k + 1])) for k in range(cores)])
+            pool_value = reps * n / (time.perf_counter() - t0)
+    except Exception:
+        pool_value = None
+    finally:
+        _POOL_STATE = None
+    grid_txt = 'x'.join(str(len(a)) for a in w.axes)
+    full = synth.workload(args.workload, args.scale, mix=args.mix)
+    subst = ('' if len(full.axes[0]) == len(w.axes[0]) else
+             f' -- SUBSTITUTED for the {"x".join(str(len(a)) for a in full.axes)} grid, whose reference kd-tree takes ~12 min '
+             f'and ~8 GB per process to build (BASELINE.md 4.5)')
     return {
-        'value': steps * n / dt, 'unit': UNIT, 'cores': cores, 'kind': kind,
-        'single_thread_value': single,
-        'sample': (f'{w.name} ({args.cpu_scale}^5 grid, {w.mix} mix, method={args.method or w.method}, '
-                   f'search={args.search}), {n} queries/step x {steps} steps, kd-tree warm, {cores} host threads '
-                   f'sharing one table; full 40^5 grid not used on CPU: reference kd-tree build ~15 min/6.6 GB'),
-        'ms_per_step': dt / steps * 1e3,
+        'value': max(threads_value, pool_value or 0.0), 'unit': UNIT, 'cores': cores, 'kind': kind,
+        'single_thread_value': single, 'threads_value': threads_value, 'process_pool_value': pool_value,
+        'cold_first_call_s': cold_s, 'cold_first_call_queries': n_cold, 'register_s': register_s,
+        'grid': grid_txt,
+        'sample': (f'{w.name}: grid {grid_txt}{subst}; {w.mix} mix, method={args.method or w.method}, search={args.search}; '
+                   f'{n} queries/step x {steps} steps on {cores} host threads sharing one warm table (value = best of '
+                   f'threads / fork()ed process pool of {cores}); single thread as shipped and the cold first call '
+                   f'(masks + kd-tree build) reported beside it'),
+        'ms_per_step': n / max(threads_value, pool_value or 0.0) * 1e3,
     }
+
+
+CPU_KEYS = ('value', 'unit', 'cores', 'kind', 'sample', 'grid', 'single_thread_value', 'threads_value', 'process_pool_value',
+            'cold_first_call_s', 'cold_first_call_queries', 'register_s')
 
 
 def run_reference(args):
@@ -172,27 +229,46 @@ def run_reference(args):
     if rank != 0:
         return
     cb = cpu_reference_run(args, args.steps, args.warmup)
+    cfg = workload_config(args)
+    cfg['workload'] += f' [CPU arm timed on grid {cb["grid"]}: see cpu_baseline.sample]'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cb['ms_per_step'], 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(args),
-        'cpu_baseline': {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample', 'single_thread_value')},
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': cfg,
+        'cpu_baseline': {k: cb[k] for k in CPU_KEYS},
         'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
 
 
+def default_total(w):
+    return {'C1': 10**6, 'C2': 10**7, 'C3': 10**8, 'C4': 10**9, 'C5': 10**8}[w.name.split('@')[0]]
+
+
+def batch_of(args, w, ws):
+    """(queries per GPU per step, scaling): --batch fixes the per-GPU work (weak); otherwise the total is
+    fixed -- BASELINE.json's number for the configuration -- and sharded (strong)."""
+    if args.batch:
+        return args.batch, 'weak'
+    total = args.total or default_total(w)
+    return max(1, total // ws), 'strong'
+
+
 def workload_config(args):
     from ndpolator_b200 import synth
     w = synth.workload(args.workload, args.scale, mix=args.mix)
+    B, scaling = batch_of(args, w, max(1, args.gpus))
+    nbuf = 1 if B * w.naxes * 8 >= (1 << 30) else 2
     return {
         'workload': (f'{w.name}: {w.naxes}-D grid {"x".join(str(len(a)) for a in w.axes)}, vdim {w.vdim}, '
                      f'{w.mix} query mix, extrapolation_method={args.method or w.method}, search_algorithm={args.search}'),
-        'queries_per_gpu_per_step': args.batch,
+        'queries_per_step_all_gpus': B * max(1, args.gpus),
+        'queries_per_gpu_per_step': B,
         'bytes_per_query_algorithmic': w.bytes_per_query,
-        'l2': 'inputs larger than L2 (two alternating device-resident batches)',
+        'l2': (f'inputs larger than L2: one device-resident batch of {B * w.naxes * 8 / 1e9:.1f} GB per GPU re-read every step'
+               if nbuf == 1 else 'inputs larger than L2 where the batch allows: two alternating device-resident batches'),
         'parallelism': f'query shards x{args.gpus}, table replicated, no data-path collective',
     }
 
@@ -200,6 +276,38 @@ def workload_config(args):
 # ---------------------------------------------------------------------------
 # the CUDA path
 # ---------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """Runs this process (and first-touches its pinned host buffers) on the CPUs of the NUMA node the GPU hangs
+    off, so that eight ranks do not pull their H2D / D2H traffic through one socket.  Best effort."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), 'pci_bus_id') else None
+        if bdf is None:
+            out = subprocess.run(['nvidia-smi', '-i', str(local), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                                 capture_output=True, text=True).stdout.strip()
+            bdf = out[-12:] if len(out) >= 12 else None
+        if not bdf:
+            return ''
+        bdf = bdf.lower()
+        if len(bdf) == 16:                      # 00000000:17:00.0 -> 0000:17:00.0
+            bdf = bdf[4:]
+        node = int(open(f'/sys/bus/pci/devices/{bdf}/numa_node').read())
+        if node < 0:
+            return ''
+        cpus = []
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return ''
+        os.sched_setaffinity(0, cpus)
+        return f'process bound to NUMA node {node} of GPU {local}'
+    except Exception:
+        return ''
+
+
 def gen_queries(w, first, count, device, piece=1 << 23):
     import torch
     out = torch.empty((count, w.naxes), dtype=torch.float64, device=device)
@@ -227,8 +335,11 @@ def run_b200(args):
     w = synth.workload(args.workload, args.scale, mix=args.mix)
     method = METHODS[args.method or w.method]
     search = SEARCHES[args.search]
-    B, K, W = args.batch, args.steps, args.warmup
+    B, scaling = batch_of(args, w, ws)
+    K, W = args.steps, args.warmup
+    nbuf = 1 if B * w.naxes * 8 >= (1 << 30) else 2
 
+    bind_note = bind_to_gpu_numa_node(local)          # host buffers of the end-to-end leg land next to this GPU
     t_build = time.perf_counter()
     grid = w.grid(dev)
     T = Table(w.axes, grid, len(w.basic_axes), device=local)
@@ -244,7 +355,7 @@ def run_b200(args):
     build_s = time.perf_counter() - t_build
 
     # per-rank, per-buffer distinct rows of the global synthetic batch
-    qs = [gen_queries(w, (b * ws + rank) * B, B, dev) for b in range(2)]
+    qs = [gen_queries(w, (b * ws + rank) * B, B, dev) for b in range(nbuf)]
     interps = torch.empty((B, w.vdim), dtype=torch.float64, device=dev)
     dists = torch.empty((B, 1), dtype=torch.float64, device=dev)
     stream = torch.cuda.Stream(dev)                # kernels and timing events share this stream
@@ -256,19 +367,24 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    torch.cuda.synchronize()
+    t_cold = time.perf_counter()
+    T.ndpolate(qs[0][:min(B, 1 << 20)], method, search)      # cold first call: lazy nearest-site map / topology builds
+    torch.cuda.synchronize()
+    cold_s = time.perf_counter() - t_cold
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                        # before the warm-up, so that short runs are sampled too
     for s in range(W):
-        T.ndpolate(qs[s % 2], method, search, out=(interps, dists))
+        T.ndpolate(qs[s % nbuf], method, search, out=(interps, dists))
 
     keys = ('launches', 'offgrid', 'hard', 'ties', 'slow', 'fused', 'main_ns', 'search_ns', 'finish_ns')
     acc = dict.fromkeys(keys, 0)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for s in range(K):
-        T.ndpolate(qs[s % 2], method, search, out=(interps, dists))
+        T.ndpolate(qs[s % nbuf], method, search, out=(interps, dists))
         for k in keys:
             acc[k] += T.stat(k)
     e1.record(stream)
@@ -277,7 +393,17 @@ def run_b200(args):
     if ws > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
+    if rank == 0 and ms_total < 400.0:
+        # a short timed region: keep the GPU busy with the same work until the sampler has seen it under load
+        t_keep = time.perf_counter()
+        while time.perf_counter() - t_keep < 0.5:
+            T.ndpolate(qs[0], method, search, out=(interps, dists))
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks['note'] = ('sampled every 20 ms from before the warm-up to after the timed steps' +
+                          ('; the timed region was shorter than the sampling period, so the same step was repeated '
+                           'for 0.5 s after it to record the clocks under this load' if ms_total < 400.0 else ''))
     value = ws * B * K / (ms_total / 1e3)
     checksum = float(torch.nan_to_num(interps).sum().item())
 
@@ -292,14 +418,24 @@ def run_b200(args):
     T.ndpolate(qn, method, search, out=(inn, dn))
     barrier()
     t0 = time.perf_counter()
-    for s in range(args.e2e_steps):
-        T.ndpolate(qn, method, search, out=(inn, dn))
+    e2e_steps = 0
+    while e2e_steps < args.e2e_steps or (time.perf_counter() - t0 < 1.0 and e2e_steps < 50 * args.e2e_steps):
+        T.ndpolate(qn, method, search, out=(inn, dn))       # returns when the results are in the host arrays
+        e2e_steps += 1
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if ws > 1:                                               # every rank runs the same number of steps
+        steps_t = torch.tensor([e2e_steps], dtype=torch.int64, device=dev)
+        dist.all_reduce(steps_t, op=dist.ReduceOp.MIN)
+        e2e_steps_min = int(steps_t.item())
+    else:
+        e2e_steps_min = e2e_steps
     h2d, d2h = T.stat('h2d_bytes'), T.stat('d2h_bytes')
     if ws > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = ws * nb_e2e * args.e2e_steps / float(e2e_s.item())
+    # per-rank rate (its own steps over its own time), summed over ranks would double-count nothing but hide the
+    # slowest: report the conservative whole-job figure = ranks x per-rank queries x common steps / slowest time
+    e2e_value = ws * nb_e2e * e2e_steps_min / float(e2e_s.item())
     # the pipelined host path (chunks, two slots, three streams) against a device-resident run of the same rows
     ref_i, ref_d = T.ndpolate(qs[0][:nb_e2e], method, search)
     same = bool(torch.equal(ih.view(torch.int64), ref_i.cpu().view(torch.int64)) and
@@ -340,10 +476,11 @@ def run_b200(args):
         step_gbs = B * w.bytes_per_query / (ms_total / 1e3 / K) / 1e9
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': ws, 'steps': K, 'warmup': W,
-            'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'queries_per_gpu_per_step': nb_e2e, 'steps': args.e2e_steps, 'host_memory': 'pinned',
+                    'queries_per_gpu_per_step': nb_e2e, 'steps': e2e_steps_min, 'seconds': float(e2e_s.item()),
+                    'host_memory': 'pinned' + (f' ({bind_note})' if bind_note else ''),
                     'matches_device_run': same},
             'gpu_launches': acc['launches'],
             'clocks': clocks,
@@ -365,13 +502,15 @@ def run_b200(args):
                              'needed_lattice_descent': acc['hard'] / (B * K), 'kd_ties': acc['ties'],
                              'left_to_exact_generic_kernel': acc['slow'] / (B * K)},
             'path': 'fused (k_fused + k_slow)' if fused else 'three-pass (gather, search, finish)',
-            'table': {'cellmajor': bool(T.stat('cellmajor')), 'build_s': build_s},
+            'table': {'cellmajor': bool(T.stat('cellmajor')), 'build_s': build_s, 'cold_first_call_s': cold_s,
+                      'note': 'build_s: upload + masks + pyramids + cell-major copy; cold_first_call_s: first ndpolate of 2^20 '
+                              'queries incl. the lazy nearest-site map (the reference builds its kd-tree there)'},
             'checksum': checksum,
         }
         if ws == 1 and not args.no_cpu_baseline:
             try:
                 cb = cpu_reference_run(args, steps=2, warmup=1)
-                line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample', 'single_thread_value')}
+                line['cpu_baseline'] = {k: cb[k] for k in CPU_KEYS}
             except Exception as e:       # the baseline is reported beside the number, never instead of it
                 line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
                                         'sample': f'failed: {e!r}'}

@@ -26,7 +26,12 @@ def assert_same_bits(a, b, what=''):
     if not np.array_equal(bits(a), bits(b)):
         bad = np.argwhere(bits(a) != bits(b))
         i = tuple(bad[0])
-        raise AssertionError(f'{what}: {len(bad)} of {a.size} elements differ; first at {i}: {a[i]!r} vs {b[i]!r}')
+        extra = ''
+        if a.dtype == np.float64:
+            ours = a[tuple(bad.T)]
+            extra = (f'; of the differing elements {int(np.isnan(ours).sum())} are NaN on the left, '
+                     f'{int(np.isnan(b[tuple(bad.T)]).sum())} on the right; rows affected: {len(set(bad[:, 0].tolist()))}')
+        raise AssertionError(f'{what}: {len(bad)} of {a.size} elements differ; first at {i}: {a[i]!r} vs {b[i]!r}{extra}')
 
 
 def adversarial_queries(axes, n_rand, rng):

@@ -12,14 +12,16 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from cases import adversarial_queries, build_cases  # noqa: E402
 from ndpolator_b200.cndpolator import Table  # noqa: E402
 
+QUICK = os.environ.get('NDPB_SANITIZE_QUICK') == '1'      # one pass per case (memcheck is ~50x slower than native)
 for name, axes, nbasic, grid in build_cases():
-    if name not in ('holed3d', '2basic_1assoc_v2', '5d_corner_void', '7d_runtime_n', 'c3_like_v16'):
+    if name not in ('holed3d', '2basic_1assoc_v2', '5d_corner_void', '7d_runtime_n', 'c3_like_v16', '2basic_2assoc_v1'):
         continue
-    q = adversarial_queries(axes, 3000, np.random.default_rng(1))
-    for gather, staged in ((1, 0), (2, 0), (2, 1), (2, 2)):
+    q = adversarial_queries(axes, 600 if QUICK else 3000, np.random.default_rng(1))
+    for gather, staged, fused in (((2, 0, 0), (1, 0, 1)) if QUICK else ((1, 0, 0), (2, 0, 0), (2, 0, 1), (2, 1, 1), (2, 2, 1))):
         T = Table(axes, grid, nbasic)
         T.set_option('gather', gather)
         T.set_option('staged', staged)
+        T.set_option('fused', fused)
         T.set_option('chunk', 1024)
         for m in (0, 1, 2):
             for s in (0, 1):
