@@ -45,6 +45,29 @@ static int fail(int code, const std::string &msg)
 extern "C" const char *ndpb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *ndpb_version(void) { return "ndpb200 0.1.0 (sm_100a; parity target ndpolator 1.3.0)"; }
 
+// device temporaries that are released on every exit path
+struct DevTemps {
+    std::vector<void *> ptrs;
+    ~DevTemps() { for (void *p : ptrs) cudaFree(p); }
+    template <class T>
+    cudaError_t alloc(T **out, size_t count)
+    {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, sizeof(T) * (count ? count : 1));
+        if (e == cudaSuccess) ptrs.push_back(p);
+        *out = (T *) p;
+        return e;
+    }
+    void release(void *p)      // hand ownership to the caller
+    {
+        for (auto &q : ptrs) if (q == p) q = nullptr;
+    }
+    void free_now(void *p)
+    {
+        for (auto &q : ptrs) if (q == p) { cudaFree(p); q = nullptr; }
+    }
+};
+
 // ---------------------------------------------------------------------------
 // table
 // ---------------------------------------------------------------------------
@@ -199,13 +222,15 @@ static int build_reduced(ndpb_table *t, int m)
     const uint32_t *bits = t->pyr[m].dev.bits[0];
     const int ref = m;                          // vertex mask: coordinate 0; hypercube mask: coordinate 1
     int *d_diff = nullptr, diff[NDP_MAX_AXES] = {0};
-    CU(cudaMalloc(&d_diff, sizeof(diff)));
-    CU(cudaMemsetAsync(d_diff, 0, sizeof(diff), t->s_compute));
-    k_mask_variance<<<blocks_for(g.nverts), NDP_BLOCK, 0, t->s_compute>>>(g, bits, ref, d_diff);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(diff, d_diff, sizeof(diff), cudaMemcpyDeviceToHost, t->s_compute));
-    CU(cudaStreamSynchronize(t->s_compute));
-    CU(cudaFree(d_diff));
+    {
+        DevTemps hold;
+        CU(hold.alloc(&d_diff, (size_t) NDP_MAX_AXES));
+        CU(cudaMemsetAsync(d_diff, 0, sizeof(diff), t->s_compute));
+        k_mask_variance<<<blocks_for(g.nverts), NDP_BLOCK, 0, t->s_compute>>>(g, bits, ref, d_diff);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(diff, d_diff, sizeof(diff), cudaMemcpyDeviceToHost, t->s_compute));
+        CU(cudaStreamSynchronize(t->s_compute));
+    }
     SliceArgs A{};
     A.g = g; A.ref = ref; A.bits = bits; A.nvar = 0;
     long long nslice = 1;
@@ -216,8 +241,8 @@ static int build_reduced(ndpb_table *t, int m)
     CU(cudaMalloc(&level0, sizeof(uint32_t) * ((nslice + 31) / 32)));
     A.out = level0;
     k_mask_slice<<<blocks_for(((nslice + 31) / 32) * 32), NDP_BLOCK, 0, t->s_compute>>>(A);
-    CU(cudaGetLastError());
-    return build_pyramid(t, t->red[m], level0, A.nvar, A.var_axis, A.dim, false);
+    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) { cudaFree(level0); CU(e); }
+    return build_pyramid(t, t->red[m], level0, A.nvar, A.var_axis, A.dim, false);      // takes ownership of level0
 }
 
 static void free_slot(Slot &s)
@@ -549,46 +574,43 @@ struct BitSet {
     __host__ __device__ bool operator()(int v) const { return (bits[v >> 5] >> (v & 31)) & 1u; }
 };
 
-static int ensure_topology(ndpb_table *t, int m)
+static int build_topology(ndpb_table *t, int m, int *parent, int *depthv, int &levels)
 {
-    Topology &T = t->topo[m];
-    if (T.built) return NDPB_OK;
     const NdpGeom &g = t->g;
     cudaStream_t st = t->s_compute;
     const int nv = g.nverts;
-    CU(cudaMalloc(&T.parent, sizeof(int) * nv));
-    CU(cudaMalloc(&T.depth, sizeof(int) * nv));
-    k_fill_int<<<t->sm_count * 8, NDP_BLOCK, 0, st>>>(T.parent, nv, -2);
-    k_fill_int<<<t->sm_count * 8, NDP_BLOCK, 0, st>>>(T.depth, nv, -1);
+    k_fill_int<<<t->sm_count * 8, NDP_BLOCK, 0, st>>>(parent, nv, -2);
+    k_fill_int<<<t->sm_count * 8, NDP_BLOCK, 0, st>>>(depthv, nv, -1);
 
     // ascending ids of the masked vertices
+    DevTemps tmp_bufs;
     int *ids[2] = {nullptr, nullptr}, *ss[2] = {nullptr, nullptr}, *se[2] = {nullptr, nullptr};
     int *flag = nullptr, *scan = nullptr, *d_count = nullptr, *d_active = nullptr;
-    void *tmp = nullptr;
+    unsigned char *tmp = nullptr;
     size_t tmp_bytes = 0, need = 0;
-    CU(cudaMalloc(&ids[0], sizeof(int) * (size_t) nv));
-    CU(cudaMalloc(&d_count, sizeof(int)));
-    CU(cudaMalloc(&d_active, sizeof(int)));
+    CU(tmp_bufs.alloc(&ids[0], (size_t) nv));
+    CU(tmp_bufs.alloc(&d_count, 1));
+    CU(tmp_bufs.alloc(&d_active, 1));
     thrust::counting_iterator<int> counting(0);
     BitSet pred{t->pyr[m].dev.bits[0]};
     CU(cub::DeviceSelect::If(nullptr, need, counting, ids[0], d_count, nv, pred, st));
     tmp_bytes = need;
-    CU(cudaMalloc(&tmp, tmp_bytes));
+    CU(tmp_bufs.alloc(&tmp, tmp_bytes));
     CU(cub::DeviceSelect::If(tmp, tmp_bytes, counting, ids[0], d_count, nv, pred, st));
     int N = 0;
     CU(cudaMemcpyAsync(&N, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     t->pyr[m].count = N;
 
-    int levels = 0;
+    levels = 0;
     if (N > 0) {
-        CU(cudaMalloc(&ids[1], sizeof(int) * (size_t) N));
-        for (int b = 0; b < 2; b++) { CU(cudaMalloc(&ss[b], sizeof(int) * (size_t) N)); CU(cudaMalloc(&se[b], sizeof(int) * (size_t) N)); }
-        CU(cudaMalloc(&flag, sizeof(int) * ((size_t) N + 1)));
-        CU(cudaMalloc(&scan, sizeof(int) * ((size_t) N + 1)));
+        CU(tmp_bufs.alloc(&ids[1], (size_t) N));
+        for (int b = 0; b < 2; b++) { CU(tmp_bufs.alloc(&ss[b], (size_t) N)); CU(tmp_bufs.alloc(&se[b], (size_t) N)); }
+        CU(tmp_bufs.alloc(&flag, (size_t) N + 1));
+        CU(tmp_bufs.alloc(&scan, (size_t) N + 1));
         CU(cub::DeviceScan::ExclusiveSum(nullptr, need, flag, scan, N + 1, st));
-        if (need > tmp_bytes) { CU(cudaFree(tmp)); tmp_bytes = need; CU(cudaMalloc(&tmp, tmp_bytes)); }
-        k_topo_init<<<blocks_for(N), NDP_BLOCK, 0, st>>>(N, ss[0], se[0], ids[0], T.parent, T.depth);
+        if (need > tmp_bytes) { tmp_bufs.free_now(tmp); tmp_bytes = need; CU(tmp_bufs.alloc(&tmp, tmp_bytes)); }
+        k_topo_init<<<blocks_for(N), NDP_BLOCK, 0, st>>>(N, ss[0], se[0], ids[0], parent, depthv);
         int cur = 0;
         for (int depth = 0;; depth++) {
             TopoArgs A{};
@@ -596,7 +618,7 @@ static int ensure_topology(ndpb_table *t, int m)
             A.ids = ids[cur]; A.seg_start = ss[cur]; A.seg_end = se[cur];
             A.flag = flag; A.scan = scan;
             A.ids2 = ids[cur ^ 1]; A.seg_start2 = ss[cur ^ 1]; A.seg_end2 = se[cur ^ 1];
-            A.parent = T.parent; A.depthv = T.depth; A.active = d_active;
+            A.parent = parent; A.depthv = depthv; A.active = d_active;
             CU(cudaMemsetAsync(d_active, 0, sizeof(int), st));
             k_topo_flags<<<blocks_for(N + 1), NDP_BLOCK, 0, st>>>(A);
             CU(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, scan, N + 1, st));
@@ -610,10 +632,24 @@ static int ensure_topology(ndpb_table *t, int m)
             if (active == 0) break;
         }
     }
-    for (int b = 0; b < 2; b++) { cudaFree(ids[b]); cudaFree(ss[b]); cudaFree(se[b]); }
-    cudaFree(flag); cudaFree(scan); cudaFree(tmp); cudaFree(d_count); cudaFree(d_active);
-    T.levels = levels;
-    T.built = true;
+    CU(cudaStreamSynchronize(st));
+    return NDPB_OK;
+}
+
+static int ensure_topology(ndpb_table *t, int m)
+{
+    Topology &T = t->topo[m];
+    if (T.built) return NDPB_OK;
+    int *parent = nullptr, *depthv = nullptr, levels = 0;
+    {
+        DevTemps hold;                   // parent / depth are released to the table only when the build succeeded
+        CU(hold.alloc(&parent, (size_t) t->g.nverts));
+        CU(hold.alloc(&depthv, (size_t) t->g.nverts));
+        int rc = build_topology(t, m, parent, depthv, levels);
+        if (rc) return rc;
+        hold.release(parent); hold.release(depthv);
+    }
+    T.parent = parent; T.depth = depthv; T.levels = levels; T.built = true;
     return NDPB_OK;
 }
 
@@ -951,8 +987,27 @@ static void reset_stats(ndpb_table *t)
 // Drives one API call: device-resident callers run as one batch per 2^30 queries;
 // host callers are cut into chunks whose H2D copy, kernels and D2H copy overlap
 // across two slots and three streams.
+static int run_call_inner(ndpb_table *t, Task task, const double *q, long long n, int method, int search,
+                          double *interps, double *dists, int *coords);
+
+// On any error inside the chunk pipeline, copies of earlier chunks may still be in flight against the caller's
+// host buffers and the slots' staging buffers: drain all three streams and reset the slots before reporting.
 static int run_call(ndpb_table *t, Task task, const double *q, long long n, int method, int search,
                     double *interps, double *dists, int *coords)
+{
+    const int rc = run_call_inner(t, task, q, n, method, search, interps, dists, coords);
+    if (rc != NDPB_OK) {
+        const std::string keep = g_last_error;
+        cudaStreamSynchronize(t->s_in); cudaStreamSynchronize(t->s_compute); cudaStreamSynchronize(t->s_out);
+        cudaGetLastError();
+        for (auto &sl : t->slot) sl.used = false;
+        g_last_error = keep;
+    }
+    return rc;
+}
+
+static int run_call_inner(ndpb_table *t, Task task, const double *q, long long n, int method, int search,
+                          double *interps, double *dists, int *coords)
 {
     const NdpGeom &g = t->g;
     reset_stats(t);

@@ -8,15 +8,15 @@
 #endif
 // software pipeline inside a warp (plan of the next tile while this tile's cells are in flight): see k_fused
 #ifndef NDP_FUSED_PIPE
-#define NDP_FUSED_PIPE 1
+#define NDP_FUSED_PIPE 2      // profiles/r02c_variants.jsonl: 8.93 ms per 2^27 C4 queries against 9.43 (PIPE 0) and 9.82 (PIPE 1)
 #endif
 // resident CTAs per SM the kernel is compiled for (register budget 65536 / (128 * OCC); shared memory per
 // CTA: 4 warps x ndpf_warp_bytes)
 #ifndef NDP_FUSED_OCC
 #if NDP_FUSED_N <= 4
-#define NDP_FUSED_OCC 6
+#define NDP_FUSED_OCC (NDP_FUSED_PIPE ? 5 : 6)
 #elif NDP_FUSED_N == 5
-#define NDP_FUSED_OCC (NDP_FUSED_PIPE ? 3 : 5)
+#define NDP_FUSED_OCC (NDP_FUSED_PIPE == 1 ? 3 : (NDP_FUSED_PIPE == 2 ? 4 : 5))
 #else
 #define NDP_FUSED_OCC (NDP_FUSED_PIPE ? 2 : 3)
 #endif
