@@ -801,7 +801,8 @@ enum Task { TASK_NDPOLATE, TASK_NEAREST, TASK_DISTANCE };
 // "fully defined", and -- when extrapolating -- a search mode that has a nearest-site map.
 static bool fused_ok(ndpb_table *t, int method, int search)
 {
-    if (t->opt_fused == 1 || !t->cells || t->g.vdim != 1 || t->g.naxes < 2 || t->g.naxes > 6 || !t->use_hc) return false;
+    if (t->opt_fused == 1 || t->g.naxes < 2 || t->g.naxes > 6 || !t->use_hc) return false;
+    if (t->g.vdim == 1 && !t->cells) return false;      // scalar tables gather from the cell-major copy, vector tables from the grid
     if ((size_t) t->nticks * sizeof(double) > 16 * 1024) return false;
     if (method == NDPB_METHOD_NONE) return true;
     if (use_brute(t, search)) return false;
@@ -821,6 +822,12 @@ static int launch_fused(ndpb_table *t, Slot &s, const double *q, long long n, in
     A.H = t->hcs; A.hc_in_smem = t->hcs.nwords * sizeof(uint32_t) <= 8 * 1024;
     if (method != NDPB_METHOD_NONE) A.M = t->nsm[nsm_geo_of_mode(mode)];
     A.slowlist = s.list; A.ctr = s.ctr;
+    if (g.vdim > 1) {
+        // k_fused_vec: the plan's cell number is the vertex below the hypercube; 2^gs lanes share a query
+        for (int a = 0; a < g.naxes; a++) { A.g.cstride[a] = g.vstride[a]; A.g.cstride32[a] = g.vstride32[a]; }
+        int G = 1;
+        while (G < g.vdim && G < 32) { G <<= 1; A.gs++; }
+    }
     const size_t fixed = (((size_t) t->nticks * 8 + 127) & ~(size_t) 127) +
                          (A.hc_in_smem ? (((size_t) t->hcs.nwords * 4 + 127) & ~(size_t) 127) : 0);
     cudaError_t e;

@@ -31,6 +31,7 @@ struct FusedArgs {
     NdpSiteMap M;
     int *slowlist;
     NdpCounters *ctr;
+    int gs;                   // k_fused_vec: log2 of the lanes that share one query (each owns components k, k + G, ...)
 };
 
 #if defined(NDP_TU_FUSED)
@@ -326,6 +327,99 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
                 }
                 cur ^= 1;
             }
+        }
+    }
+    if (METHOD != NDP_M_NONE) {
+        for (int off = 16; off; off >>= 1) n_searched += __shfl_xor_sync(0xffffffffu, n_searched, off);
+        if (lane == 0 && n_searched) atomicAdd(&A.ctr->n_off, n_searched);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_fused_vec: the same plan for vector-valued tables (vdim > 1).  A corner vector is contiguous in the
+// ORIGINAL grid (C3: 16 passbands = one 128-byte line), so no cell-major copy is involved: the plan of a
+// query (one lane each) is broadcast to the G = 2^gs lanes that share it, lane k of the group gathers
+// component k, k + G, ... of the 2^N corners with coalesced G*8-byte loads and reduces them in registers.
+// In A.g the cell strides hold the VERTEX strides (the plan's "cell" is the vertex below the hypercube).
+// ---------------------------------------------------------------------------
+template <int N, int METHOD, int MODE, int VS>
+__global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, 4) k_fused_vec(const __grid_constant__ FusedArgs A)
+{
+    extern __shared__ __align__(128) unsigned char ndp_smem[];
+    const NdpGeom &g = A.g;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *s_ticks = reinterpret_cast<double *>(ndp_smem);
+    const unsigned ticks_bytes = ((unsigned) A.nticks * 8u + 127u) & ~127u;
+    uint32_t *s_hc = reinterpret_cast<uint32_t *>(ndp_smem + ticks_bytes);
+    for (int i = threadIdx.x; i < A.nticks; i += blockDim.x) s_ticks[i] = A.ticks[i];
+    if (A.hc_in_smem)
+        for (int i = threadIdx.x; i < A.H.nwords; i += blockDim.x) s_hc[i] = A.H.bits[i];
+    __syncthreads();
+    const uint32_t *hcbits = A.hc_in_smem ? s_hc : A.H.bits;
+
+    const int V = g.vdim, gs = A.gs, G = 1 << gs;
+    const int qi = (int) lane >> gs, kl = (int) lane & (G - 1);
+    const int per_sweep = 32 >> gs;
+    const long long ntiles = (A.n + 31) / 32;
+    const long long tile_stride = (long long) gridDim.x * NDP_FUSED_WARPS;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    int n_searched = 0;
+
+    for (long long tile = (long long) blockIdx.x * NDP_FUSED_WARPS + warp; tile < ntiles; tile += tile_stride) {
+        const long long w = tile * 32 + lane;
+        NdpPlan<N> P;
+        P.kind = NDP_PLAN_IDLE; P.cell = 0; P.vflat = 0; P.pin = 0; P.sel = 0; P.dist = 0.0; P.searched = 0;
+#pragma unroll
+        for (int a = 0; a < N; a++) P.x[a] = 0.0;
+        if (w < A.n) {
+            double qv[N];
+#pragma unroll
+            for (int a = 0; a < N; a++) qv[a] = A.q[w * N + a];
+            int idx[N], flg[N];
+            double nrm[N];
+            ndp_import_query<N>(g, s_ticks, qv, idx, flg, nrm);
+            ndp_fused_plan<N, METHOD, MODE, VS>(g, A.H, hcbits, A.M, idx, flg, nrm, P);
+        }
+        const long long mybase = P.kind == NDP_PLAN_VALUE ? P.vflat : P.cell;
+        const int meta = (P.kind << 16) | ((int) P.pin << 8) | (int) P.sel;
+        for (int s = 0; s < G; s++) {
+            const int src = s * per_sweep + qi;
+            const int m = __shfl_sync(0xffffffffu, meta, src);
+            const long long base = __shfl_sync(0xffffffffu, mybase, src);
+            double x[N];
+#pragma unroll
+            for (int a = 0; a < N; a++) x[a] = __shfl_sync(0xffffffffu, P.x[a], src);
+            const int kind = m >> 16;
+            const unsigned pin = (unsigned) (m >> 8) & 0xffu, sel = (unsigned) m & 0xffu;
+            if (kind == NDP_PLAN_IDLE || kind == NDP_PLAN_SLOW) continue;
+            double *out = A.interps + (tile * 32 + src) * (long long) V;
+            for (int k = kl; k < V; k += G) {
+                double val = qnan;
+                if (kind == NDP_PLAN_GATHER) {
+                    const double *b = A.grid + base * V + k;
+                    bool unused;
+                    val = ndp_cell_reduce<N>([&](double *fv) {
+#pragma unroll
+                        for (int j = 0; j < (1 << N); j++) {
+                            long long off = 0;
+#pragma unroll
+                            for (int a = 0; a < N; a++) if ((j >> (N - 1 - a)) & 1) off += g.cstride[a];
+                            fv[j] = b[off * V];
+                        }
+                    }, x, pin, sel, unused);
+                } else if (METHOD == NDP_M_NEAREST && kind == NDP_PLAN_VALUE) val = A.grid[base * V + k];
+                out[k] = val;
+            }
+        }
+        if (P.kind != NDP_PLAN_IDLE && P.kind != NDP_PLAN_SLOW) A.dists[w] = P.dist;
+        if (METHOD != NDP_M_NONE) n_searched += P.searched;
+        const unsigned slow = __ballot_sync(0xffffffffu, P.kind == NDP_PLAN_SLOW);
+        if (slow) {
+            int base = 0;
+            const int leader = __ffs(slow) - 1;
+            if ((int) lane == leader) base = atomicAdd(&A.ctr->n_slow, __popc(slow));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (P.kind == NDP_PLAN_SLOW) A.slowlist[base + __popc(slow & ((1u << lane) - 1u))] = (int) w;
         }
     }
     if (METHOD != NDP_M_NONE) {

@@ -41,6 +41,33 @@ static cudaError_t go(const FusedArgs &A, int sm_count, size_t smem_fixed, cudaS
     return cudaGetLastError();
 }
 
+template <int METHOD, int MODE, int VS>
+static cudaError_t go_vec(const FusedArgs &A, int sm_count, size_t smem_fixed, cudaStream_t st)
+{
+    constexpr int N = NDP_FUSED_N;
+    auto kern = k_fused_vec<N, METHOD, MODE, VS>;
+    int per_sm = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NDP_FUSED_WARPS * 32, smem_fixed);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const long long tiles = (A.n + 31) / 32;
+    const long long want = (tiles + NDP_FUSED_WARPS - 1) / NDP_FUSED_WARPS;
+    const int blocks = (int) std::max<long long>(1, std::min<long long>(want, (long long) sm_count * per_sm));
+    kern<<<blocks, NDP_FUSED_WARPS * 32, smem_fixed, st>>>(A);
+    return cudaGetLastError();
+}
+
+template <int VS>
+static cudaError_t by_mode_vec(const FusedArgs &A, int method, int mode, int sm_count, size_t smem_fixed, cudaStream_t st)
+{
+    switch (mode) {
+    case NDP_MODE_KD_NEAREST: return go_vec<NDP_M_NEAREST, NDP_MODE_KD_NEAREST, VS>(A, sm_count, smem_fixed, st);
+    case NDP_MODE_KD_LINEAR: return go_vec<NDP_M_LINEAR, NDP_MODE_KD_LINEAR, VS>(A, sm_count, smem_fixed, st);
+    case NDP_MODE_LS_NEAREST: return go_vec<NDP_M_NEAREST, NDP_MODE_LS_NEAREST, VS>(A, sm_count, smem_fixed, st);
+    default: return go_vec<NDP_M_LINEAR, NDP_MODE_LS_LINEAR, VS>(A, sm_count, smem_fixed, st);
+    }
+}
+
 template <int VS>
 static cudaError_t by_mode(const FusedArgs &A, int method, int mode, int sm_count, size_t smem_fixed, cudaStream_t st)
 {
@@ -56,6 +83,11 @@ static cudaError_t by_mode(const FusedArgs &A, int method, int mode, int sm_coun
 #define NDP_CAT(a, b) NDP_CAT2(a, b)
 cudaError_t NDP_CAT(ndp_launch_fused_, NDP_FUSED_N)(const FusedArgs &A, int method, int mode, int sm_count, size_t smem_fixed, cudaStream_t st)
 {
+    if (A.g.vdim > 1) {          // vector-valued table: gather from the original grid, G lanes per query
+        if (method == NDP_M_NONE) return go_vec<NDP_M_NONE, 0, 0>(A, sm_count, smem_fixed, st);
+        return nsm_leading_pair(A.M) ? by_mode_vec<1>(A, method, mode, sm_count, smem_fixed, st)
+                                     : by_mode_vec<0>(A, method, mode, sm_count, smem_fixed, st);
+    }
     if (method == NDP_M_NONE) return go<NDP_M_NONE, 0, 0>(A, sm_count, smem_fixed, st);
     // tables whose voids depend on exactly their two leading axes take the specialised candidate loop
     return nsm_leading_pair(A.M) ? by_mode<1>(A, method, mode, sm_count, smem_fixed, st)

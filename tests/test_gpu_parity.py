@@ -45,7 +45,8 @@ def test_cuda_matches_reference_golden(path, variant):
     if gather == 2 and len(axes) <= 6 and z['grid'].shape[-1] * 8 < 128:
         assert T.stat('cellmajor') == 1
     scalar = z['grid'].shape[-1] == 1 and 2 <= len(axes) <= 6
-    if gather == 2 and not fused_off and scalar:
+    vector = z['grid'].shape[-1] > 1 and 2 <= len(axes) <= 6
+    if not fused_off and ((gather == 2 and scalar) or vector):
         # the last call was distance(); run one ndpolate to read which path served it
         T.ndpolate(z['q'], 2, 0)
         assert T.stat('fused') == (0 if 'assoc_dependent_nan' in path else 1)
