@@ -93,6 +93,14 @@ int ndpb_find_nearest(ndpb_table *t, const double *query_pts, int64_t n, int met
 int ndpb_ndpolate(ndpb_table *t, const double *query_pts, int64_t n, int method, int search,
                   double *interps, double *dists);
 
+/* The hypercube-caching path (reference README "Hypercube caching", ndpolator/ndpolator.py:110-187): ndpolate
+ * from the import products of a batch (what ndpb_find returned; host or DEVICE pointers -- kept on the device
+ * they never round-trip through the host), e.g. on several tables that share their axes.  Same results as
+ * ndpb_ndpolate on the original query points.  The reference has no such entry point: there the caller
+ * interpolates the cached hypercubes itself.  n < 2^31. */
+int ndpb_ndpolate_cached(ndpb_table *t, const double *normed, const int32_t *indices, const int32_t *flags,
+                         int64_t n, int method, int search, double *interps, double *dists);
+
 /* Replaces cndpolator.distance (src/ndp_py.c:196-251): LINEAR method, KDTREE
  * search, for every point. */
 int ndpb_distance(ndpb_table *t, const double *query_pts, int64_t n, double *dists);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get('NDPB_LIB') or os.path.join(HERE, 'libndpb200.so')
 # every symbol include/ndpb200.h declares (tests check the export list against the header)
 SYMBOLS = [
     'ndpb_table_create', 'ndpb_table_destroy', 'ndpb_find', 'ndpb_hypercubes', 'ndpb_find_nearest',
-    'ndpb_ndpolate', 'ndpb_distance', 'ndpb_table_nverts', 'ndpb_table_masks', 'ndpb_table_tree_topology',
+    'ndpb_ndpolate', 'ndpb_ndpolate_cached', 'ndpb_distance', 'ndpb_table_nverts', 'ndpb_table_masks', 'ndpb_table_tree_topology',
     'ndpb_table_set_option', 'ndpb_table_stat', 'ndpb_table_wait_stream', 'ndpb_last_error', 'ndpb_version',
     'ndpb_group_create', 'ndpb_group_destroy', 'ndpb_group_size', 'ndpb_group_table', 'ndpb_group_ndpolate',
     'ndpb_group_distance', 'ndpb_group_set_option', 'ndpb_group_stat',
@@ -54,6 +54,8 @@ def lib():
     L.ndpb_find_nearest.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp]
     L.ndpb_ndpolate.restype = C.c_int
     L.ndpb_ndpolate.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp]
+    L.ndpb_ndpolate_cached.restype = C.c_int
+    L.ndpb_ndpolate_cached.argtypes = [_vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp]
     L.ndpb_distance.restype = C.c_int
     L.ndpb_distance.argtypes = [_vp, _vp, C.c_int64, _vp]
     L.ndpb_table_nverts.restype = C.c_int64

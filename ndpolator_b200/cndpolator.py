@@ -176,18 +176,49 @@ class Table:
         _lib.check(_lib.lib().ndpb_find(self._h, qp, n, _ptr(idx), _ptr(flg), _ptr(nrm)))
         return idx, flg, nrm
 
+    def _cached_inputs(self, normed, indices, flags):
+        """-> (normed, indices, flags, n, on_device): contiguous float64 / int32 / int32, all on the host or all on
+        this table's GPU (device tensors stay where they are: the cache path never round-trips through the host)."""
+        dev = _is_cuda(normed)
+        if dev != _is_cuda(indices) or dev != _is_cuda(flags):
+            raise ValueError('normed_query_pts, indices and flags must all live on the host or all on the device')
+        if dev:
+            import torch
+            nrm = normed.to(torch.float64).contiguous()
+            idx = indices.to(torch.int32).contiguous()
+            flg = flags.to(torch.int32).contiguous()
+            for t in (nrm, idx, flg):
+                if t.device.index != self.device:
+                    raise ValueError(f'cached import products live on {t.device}, the table on cuda:{self.device}')
+            self._order_after_producer(True)
+        else:
+            nrm = _host_f64(normed)
+            idx = np.ascontiguousarray(indices, dtype=np.int32)
+            flg = np.ascontiguousarray(flags, dtype=np.int32)
+        if tuple(nrm.shape) != tuple(idx.shape) or tuple(nrm.shape) != tuple(flg.shape) or nrm.shape[-1] != self.naxes:
+            raise ValueError(f'cached import products must all have shape (N, {self.naxes})')
+        return nrm, idx, flg, int(idx.shape[0]), dev
+
     def hypercubes_raw(self, normed, indices, flags):
-        nrm = _host_f64(normed)
-        idx = np.ascontiguousarray(indices, dtype=np.int32)
-        flg = np.ascontiguousarray(flags, dtype=np.int32)
-        n = idx.shape[0]
+        """-> (dim (n,), fdhc (n,), v (n, 2^naxes * vdim)): one packed block per output instead of N arrays; the
+        first 2^dim[i] * vdim values of row i are the hypercube of query i.  Device inputs give device outputs."""
+        nrm, idx, flg, n, dev = self._cached_inputs(normed, indices, flags)
         slot = (1 << self.naxes) * self.vdim
-        dim = np.empty(n, np.int32)
-        fdhc = np.empty(n, np.int32)
-        v = np.empty((n, slot), np.float64)
-        _lib.check(_lib.lib().ndpb_hypercubes(self._h, nrm.ctypes.data, idx.ctypes.data, flg.ctypes.data, n,
-                                               dim.ctypes.data, fdhc.ctypes.data, v.ctypes.data))
+        dim = _empty((n,), np.int32, dev, self.device)
+        fdhc = _empty((n,), np.int32, dev, self.device)
+        v = _empty((n, slot), np.float64, dev, self.device)
+        _lib.check(_lib.lib().ndpb_hypercubes(self._h, _ptr(nrm), _ptr(idx), _ptr(flg), n, _ptr(dim), _ptr(fdhc), _ptr(v)))
         return dim, fdhc, v
+
+    def ndpolate_cached(self, normed, indices, flags, method=0, search=0):
+        """ndpolate from cached import products (what find() returned) -- the hypercube-caching path of the
+        reference's README, device-resident when the cache is.  Same results as ndpolate() on the original points."""
+        nrm, idx, flg, n, dev = self._cached_inputs(normed, indices, flags)
+        interps = _empty((n, self.vdim), np.float64, dev, self.device)
+        dists = _empty((n, 1), np.float64, dev, self.device)
+        _lib.check(_lib.lib().ndpb_ndpolate_cached(self._h, _ptr(nrm), _ptr(idx), _ptr(flg), n, int(method), int(search),
+                                                    _ptr(interps), _ptr(dists)))
+        return interps, dists
 
     def find_nearest(self, query_pts, method, search):
         q, qp, n, dev = _prep_queries(query_pts, self.naxes, self.device)
@@ -215,6 +246,29 @@ class Table:
         dists = _empty((n, 1), np.float64, dev, self.device)
         _lib.check(_lib.lib().ndpb_distance(self._h, qp, n, _ptr(dists)))
         return dists
+
+
+class PackedHypercubes:
+    """Device-resident result of find_hypercubes(): `values` (N, 2^naxes * vdim) holds the hypercube of query i
+    in its first 2^dim[i] * vdim entries (corner-major, first free axis = most significant bit, as in the
+    reference); `dim` (N,) and `fdhc` (N,) are device tensors too.  hc[i] gives what the reference's tuple
+    element i is, as a device tensor of shape (2,)*dim[i] + (vdim,); len(hc) == N."""
+
+    def __init__(self, dim, fdhc, values, vdim):
+        self.dim, self.fdhc, self.values, self.vdim = dim, fdhc, values, vdim
+        self._dim_host = None
+
+    def __len__(self):
+        return int(self.dim.shape[0])
+
+    def __getitem__(self, i):
+        if self._dim_host is None:
+            self._dim_host = self.dim.cpu().numpy()
+        d = int(self._dim_host[i])
+        return self.values[i, :(1 << d) * self.vdim].reshape((2,) * d + (self.vdim,))
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
 
 
 class Group:
@@ -331,6 +385,9 @@ def hypercubes(normed_query_pts, indices, axes, flags, grid, nbasic=0, capsule=N
         if table is not capsule:
             table.close()
     vdim = table.vdim
+    if _is_cuda(v):
+        # device-resident cache: one packed block (PackedHypercubes) instead of N arrays; index it like the tuple
+        return PackedHypercubes(dim, fdhc, v, vdim)
     return tuple(v[i, :(1 << int(d)) * vdim].reshape((2,) * int(d) + (vdim,)).copy() for i, d in enumerate(dim))
 
 

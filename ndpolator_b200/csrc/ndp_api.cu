@@ -856,6 +856,7 @@ static int launch_slow(ndpb_table *t, Slot &s, const double *q, int method, int 
     A.grid = t->grid; A.q = q; A.method = method; A.search = search;
     A.list = tie ? s.tielist : s.list;
     A.count = tie ? &s.ctr->n_tie : &s.ctr->n_slow;
+    A.count_host = 0; A.c_idx = nullptr; A.c_flg = nullptr; A.c_nrm = nullptr;
     A.interps = interps; A.dists = dists; A.tielist = s.tielist; A.count_searched = tie ? 0 : 1; A.ctr = s.ctr;
     CU(ndp_launch_slow(A, t->sm_count * 2, smem_bytes(t), st));
     t->st_launches++;
@@ -1318,4 +1319,58 @@ extern "C" int ndpb_group_ndpolate(ndpb_group *g, const double *query_pts, int64
 extern "C" int ndpb_group_distance(ndpb_group *g, const double *query_pts, int64_t n, double *dists)
 {
     return group_call(g, 1, query_pts, n, NDPB_METHOD_LINEAR, NDPB_SEARCH_KDTREE, nullptr, dists);
+}
+
+// ---------------------------------------------------------------------------
+// Hypercube-caching path (reference README "Hypercube caching", ndpolator/ndpolator.py:110-187): the caller
+// keeps the import products of a batch (ndpb_find) -- on the device, if it passes device pointers -- and
+// interpolates from them, e.g. on several tables that share their axes.  Runs the exact generic kernel
+// (k_slow) over all queries; identical results to ndpb_ndpolate on the original query points.
+// ---------------------------------------------------------------------------
+extern "C" int ndpb_ndpolate_cached(ndpb_table *t, const double *normed, const int32_t *indices, const int32_t *flags,
+                                    int64_t n, int method, int search, double *interps, double *dists)
+{
+    int rc = check_call(t, normed, n, true);
+    if (rc) return rc;
+    if (method < NDPB_METHOD_NONE || method > NDPB_METHOD_LINEAR) return fail(NDPB_ERR_INVALID, "invalid extrapolation method");
+    if (search < NDPB_SEARCH_KDTREE || search > NDPB_SEARCH_LINEAR) return fail(NDPB_ERR_INVALID, "invalid search algorithm");
+    if (n > 0 && (!indices || !flags || !interps || !dists)) return fail(NDPB_ERR_INVALID, "NULL argument");
+    if (n >= (1LL << 31)) return fail(NDPB_ERR_INVALID, "at most 2^31 - 1 cached queries per call");
+    std::lock_guard<std::mutex> lk(t->mu);
+    CU(cudaSetDevice(t->device));
+    reset_stats(t);
+    if (n == 0) return NDPB_OK;
+    const size_t e = (size_t) n * t->g.naxes;
+    Staged<double> nrm, out_i, out_d; Staged<int32_t> idx, flg;
+    if ((rc = nrm.in(normed, e)) || (rc = idx.in(indices, e)) || (rc = flg.in(flags, e)) ||
+        (rc = out_i.out(interps, (size_t) n * t->g.vdim)) || (rc = out_d.out(dists, (size_t) n))) return rc;
+    Slot &s = t->slot[0];
+    rc = ensure_slot(t, s, n, false, false, false, false, true);
+    if (rc) return rc;
+    cudaStream_t st = t->s_compute;
+    const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 0) CU(cudaMemsetAsync(s.ctr, 0, sizeof(NdpCounters), st));
+        SlowArgs A{};
+        A.g = t->g; A.F = t->pyr[m].d_desc; A.R = t->red[m].d_desc;
+        A.have_topo = t->topo[m].built ? 1 : 0;
+        A.topo.parent = t->topo[m].parent; A.topo.depth = t->topo[m].depth;
+        A.ticks = t->ticks; A.nticks = t->nticks; A.ticks_in_smem = ticks_in_smem(t);
+        A.grid = t->grid; A.q = nullptr; A.method = method; A.search = search;
+        A.list = pass ? s.tielist : nullptr; A.count = &s.ctr->n_tie; A.count_host = n;
+        A.c_idx = idx.dev; A.c_flg = flg.dev; A.c_nrm = nrm.dev;
+        A.interps = out_i.dev; A.dists = out_d.dev; A.tielist = s.tielist; A.count_searched = pass ? 0 : 1; A.ctr = s.ctr;
+        const int blocks = (int) std::min<long long>((n + NDP_BLOCK - 1) / NDP_BLOCK, (long long) t->sm_count * 8);
+        CU(ndp_launch_slow(A, std::max(blocks, 1), smem_bytes(t), st));
+        t->st_launches++;
+        CU(cudaMemcpyAsync(s.ctr_host, s.ctr, sizeof(NdpCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (pass == 1 || s.ctr_host->n_tie == 0) break;
+        t->st_ties += s.ctr_host->n_tie;
+        rc = ensure_topology(t, m);              // kd distance ties: build the reference-shaped topology, redo them
+        if (rc) return rc;
+    }
+    t->st_hard += s.ctr_host->n_hard;
+    if ((rc = out_i.back()) || (rc = out_d.back())) return rc;
+    return NDPB_OK;
 }

@@ -441,7 +441,9 @@ struct SlowArgs {
     const double *grid;
     const double *q;
     int method, search;
-    const int *list; const int *count;     // query ids to do, device count
+    const int *list; const int *count;     // query ids to do, device count; list == nullptr: queries 0 .. count_host
+    long long count_host;
+    const int *c_idx; const int *c_flg; const double *c_nrm;   // cached import products (n x naxes) instead of q, or nullptr
     double *interps; double *dists;
     int *tielist;                          // out: query ids whose kd tie needs the topology (have_topo == 0)
     int count_searched;                    // 1: add the searched queries to ctr->n_off (slow pass), 0: tie pass
@@ -458,12 +460,14 @@ __global__ void __launch_bounds__(NDP_BLOCK, 2) k_slow(const __grid_constant__ S
     const int n = g.naxes, V = g.vdim;
     const int mode = ndp_mode_of(A.method, A.search);
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    const long long total = *A.count;
+    const long long total = A.list ? (long long) *A.count : A.count_host;
     for (long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long) gridDim.x * blockDim.x) {
-        const long long i = A.list[s];
+        const long long i = A.list ? (long long) A.list[s] : s;
         int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES];
         double nrm[NDP_MAX_AXES];
-        ndp_import_query_seq<0>(g, tk, A.q + i * n, idx, flg, nrm);
+        if (A.c_idx) {
+            for (int a = 0; a < n; a++) { idx[a] = A.c_idx[i * n + a]; flg[a] = A.c_flg[i * n + a]; nrm[a] = A.c_nrm[i * n + a]; }
+        } else ndp_import_query_seq<0>(g, tk, A.q + i * n, idx, flg, nrm);
         unsigned pin, sel;
         const bool oob = ndp_classify<0>(g, flg, nrm, pin, sel);
         bool fdhc = !oob;

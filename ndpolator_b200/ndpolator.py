@@ -106,6 +106,22 @@ class Ndpolator():
         capsule = self._capsule(name) if same_axes else None
         return cndpolator.hypercubes(normed_query_pts=normed_query_pts, indices=indices, axes=axes, flags=flags, grid=grid, capsule=capsule)
 
+    def ndpolate_cached(self, name: str, normed_query_pts, indices, flags, extrapolation_method: str = 'none',
+                        search_algorithm: str = 'kdtree') -> dict:
+        """Extension (not in the reference): ndpolate from cached import products -- what import_query_pts()
+        returned, kept on the device if they were computed there -- e.g. for several tables on the same axes.
+        Same result dictionary as ndpolate()."""
+        methods = {'none': ExtrapolationMethod.NONE, 'nearest': ExtrapolationMethod.NEAREST, 'linear': ExtrapolationMethod.LINEAR}
+        searches = {'kdtree': SearchAlgorithm.KDTREE, 'linear': SearchAlgorithm.LINEAR}
+        if extrapolation_method not in methods:
+            raise ValueError(f"extrapolation_method={extrapolation_method} is not valid; it must be one of {methods.keys()}.")
+        if search_algorithm not in searches:
+            raise ValueError(f"search_algorithm={search_algorithm} is not valid; it must be one of {searches.keys()}.")
+        capsule = self._capsule(name)
+        table = capsule.member(0) if isinstance(capsule, cndpolator.Group) else capsule
+        interps, dists = table.ndpolate_cached(normed_query_pts, indices, flags, methods[extrapolation_method], searches[search_algorithm])
+        return {'interps': interps} if extrapolation_method == 'none' else {'interps': interps, 'dists': dists}
+
     def distance(self, name: str, query_pts: np.ndarray) -> np.ndarray:
         # reference ndpolator/ndpolator.py:229-251 (here the table is cached on first use as well)
         if not cndpolator._is_cuda(query_pts):

@@ -288,3 +288,92 @@ def test_c4_full_size_properties():
     a = O.ndpolate(q[inside].cpu().numpy(), 0, 0)
     assert_same_bits(a[0], res[0][0][inside].cpu().numpy(), 'C4 full size, in-grid vs oracle')
     T.close()
+
+
+def _group_case():
+    from ndpolator_b200 import synth
+    w = synth.workload('C4', 12, n_queries=300000)
+    return w, w.grid(), w.queries(0, 300000)
+
+
+@pytest.mark.parametrize('ndev', [1, 2, 8])
+def test_group_one_call_several_gpus(ndev):
+    """ndpb_group: one host batch cut into contiguous ranges over `ndev` replicated tables, each device copying
+    its results into its slice of the caller's arrays -- bit for bit what one table returns (and the oracle)."""
+    import torch
+    if torch.cuda.device_count() < ndev:
+        pytest.skip(f'needs {ndev} GPUs')
+    from ndpolator_b200.cndpolator import Group
+    w, grid, q = _group_case()
+    O = Oracle('port', w.axes, grid, 5)
+    G = Group(w.axes, grid, 5, devices=list(range(ndev)))
+    G.set_option('min_queries_per_device', 1000)
+    for m in (0, 1, 2):
+        want = O.ndpolate(q, m, 0, threads=os.cpu_count() or 1)
+        got = G.ndpolate(q, m, 0)
+        assert_same_bits(want[0], got[0], f'group interps method {m}')
+        assert_same_bits(want[1], got[1], f'group dists method {m}')
+        assert G.stat('used_devices') == ndev
+    assert_same_bits(O.distance(q[:5000]), G.distance(q[:5000]), 'group distance')
+    small = G.ndpolate(q[:10], 2, 0)                       # a batch too small to split runs on one device
+    assert G.stat('used_devices') == 1
+    assert_same_bits(small[0], O.ndpolate(q[:10], 2, 0)[0], 'small batch')
+    with pytest.raises(ValueError):
+        G.ndpolate(torch.zeros((4, 5), dtype=torch.float64, device='cuda'), 0, 0)
+    G.close()
+
+
+def test_ndpolator_class_with_device_list():
+    import torch
+    from ndpolator_b200 import Ndpolator
+    w, grid, q = _group_case()
+    devices = list(range(min(2, torch.cuda.device_count())))
+    ndp = Ndpolator(w.basic_axes, devices=devices)
+    ndp.register('t', None, grid)
+    got = ndp.ndpolate('t', q[:50000], extrapolation_method='linear')
+    O = Oracle('port', w.axes, grid, 5)
+    want = O.ndpolate(q[:50000], 2, 0, threads=os.cpu_count() or 1)
+    assert_same_bits(want[0], got['interps'], 'Ndpolator(devices=...) interps')
+    assert_same_bits(want[1], got['dists'], 'Ndpolator(devices=...) dists')
+
+
+@pytest.mark.parametrize('case', [c for c in build_cases(seed=21) if c[0] in ('holed3d', '2basic_1assoc_v2', '5d_corner_void', 'c3_like_v16')],
+                         ids=lambda c: c[0])
+def test_device_resident_cache_path(case):
+    """import_query_pts -> find_hypercubes -> ndpolate_cached on DEVICE tensors (reference README
+    'Hypercube caching', ndpolator/ndpolator.py:110-187): nothing round-trips through the host, and every product
+    equals the oracle's / the uncached call's, bit for bit."""
+    import torch
+    from ndpolator_b200 import Ndpolator
+    name, axes, nbasic, grid = case
+    q = adversarial_queries(axes, 5000, np.random.default_rng(77))
+    O = Oracle('port', axes, grid, nbasic)
+    ndp = Ndpolator(tuple(axes[:nbasic]))
+    ndp.register('t', tuple(axes[nbasic:]) or None, grid)
+    qd = torch.as_tensor(q, device='cuda')
+    ndp.ndpolate('t', qd)                                    # creates the device table
+    idx, flg, nrm = ndp.import_query_pts('t', qd)
+    assert idx.is_cuda and flg.is_cuda and nrm.is_cuda
+    fo = O.find(q)
+    for a, b, what in zip(fo, (idx, flg, nrm), ('indices', 'flags', 'normed')):
+        assert_same_bits(a, b.cpu().numpy(), what)
+    hc = ndp.find_hypercubes('t', nrm, idx, flg, tuple(axes[nbasic:]) or None)
+    assert hc.values.is_cuda and len(hc) == len(q)
+    dim_o, fdhc_o, v_o = O.hypercubes(*fo)
+    assert_same_bits(dim_o, hc.dim.cpu().numpy(), 'dim')
+    assert_same_bits(fdhc_o, hc.fdhc.cpu().numpy(), 'fdhc')
+    vdim = grid.shape[-1]
+    for i in (0, 17, len(q) - 1):
+        m = (1 << int(dim_o[i])) * vdim
+        assert_same_bits(v_o[i, :m].reshape(hc[i].shape), hc[i].cpu().numpy(), f'hypercube {i}')
+    for method, m in (('none', 0), ('nearest', 1), ('linear', 2)):
+        got = ndp.ndpolate_cached('t', nrm, idx, flg, extrapolation_method=method)
+        want = O.ndpolate(q, m, 0)
+        assert got['interps'].is_cuda
+        assert_same_bits(want[0], got['interps'].cpu().numpy(), f'cached interps {method}')
+        if m:
+            assert_same_bits(want[1], got['dists'].cpu().numpy(), f'cached dists {method}')
+    # host cache gives host results
+    got = ndp.ndpolate_cached('t', fo[2], fo[0], fo[1], extrapolation_method='linear')
+    assert isinstance(got['interps'], np.ndarray)
+    assert_same_bits(O.ndpolate(q, 2, 0)[0], got['interps'], 'cached interps from host arrays')
