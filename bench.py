@@ -51,6 +51,9 @@ def parse():
                     help='ticks per axis of the grid the CPU reference is timed on (default: 24 for C4 -- BASELINE.md 4.5 -- else full size)')
     ap.add_argument('--cpu-queries', type=int, default=20000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--inprocess', action='store_true',
+                    help='ONE process, --gpus N devices through ndpb_group (one ndpolate call split over N GPUs): end-to-end '
+                         'from pinned host arrays only; launch with plain python, not torchrun')
     return ap.parse_args()
 
 
@@ -520,6 +523,82 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def interleave_host_memory():
+    """set_mempolicy(MPOL_INTERLEAVE, all nodes) for this thread: the pinned batch of an in-process multi-GPU
+    call is then spread over the NUMA nodes instead of sitting next to one socket.  Best effort (x86-64 syscall)."""
+    try:
+        import ctypes
+        nodes = [int(d[4:]) for d in os.listdir('/sys/devices/system/node') if d.startswith('node') and d[4:].isdigit()]
+        if len(nodes) < 2:
+            return f'{len(nodes)} NUMA node'
+        mask = ctypes.c_ulong(sum(1 << n for n in nodes))
+        libc = ctypes.CDLL(None, use_errno=True)
+        rc = libc.syscall(238, 3, ctypes.byref(mask), ctypes.c_ulong(max(nodes) + 2))      # SYS_set_mempolicy, MPOL_INTERLEAVE
+        return f'interleaved over {len(nodes)} NUMA nodes' if rc == 0 else f'set_mempolicy failed ({ctypes.get_errno()})'
+    except Exception as e:
+        return f'not interleaved ({e!r})'
+
+
+def run_inprocess(args):
+    """One process, one ndpolate call per step over N GPUs (ndpb_group / cndpolator.Group): host arrays in, host
+    arrays out, every GPU copying its slice back itself -- the API-level multi-GPU number."""
+    import numpy as np
+    import torch
+    from ndpolator_b200 import synth
+    from ndpolator_b200.cndpolator import Group, Table
+    n_dev = args.gpus
+    w = synth.workload(args.workload, args.scale, mix=args.mix)
+    method = METHODS[args.method or w.method]
+    search = SEARCHES[args.search]
+    policy = interleave_host_memory()
+    per_gpu = args.e2e_batch
+    total = per_gpu * n_dev
+    grid = w.grid()                                            # host grid: every member uploads its own replica
+    t0 = time.perf_counter()
+    G = Group(w.axes, grid, len(w.basic_axes), devices=list(range(n_dev)))
+    build_s = time.perf_counter() - t0
+    qh = torch.empty((total, w.naxes), dtype=torch.float64).pin_memory()
+    for lo in range(0, total, 1 << 23):
+        c = min(1 << 23, total - lo)
+        qh[lo:lo + c] = w.queries(lo, c, 'cuda:0').cpu()
+    ih = torch.empty((total, w.vdim), dtype=torch.float64).pin_memory()
+    dh = torch.empty((total, 1), dtype=torch.float64).pin_memory()
+    qn, inn, dn = qh.numpy(), ih.numpy(), dh.numpy()
+    sampler = ClockSampler(0)
+    sampler.start()
+    for _ in range(max(1, args.warmup)):
+        G.ndpolate(qn, method, search, out=(inn, dn))
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < args.steps or time.perf_counter() - t0 < 1.0:
+        G.ndpolate(qn, method, search, out=(inn, dn))
+        steps += 1
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    # same rows through ONE table: identical bits
+    T = G.member(0)
+    sub = min(total, 1 << 22)
+    ri, rd = T.ndpolate(qn[:sub], method, search)
+    same = bool(np.array_equal(ri.view(np.uint64), inn[:sub].view(np.uint64)) and np.array_equal(rd.view(np.uint64), dn[:sub].view(np.uint64)))
+    if not same:
+        raise SystemExit('bench.py --inprocess: group results differ from a single table')
+    value = total * steps / dt
+    cfg = workload_config(args)
+    cfg['queries_per_step_all_gpus'] = total
+    cfg['queries_per_gpu_per_step'] = per_gpu
+    cfg['parallelism'] = f'ONE process, one ndpolate call per step split over {n_dev} GPUs (ndpb_group): contiguous query ranges, table replicated, every GPU copies its slice of the results back; no collective'
+    print(json.dumps({
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_dev, 'steps': steps, 'warmup': max(1, args.warmup),
+        'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': cfg, 'mode': 'inprocess-group (value IS the end-to-end number: host arrays in and out)',
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': G.stat('h2d_bytes'), 'd2h_bytes_per_step': G.stat('d2h_bytes'),
+                'queries_per_gpu_per_step': per_gpu, 'steps': steps, 'seconds': dt, 'host_memory': f'pinned, {policy}',
+                'matches_single_table': same},
+        'gpu_launches': G.stat('launches') * steps, 'clocks': clocks,
+        'table': {'build_s': build_s, 'note': 'N replicas built concurrently, one host thread per device'},
+    }))
+
+
 def main():
     args = parse()
     # Only the JSON line may reach stdout: libraries (NCCL's version banner, for one) write to
@@ -538,6 +617,8 @@ def main():
 
     if args.impl == 'reference':
         run_reference(args)
+    elif args.inprocess:
+        run_inprocess(args)
     else:
         run_b200(args)
 

@@ -1,0 +1,24 @@
+#!/bin/bash
+# One N-GPU gpurun call: group tests, PCIe probe, torchrun bench at the given rank counts, in-process group bench.
+#   gpurun --gpus 8 -- 'bash tools/gpu_multi.sh r02g 8 "4 8"'
+TAG=$1; NMAX=$2; RANKS=${3:-$NMAX}
+OUT=gpurun_out; mkdir -p $OUT
+timeout 600 python -m pytest tests -m gpu -x -q -k "group or device_list" > $OUT/${TAG}_tests_group.log 2>&1; echo "group tests rc=$?"; tail -2 $OUT/${TAG}_tests_group.log
+: > $OUT/${TAG}_probe_pcie.jsonl
+for n in $RANKS; do
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 tools/probe_pcie.py 2>/dev/null >> $OUT/${TAG}_probe_pcie.jsonl
+done
+grep '"both"' $OUT/${TAG}_probe_pcie.jsonl | cut -c1-260
+for n in $RANKS; do
+  timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $n --steps 8 --warmup 3 > $OUT/${TAG}_bench_${n}gpu.json 2> $OUT/${TAG}_bench_${n}gpu.err; echo "bench $n rc=$?"
+done
+timeout 600 python bench.py --gpus $NMAX --inprocess --steps 10 --warmup 2 --e2e-batch 16777216 > $OUT/${TAG}_bench_inprocess_${NMAX}gpu.json 2> $OUT/${TAG}_bench_inprocess_${NMAX}gpu.err; echo "inprocess rc=$?"
+python - <<PY
+import json, glob
+for f in sorted(glob.glob('$OUT/${TAG}_bench_*gpu.json')):
+    try:
+        d = json.load(open(f))
+        print(f.split('/')[-1], 'n', d['n_gpus'], 'value %.3e' % d['value'], 'ms %.2f' % d['ms_per_step'], 'e2e %.3e' % d['e2e']['value'], d['e2e'].get('host_memory'), d['clocks']['sm_mhz'], d['clocks']['reasons'])
+    except Exception as e:
+        print(f, 'unreadable', e)
+PY
