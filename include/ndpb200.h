@@ -127,7 +127,9 @@ int ndpb_table_wait_stream(ndpb_table *t, uint64_t producer_stream);
 
 /* Tuning knobs that never change results.  Keys: "gather" = 0 auto | 1 strided
  * (original layout) | 2 cell-major; "linear_search" = 0 auto | 1 brute force |
- * 2 lattice; "chunk" = queries per staged chunk for host buffers; "fused" = 0 auto | 1 never use the
+ * 2 lattice; "chunk" = queries per staged chunk for host buffers; "block_order" = 0 auto | K: blocked copy of a scalar table with 2^K corners per
+ * contiguous block (K = naxes is the cell-major copy; smaller K costs 2^K times the grid instead of 2^naxes);
+ * "fused" = 0 auto | 1 never use the
  * fused kernel (import + mask/nearest-site-map plan + one cell gather per query); "staged" = 0 auto: one-stage
  * cp.async gather, 4 CTAs/SM | 1 never use the staged gather kernels | 2 two-stage ring | 3 one stage,
  * 5 CTAs/SM (only used when the fused kernel is off or does not apply);
@@ -142,7 +144,7 @@ int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t value);
  * "hard" queries that needed the lattice descent, "ties" queries resolved
  * through the kd topology, "slow" queries the fused kernel handed to the exact generic
  * kernel, "fused" batches that went through the fused kernel, "h2d_bytes", "d2h_bytes",
- * "cellmajor" (0/1), "use_hc" (0/1: the hypercube-mask bit decides "fully defined"),
+ * "cellmajor" (0/1), "block_order" (order of the blocked copy in use, 0 = none), "use_hc" (0/1: the hypercube-mask bit decides "fully defined"),
  * "main_ns" / "search_ns" / "finish_ns" device time (CUDA events) of the gather kernel
  * (fused or staged), of the search / slow-list kernels and of the extrapolation finish,
  * "nsm_regions_nearest" / "nsm_regions_linear" regions of the nearest-site maps built so

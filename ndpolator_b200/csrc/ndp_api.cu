@@ -104,7 +104,10 @@ struct ndpb_table {
     NdpGeom g{};
     int nticks = 0;
     bool has_grid = false;
-    double *ticks = nullptr, *grid = nullptr, *cells = nullptr;
+    double *ticks = nullptr, *grid = nullptr;
+    double *cells = nullptr;                // full cell-major copy (block order == naxes), what the staged / direct kernels read
+    double *blocks = nullptr;               // blocked copy of a scalar table (ndp_fused.cuh: NdpBlocks), what k_fused reads
+    int block_order = 0;
     long long grid_doubles = 0;
     Pyramid pyr[2];                         // [0] vmask, [1] hcmask: over the whole basic lattice
     Pyramid red[2];                         // the same masks over their variant axes only
@@ -122,7 +125,7 @@ struct ndpb_table {
     std::mutex mu;
     int sm_count = 148;
     // options
-    int opt_gather = 0, opt_linear_search = 0, opt_staged = 0, opt_fused = 0;
+    int opt_gather = 0, opt_linear_search = 0, opt_staged = 0, opt_fused = 0, opt_block_order = 0;
     long long opt_chunk = 1 << 20;          // profiles/r01p_sweep_chunk.txt: 1 Mi beats 2, 4 and 8 Mi end to end
     int opt_fast_blocks = 64, opt_hard_blocks = 256;   // grid-stride CTAs per SM of the two search passes (profiles/r01p_sweep_search.txt)
     // stats of the last call
@@ -261,7 +264,8 @@ extern "C" int ndpb_table_destroy(ndpb_table *t)
     if (!t) return NDPB_OK;
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
-    cudaFree(t->ticks); cudaFree(t->grid); cudaFree(t->cells);
+    cudaFree(t->ticks); cudaFree(t->grid);
+    if (t->blocks) cudaFree(t->blocks); else cudaFree(t->cells);      // cells aliases blocks when the order is naxes
     for (Pyramid *set : {t->pyr, t->red})
         for (int m = 0; m < 2; m++) {
             for (auto p : set[m].owned) cudaFree(p);
@@ -278,20 +282,51 @@ extern "C" int ndpb_table_destroy(ndpb_table *t)
     return NDPB_OK;
 }
 
+static void drop_cells(ndpb_table *t)
+{
+    if (t->blocks) cudaFree(t->blocks); else cudaFree(t->cells);
+    t->blocks = t->cells = nullptr;
+    t->block_order = 0;
+}
+
+// The gather-friendly copy of the grid.  Scalar tables: the blocked layout of ndp_fused.cuh with the largest block
+// order whose copy (2^order times the grid) fits in half of the free device memory -- order == naxes is the
+// cell-major copy (one contiguous (8 << n)-byte burst per query), smaller orders cost 2^(n - order) bursts of
+// (8 << order) bytes per query and serve tables whose full copy would not fit.  Small-vector tables (vdim * 8 <
+// 128): the full cell-major copy when it fits.  Vectors of a full line and more are gathered from the grid itself.
 static int maybe_build_cells(ndpb_table *t)
 {
     const NdpGeom &g = t->g;
-    if (t->cells || t->opt_gather == 1 || g.naxes > 6) return NDPB_OK;
-    // pays when a corner vector is smaller than a 128-byte line; must fit comfortably
-    const long long bytes = (g.ncells << g.naxes) * g.vdim * (long long) sizeof(double);
+    if (t->cells || t->blocks || t->opt_gather == 1 || g.naxes > 6) return NDPB_OK;
     if (t->opt_gather != 2 && g.vdim * sizeof(double) >= 128) return NDPB_OK;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    if (bytes > (long long) (free_b / 2)) return NDPB_OK;
-    CU(cudaMalloc(&t->cells, bytes));
-    k_build_cells<<<t->sm_count * 16, NDP_BLOCK, 0, t->s_compute>>>(g, t->grid, t->cells);
+    if (g.vdim != 1) {
+        const long long bytes = (g.ncells << g.naxes) * g.vdim * (long long) sizeof(double);
+        if (bytes > (long long) (free_b / 2)) return NDPB_OK;
+        CU(cudaMalloc(&t->cells, bytes));
+        k_build_cells<<<t->sm_count * 16, NDP_BLOCK, 0, t->s_compute>>>(g, t->grid, t->cells);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(t->s_compute));
+        return NDPB_OK;
+    }
+    NdpBlocks B{};
+    int order = 0;
+    for (int k = g.naxes; k >= 1; k--) {
+        if (t->opt_block_order && k != t->opt_block_order) continue;
+        ndp_blocks_setup(g, k, B);
+        if (((B.nblocks << k) * (long long) sizeof(double)) <= (long long) (free_b / 2)) { order = k; break; }
+    }
+    if (!order) return NDPB_OK;
+    CU(cudaMalloc(&t->blocks, (size_t) (B.nblocks << order) * sizeof(double)));
+    BlockBuildArgs A{};
+    A.g = g; A.order = order; A.nblocks = B.nblocks; A.grid = t->grid; A.blocks = t->blocks;
+    for (int a = 0; a < g.naxes; a++) A.stride[a] = B.stride[a];
+    k_build_blocks<<<t->sm_count * 16, NDP_BLOCK, 0, t->s_compute>>>(A);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(t->s_compute));
+    t->block_order = order;
+    if (order == g.naxes) t->cells = t->blocks;
     return NDPB_OK;
 }
 
@@ -461,8 +496,14 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
     if (k == "gather") {
         if (value < 0 || value > 2) return fail(NDPB_ERR_INVALID, "gather must be 0, 1 or 2");
         t->opt_gather = (int) value;
-        if (value == 1 && t->cells) { CU(cudaDeviceSynchronize()); CU(cudaFree(t->cells)); t->cells = nullptr; }
+        if (value == 1 && (t->cells || t->blocks)) { CU(cudaDeviceSynchronize()); drop_cells(t); }
         if (value != 1 && t->has_grid) return maybe_build_cells(t);
+        return NDPB_OK;
+    }
+    if (k == "block_order") {
+        if (value < 0 || value > t->g.naxes) return fail(NDPB_ERR_INVALID, "block_order must be 0 (auto: the largest that fits) or 1..naxes");
+        t->opt_block_order = (int) value;
+        if (t->has_grid && t->opt_gather != 1) { CU(cudaDeviceSynchronize()); drop_cells(t); return maybe_build_cells(t); }
         return NDPB_OK;
     }
     if (k == "linear_search") {
@@ -527,6 +568,7 @@ extern "C" int64_t ndpb_table_stat(const ndpb_table *t, const char *key)
     if (k == "h2d_bytes") return t->st_h2d;
     if (k == "d2h_bytes") return t->st_d2h;
     if (k == "cellmajor") return t->cells ? 1 : 0;
+    if (k == "block_order") return t->block_order;
     if (k == "slow") return t->st_slow;
     if (k == "fused") return t->st_fused;
     if (k == "use_hc") return t->use_hc ? 1 : 0;
@@ -802,7 +844,7 @@ enum Task { TASK_NDPOLATE, TASK_NEAREST, TASK_DISTANCE };
 static bool fused_ok(ndpb_table *t, int method, int search)
 {
     if (t->opt_fused == 1 || t->g.naxes < 2 || t->g.naxes > 6 || !t->use_hc) return false;
-    if (t->g.vdim == 1 && !t->cells) return false;      // scalar tables gather from the cell-major copy, vector tables from the grid
+    if (t->g.vdim == 1 && !t->blocks) return false;     // scalar tables gather from the blocked copy, vector tables from the grid
     if ((size_t) t->nticks * sizeof(double) > 16 * 1024) return false;
     if (method == NDPB_METHOD_NONE) return true;
     if (use_brute(t, search)) return false;
@@ -817,8 +859,13 @@ static int launch_fused(ndpb_table *t, Slot &s, const double *q, long long n, in
     const NdpGeom &g = t->g;
     const int mode = ndp_mode_of(method, search);
     FusedArgs A{};
-    A.g = g; A.ticks = t->ticks; A.nticks = t->nticks; A.cells = t->cells; A.grid = t->grid;
+    A.g = g; A.ticks = t->ticks; A.nticks = t->nticks; A.cells = t->blocks; A.grid = t->grid;
     A.q = q; A.n = n; A.interps = interps; A.dists = dists;
+    if (g.vdim == 1) {
+        // the plan's cell number is a block number of the blocked copy
+        ndp_blocks_setup(g, t->block_order, A.B);
+        for (int a = 0; a < g.naxes; a++) { A.g.cstride[a] = A.B.stride[a]; A.g.cstride32[a] = g.small ? (int) A.B.stride[a] : 0; }
+    }
     A.H = t->hcs; A.hc_in_smem = t->hcs.nwords * sizeof(uint32_t) <= 8 * 1024;
     if (method != NDPB_METHOD_NONE) A.M = t->nsm[nsm_geo_of_mode(mode)];
     A.slowlist = s.list; A.ctr = s.ctr;

@@ -25,6 +25,44 @@ struct NdpHcSlice {
     int nwords;
 };
 
+// Blocked cell layout.  With block order K (1 <= K <= n) the corner values of a cell are stored as 2^(n-K)
+// BLOCKS of 2^K doubles: a block holds the corners that differ on the LAST K axes, and the blocks of one cell
+// differ on the first n-K ("outer") axes.  Blocks are indexed by vertex coordinates on the outer axes and cell
+// coordinates on the inner ones, so neighbouring cells share their outer-axis blocks: the copy costs 2^K times
+// the grid instead of 2^n (K = n: one block per cell = the cell-major copy).  The image of a cell in shared
+// memory is the same for every K -- corner j at byte 8 j, axis 0 = most significant bit -- so the reduction
+// does not change; only the source address of each 16-byte piece does:
+//   address(piece s of the cell below `sup`) = blocks + cell_of(sup) * (8 << K) + ndp_block_piece_offset(s),
+// cell_of() taken with the block strides.
+struct NdpBlocks {
+    int order;                          // K
+    long long stride[NDP_MAX_AXES];     // blocks per +1 on axis a (vertex coordinate on outer, cell coordinate on inner axes)
+    long long nblocks;
+};
+
+inline void ndp_blocks_setup(const NdpGeom &g, int order, NdpBlocks &B)
+{
+    const int n = g.naxes;
+    B.order = order;
+    long long st = 1;
+    for (int a = n - 1; a >= 0; a--) {
+        B.stride[a] = st;
+        st *= (a >= n - order) ? g.len[a] - 1 : g.len[a];
+    }
+    B.nblocks = st;
+}
+
+// byte offset, relative to the cell's first block, of the 16-byte piece s (corners 2 s and 2 s + 1) of a cell
+NDP_HD long long ndp_block_piece_offset(int n, int order, const long long *bstride, int s)
+{
+    const int j = 2 * s;                                   // corner number of the piece's first double
+    const int outer = j >> order;                          // bits of the outer axes, axis 0 = most significant
+    long long blocks = 0;
+    for (int a = 0; a < n - order; a++)
+        if ((outer >> (n - order - 1 - a)) & 1) blocks += bstride[a];
+    return blocks * ((long long) 8 << order) + (long long) (j & ((1 << order) - 1)) * 8;
+}
+
 template <int N>
 struct NdpPlan {
     int kind;

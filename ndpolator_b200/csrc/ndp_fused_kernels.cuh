@@ -20,6 +20,9 @@
 #include "ndp_kernels.cuh"
 
 #define NDP_FUSED_WARPS 4
+#ifndef NDP_FUSED_TMAQ
+#define NDP_FUSED_TMAQ 1      // query tiles by TMA bulk copy + mbarrier (0: per-lane cp.async pieces; same results)
+#endif
 
 struct FusedArgs {
     NdpGeom g;
@@ -32,6 +35,7 @@ struct FusedArgs {
     int *slowlist;
     NdpCounters *ctr;
     int gs;                   // k_fused_vec: log2 of the lanes that share one query (each owns components k, k + G, ...)
+    NdpBlocks B;              // k_fused: layout of `cells` (block order n = the cell-major copy); g.cstride holds B.stride
 };
 
 #if defined(NDP_TU_FUSED)
@@ -94,10 +98,32 @@ __device__ __forceinline__ void ndpf_cp_async8(unsigned dst, const void *src)
 }
 __device__ __forceinline__ void ndpf_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-// shared memory per warp: 32 copy slots; PIPE: + 2 query tiles + 2 tiles of saved plans (x[N], dist, 4 ints per lane)
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a contiguous block into shared memory, completion counted in
+// bytes on an mbarrier (SYNCS): one elected lane moves a whole tile of queries with one instruction.
+__device__ __forceinline__ void ndpf_mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ndpf_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void ndpf_mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ndpf_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ndpf_mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tNDPF_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra NDPF_DONE;\n\t"
+                 "bra NDPF_WAIT;\n\tNDPF_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// shared memory per warp: 32 copy slots; PIPE: + 2 query tiles + their 2 mbarriers; PIPE 1: + 2 tiles of saved plans
 __host__ __device__ constexpr unsigned ndpf_warp_bytes(int n, int pipe)
 {
-    return 32u * ((8u << n) + 16u) + (pipe ? 2u * 32u * 8u * (unsigned) n : 0u) +
+    return 32u * ((8u << n) + 16u) + (pipe ? 2u * 32u * 8u * (unsigned) n + 16u : 0u) +
            (pipe == 1 ? 2u * 32u * (8u * ((unsigned) n + 1u) + 16u) : 0u);
 }
 
@@ -145,14 +171,18 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
 
     unsigned char *s_slots = s_warp;
     unsigned char *s_q = s_warp + 32u * SLOT;                       // PIPE: [2][32][N] doubles
-    unsigned char *s_item = s_q + 2u * QTILE;                       // PIPE: [2][N + 1][32] doubles + [2][32] uint4
+    const unsigned s_bar = ndpf_smem_u32(s_q + 2u * QTILE);         // PIPE: one mbarrier per query buffer
+    unsigned char *s_item = s_q + 2u * QTILE + 16u;                 // PIPE 1: [2][N + 1][32] doubles + [2][32] uint4
     const unsigned char *my_slot = s_slots + (size_t) lane * SLOT;
     // cooperative copy: a cell is fetched by LPB consecutive lanes, 16 bytes each, i.e. as ONE contiguous (8 << N)-
     // byte request (measured on B200, tools/probe_gather.cu: 5.5x the rate of per-thread walks).  In sweep k the
     // LPB lanes of group `grp` fetch the cell of lane grp * LPB + k: a width-LPB shuffle with a constant lane.
     const unsigned sub = lane % LPB, grp = lane / LPB;
     const unsigned dst0 = ndpf_smem_u32(s_slots + (size_t) (grp * LPB) * SLOT) + sub * 16u;
-    const unsigned char *src0 = reinterpret_cast<const unsigned char *>(A.cells) + sub * 16u;
+    // blocked layout (NdpBlocks): piece `sub` of a cell sits at a fixed offset from the cell's first block
+    const unsigned BLOCK_BYTES = 8u << A.B.order;
+    const unsigned char *src0 = reinterpret_cast<const unsigned char *>(A.cells) + ndp_block_piece_offset(N, A.B.order, A.B.stride, (int) sub);
+    const long long src_step = CHUNKS > LPB ? ndp_block_piece_offset(N, A.B.order, A.B.stride, LPB) : 0;   // 512-byte cells: second sweep
 
     const long long ntiles = (A.n + 31) / 32;
     const long long tile_stride = (long long) gridDim.x * NDP_FUSED_WARPS;
@@ -179,20 +209,20 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
 #pragma unroll
             for (int k = 0; k < LPB; k++) {
                 const int oc = __shfl_sync(0xffffffffu, mine, k, LPB);
-                const unsigned char *src = ndpf_cell_ptr(src0, (unsigned) oc, CELL_BYTES);
+                const unsigned char *src = ndpf_cell_ptr(src0, (unsigned) oc, BLOCK_BYTES);
 #pragma unroll
                 for (int c = 0; c < CHUNKS / LPB; c++)
-                    ndpf_cp_async16_if(dst0 + (unsigned) k * SLOT + (unsigned) (c * LPB) * 16u, src + (c * LPB) * 16, oc);
+                    ndpf_cp_async16_if(dst0 + (unsigned) k * SLOT + (unsigned) (c * LPB) * 16u, src + c * src_step, oc);
             }
         } else {
             const long long mine = P.kind == NDP_PLAN_GATHER ? P.cell : -1;
 #pragma unroll
             for (int k = 0; k < LPB; k++) {
                 const long long oc = __shfl_sync(0xffffffffu, mine, k, LPB);
-                const unsigned char *src = src0 + (unsigned long long) oc * CELL_BYTES;
+                const unsigned char *src = src0 + (unsigned long long) oc * BLOCK_BYTES;
 #pragma unroll
                 for (int c = 0; c < CHUNKS / LPB; c++)
-                    ndpf_cp_async16_if(dst0 + (unsigned) k * SLOT + (unsigned) (c * LPB) * 16u, src + (c * LPB) * 16, (int) (oc >> 32));
+                    ndpf_cp_async16_if(dst0 + (unsigned) k * SLOT + (unsigned) (c * LPB) * 16u, src + c * src_step, (int) (oc >> 32));
             }
         }
     };
@@ -243,13 +273,25 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
             __syncwarp();                          // the slots may be overwritten by the next tile's copies
         }
     } else {
-        // query prefetch: the tile's 32 rows are contiguous in global memory; 16-byte pieces, coalesced
+        // query prefetch: the tile's 32 rows are contiguous in global memory.  A whole, 16-byte-aligned tile is ONE
+        // TMA bulk copy issued by lane 0, completing on the buffer's mbarrier; a partial last tile or an unaligned
+        // query array goes through per-lane cp.async pieces in the current cp.async group instead.
+        unsigned by_tma = 0, phase = 0;                                            // per buffer: bit `buf`
+        if (lane == 0) { ndpf_mbar_init(s_bar, 1); ndpf_mbar_init(s_bar + 8u, 1); ndpf_mbar_fence_init(); }
+        __syncwarp();
         auto prefetch_q = [&](long long tile, int buf) {
             if (tile >= ntiles) return;
             const unsigned dst = ndpf_smem_u32(s_q + (unsigned) buf * QTILE);
             const unsigned char *src = reinterpret_cast<const unsigned char *>(A.q) + tile * (long long) QTILE;
             const long long left = (A.n - tile * 32) * (long long) QROW;            // bytes of this tile that exist
-            if (q_aligned) {
+            by_tma &= ~(1u << buf);
+            if (NDP_FUSED_TMAQ && q_aligned && left >= (long long) QTILE) {
+                by_tma |= 1u << buf;
+                if (lane == 0) {
+                    ndpf_mbar_expect_tx(s_bar + 8u * (unsigned) buf, QTILE);
+                    ndpf_bulk_g2s(dst, src, QTILE, s_bar + 8u * (unsigned) buf);
+                }
+            } else if (q_aligned) {
 #pragma unroll
                 for (unsigned c = 0; c < (QCHUNKS + 31u) / 32u; c++) {
                     const unsigned piece = c * 32u + lane;
@@ -263,6 +305,13 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
                     const long long off = (long long) (c * 32u + lane) * 8;
                     if (off < left) ndpf_cp_async8(dst + (c * 32u + lane) * 8u, src + off);
                 }
+            }
+        };
+        // the queries of buffer `buf` have landed (its cp.async group, if any, was waited for by the caller)
+        auto await_q = [&](int buf) {
+            if (by_tma & (1u << buf)) {
+                ndpf_mbar_wait(s_bar + 8u * (unsigned) buf, (phase >> buf) & 1u);
+                phase ^= 1u << buf;
             }
         };
         double *itemd = reinterpret_cast<double *>(s_item);                         // [2][N + 1][32]
@@ -289,6 +338,7 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
             prefetch_q(tile0 + tile_stride, 1);
             ndpf_cp_async_commit();
             ndpf_cp_async_wait1();
+            await_q(0);
             __syncwarp();
             NdpPlan<N> P;
             make_plan(tile0, reinterpret_cast<const double *>(s_q) + lane * N, P);
@@ -309,6 +359,7 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
                 if (next < ntiles) {
                     // q(next) sits in the group before the newest one; the cells of `tile` stay in flight meanwhile
                     ndpf_cp_async_wait1();
+                    await_q(cur ^ 1);
                     __syncwarp();
                     make_plan(next, reinterpret_cast<const double *>(s_q + (unsigned) (cur ^ 1) * QTILE) + lane * N, Pn);
                     item_of(Pn, itn);

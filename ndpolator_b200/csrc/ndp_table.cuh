@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 #include "ndp_core.cuh"
+#include "ndp_fused.cuh"
 
 // vmask[v] = component 0 of the basic vertex (associated indices 0) is not NaN
 // (ndp_types.c:179-184).  One warp packs 32 vertices into one word.
@@ -171,6 +172,37 @@ __global__ void k_build_cells(const __grid_constant__ NdpGeom g, const double *_
             vert += (long long) (c + ((j >> (n - 1 - a)) & 1)) * g.vstride[a];
         }
         for (int k = 0; k < V; k++) cells[e * V + k] = grid[vert * V + k];
+    }
+}
+
+// Blocked copy (ndp_fused.cuh: NdpBlocks): blocks[(block * 2^K + i)] = corner whose last-K-axes bits are i of the
+// cell whose inferior corner is the block's coordinates (vertex coordinates on the outer axes).  K = n gives
+// k_build_cells' layout.  Scalar tables only.
+struct BlockBuildArgs {
+    NdpGeom g;
+    int order;
+    long long stride[NDP_MAX_AXES];
+    long long nblocks;
+    const double *grid; double *blocks;
+};
+
+__global__ void k_build_blocks(const __grid_constant__ BlockBuildArgs A)
+{
+    const int n = A.g.naxes, K = A.order;
+    const long long total = A.nblocks << K;
+    for (long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long) gridDim.x * blockDim.x) {
+        const int i = (int) (e & ((1LL << K) - 1));
+        long long blk = e >> K;
+        long long vert = 0;
+        for (int a = n - 1; a >= 0; a--) {
+            const bool inner = a >= n - K;
+            const int d = inner ? A.g.len[a] - 1 : A.g.len[a];
+            int c = (int) (blk % d);
+            blk /= d;
+            if (inner) c += (i >> (n - 1 - a)) & 1;
+            vert += (long long) c * A.g.vstride[a];
+        }
+        A.blocks[e] = A.grid[vert];
     }
 }
 

@@ -73,6 +73,10 @@ class HostSim:
         self.lib.hs_ndpolate(self.h, C.c_longlong(len(q)), _p(q, _dp), int(method), int(search), int(variant), _p(i, _dp), _p(d, _dp))
         return i, d
 
+    def set_block_order(self, order):
+        """Blocked copy of the grid (ndp_fused.cuh: NdpBlocks) for the fused path; 0 on tables it does not apply to."""
+        return int(self.lib.hs_set_block_order(self.h, int(order)))
+
     def ndpolate_fused(self, q, method, search):
         """The fused path's logic (plan from masks + nearest-site map, one gather); None when the
         table or mode does not qualify for it."""

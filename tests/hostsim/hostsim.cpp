@@ -32,7 +32,38 @@ struct HsTable {
     std::vector<uint32_t> nsm_ents[3];
     NdpHcSlice hcs;
     bool use_hc = false;                     // hypercube-mask bit <=> fully defined hypercube (see build_fused)
+    NdpBlocks B{};                           // blocked copy of a scalar table (mirrors k_build_blocks); order 0 = none
+    std::vector<double> blocks;
 };
+
+// mirrors k_build_blocks
+static void build_blocks(HsTable *t, int order)
+{
+    const NdpGeom &g = t->g;
+    const int n = g.naxes;
+    ndp_blocks_setup(g, order, t->B);
+    t->blocks.resize((size_t) (t->B.nblocks << order));
+    for (long long e = 0; e < (t->B.nblocks << order); e++) {
+        const int i = (int) (e & ((1LL << order) - 1));
+        long long blk = e >> order, vert = 0;
+        for (int a = n - 1; a >= 0; a--) {
+            const bool inner = a >= n - order;
+            const int d = inner ? g.len[a] - 1 : g.len[a];
+            int c = (int) (blk % d); blk /= d;
+            if (inner) c += (i >> (n - 1 - a)) & 1;
+            vert += (long long) c * g.vstride[a];
+        }
+        t->blocks[e] = t->grid[vert];
+    }
+}
+
+extern "C" int hs_set_block_order(void *h, int order)
+{
+    HsTable *t = (HsTable *) h;
+    if (t->g.vdim != 1 || order < 1 || order > t->g.naxes) return 0;
+    build_blocks(t, order);
+    return 1;
+}
 
 static void set_bit(std::vector<uint32_t> &b, long long i) { b[i >> 5] |= 1u << (i & 31); }
 
@@ -397,8 +428,11 @@ static void ndpolate_n(HsTable *t, long long nq, const double *q, int method, in
 template <int N, int METHOD, int MODE>
 static void fused_n(HsTable *t, long long nq, const double *q, int search, double *interps, double *dists)
 {
-    const NdpGeom &g = t->g;
+    NdpGeom g = t->g;
     const NdpSiteMap &M = t->nsm[nsm_geo_of_mode(MODE)];
+    const bool blocked = t->B.order > 0;
+    if (blocked)        // mirrors launch_fused: the plan's cell number is a block number
+        for (int a = 0; a < g.naxes; a++) { g.cstride[a] = t->B.stride[a]; g.cstride32[a] = g.small ? (int) t->B.stride[a] : 0; }
     for (long long i = 0; i < nq; i++) {
         int idx[N], flg[N]; double nrm[N];
         ndp_import_query<N>(g, t->ticks.data(), q + i * N, idx, flg, nrm);
@@ -407,7 +441,14 @@ static void fused_n(HsTable *t, long long nq, const double *q, int search, doubl
         switch (P.kind) {
         case NDP_PLAN_GATHER: {
             bool bad;
-            const double2 *b2 = reinterpret_cast<const double2 *>(t->cells.data() + (P.cell << N));
+            double2 image[1 << (N - 1)];             // the cell as k_fused's copy sweeps assemble it in shared memory
+            const double2 *b2 = image;
+            if (blocked) {
+                for (int s = 0; s < (1 << (N - 1)); s++) {
+                    const long long off = P.cell * ((long long) 8 << t->B.order) + ndp_block_piece_offset(N, t->B.order, t->B.stride, s);
+                    std::memcpy(&image[s], reinterpret_cast<const char *>(t->blocks.data()) + off, 16);
+                }
+            } else b2 = reinterpret_cast<const double2 *>(t->cells.data() + (P.cell << N));
             interps[i] = ndp_cell_reduce_halves<N>(b2, P.x, P.pin, P.sel, bad);
             dists[i] = P.dist;
             t->n_mapped += (P.dist != 0.0);

@@ -169,3 +169,20 @@ def test_fused_plan_on_baseline_mixes(spec):
             assert_same_bits(a[1], b[1], f'dists {m}/{s}')
     st = H.stats()
     assert st['slow'] < 1e-3 * st['mapped']
+
+
+@pytest.mark.parametrize('case', [c for c in build_cases(seed=3) if c[0] in ('holed3d', '4d', '5d_corner_void', '2basic_2assoc_v1')],
+                         ids=lambda c: c[0])
+def test_blocked_layout_gives_the_same_cells(case):
+    """Every block order of the blocked grid copy (2^K corners per contiguous block, K = 1 .. naxes; K = naxes is the
+    cell-major copy) assembles the same cell image, hence the same bits as the oracle."""
+    from hostsim.driver import HostSim
+    name, axes, nbasic, grid = case
+    q = adversarial_queries(axes, 1200, np.random.default_rng(41))
+    O, H = Oracle('port', axes, grid, nbasic), HostSim(axes, grid, nbasic)
+    want = O.ndpolate(q, 2, 0)
+    for order in range(1, len(axes) + 1):
+        assert H.set_block_order(order) == 1
+        got = H.ndpolate_fused(q, 2, 0)
+        assert_same_bits(want[0], got[0], f'interps, block order {order}')
+        assert_same_bits(want[1], got[1], f'dists, block order {order}')

@@ -377,3 +377,24 @@ def test_device_resident_cache_path(case):
     got = ndp.ndpolate_cached('t', fo[2], fo[0], fo[1], extrapolation_method='linear')
     assert isinstance(got['interps'], np.ndarray)
     assert_same_bits(O.ndpolate(q, 2, 0)[0], got['interps'], 'cached interps from host arrays')
+
+
+@pytest.mark.parametrize('case', [c for c in build_cases(seed=21) if c[0] in ('holed3d', '4d', '5d_corner_void', '2basic_2assoc_v1')],
+                         ids=lambda c: c[0])
+def test_blocked_copy_every_order(case):
+    """The blocked grid copy k_fused gathers from (2^K corners per contiguous block; K = naxes is the cell-major
+    copy, smaller K serves tables whose full copy would not fit): every order gives the oracle's bits."""
+    name, axes, nbasic, grid = case
+    q = adversarial_queries(axes, 20000, np.random.default_rng(99))
+    O = Oracle('port', axes, grid, nbasic)
+    want = {m: O.ndpolate(q, m, 0) for m in (0, 1, 2)}
+    T = _table(axes, grid, nbasic)
+    for order in range(1, len(axes) + 1):
+        T.set_option('block_order', order)
+        assert T.stat('block_order') == order and T.stat('cellmajor') == (1 if order == len(axes) else 0)
+        for m in (0, 1, 2):
+            got = T.ndpolate(q, m, 0)
+            assert T.stat('fused') == 1
+            assert_same_bits(want[m][0], got[0], f'interps, method {m}, block order {order}')
+            assert_same_bits(want[m][1], got[1], f'dists, method {m}, block order {order}')
+    T.close()
