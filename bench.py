@@ -37,6 +37,9 @@ def parse():
     ap.add_argument('--workload', default='C4')
     ap.add_argument('--scale', type=int, default=None, help='ticks per axis (default: the size BASELINE.json names)')
     ap.add_argument('--mix', default='near', choices=['near', 'deep'])
+    ap.add_argument('--spacing', type=float, default=None,
+                    help='tick spacing of the synthetic axes (default: 1, the integers); e.g. 0.3 exercises the general '
+                         'index search with IEEE divisions instead of the exact power-of-two-spacing multiply')
     ap.add_argument('--method', default=None, choices=[None, 'none', 'nearest', 'linear'])
     ap.add_argument('--search', default='kdtree', choices=['kdtree', 'linear'])
     ap.add_argument('--total', type=int, default=None,
@@ -51,6 +54,11 @@ def parse():
                     help='ticks per axis of the grid the CPU reference is timed on (default: 24 for C4 -- BASELINE.md 4.5 -- else full size)')
     ap.add_argument('--cpu-queries', type=int, default=20000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--api-mode', default='auto', choices=['auto', 'sync', 'async'],
+                    help="device-resident timed steps: 'sync' = every call returns with its results complete (the reference's "
+                         "semantics), 'async' = stream-ordered calls (table option async=1) and ONE ndpb_table_sync after the K "
+                         "steps, inside the timed region; auto = async for steps of at most 2^24 queries per GPU, where the "
+                         "per-call host round trip is a visible share of the step")
     ap.add_argument('--inprocess', action='store_true',
                     help='ONE process, --gpus N devices through ndpb_group (one ndpolate call split over N GPUs): end-to-end '
                          'from pinned host arrays only; launch with plain python, not torchrun')
@@ -167,7 +175,7 @@ def cpu_reference_run(args, steps, warmup):
     from oracle import oracle as orc
     kind = 'reference' if orc.have('reference') else 'port'
     scale = cpu_scale_of(args)
-    w = synth.workload(args.workload, scale, mix=args.mix, n_queries=args.cpu_queries)
+    w = synth.workload(args.workload, scale, mix=args.mix, n_queries=args.cpu_queries, spacing=args.spacing)
     method = METHODS[args.method or w.method]
     search = SEARCHES[args.search]
     cores = os.cpu_count() or 1
@@ -206,7 +214,7 @@ def cpu_reference_run(args, steps, warmup):
     finally:
         _POOL_STATE = None
     grid_txt = 'x'.join(str(len(a)) for a in w.axes)
-    full = synth.workload(args.workload, args.scale, mix=args.mix)
+    full = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing)
     subst = ('' if len(full.axes[0]) == len(w.axes[0]) else
              f' -- SUBSTITUTED for the {"x".join(str(len(a)) for a in full.axes)} grid, whose reference kd-tree takes ~12 min '
              f'and ~8 GB per process to build (BASELINE.md 4.5)')
@@ -247,7 +255,7 @@ def run_reference(args):
 
 
 def default_total(w):
-    return {'C1': 10**6, 'C2': 10**7, 'C3': 10**8, 'C4': 10**9, 'C5': 10**8}[w.name.split('@')[0]]
+    return {'C1': 10**6, 'C2': 10**7, 'C3': 10**8, 'C4': 10**9, 'C5': 10**8}[w.name.split('@')[0].split('/')[0]]
 
 
 def batch_of(args, w, ws):
@@ -261,7 +269,7 @@ def batch_of(args, w, ws):
 
 def workload_config(args):
     from ndpolator_b200 import synth
-    w = synth.workload(args.workload, args.scale, mix=args.mix)
+    w = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing)
     B, scaling = batch_of(args, w, max(1, args.gpus))
     nbuf = 1 if B * w.naxes * 8 >= (1 << 30) else 2
     return {
@@ -335,7 +343,7 @@ def run_b200(args):
     if ws > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    w = synth.workload(args.workload, args.scale, mix=args.mix)
+    w = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing)
     method = METHODS[args.method or w.method]
     search = SEARCHES[args.search]
     B, scaling = batch_of(args, w, ws)
@@ -370,28 +378,51 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_async = args.api_mode == 'async' or (args.api_mode == 'auto' and B <= (1 << 24))
     torch.cuda.synchronize()
     t_cold = time.perf_counter()
     T.ndpolate(qs[0][:min(B, 1 << 20)], method, search)      # cold first call: lazy nearest-site map / topology builds
     torch.cuda.synchronize()
     cold_s = time.perf_counter() - t_cold
+    if use_async:
+        T.set_option('async', 1)
+        T.ndpolate(qs[0][:min(B, 1 << 20)], method, search)  # builds the kd topology the stream-ordered mode needs
+        T.sync()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                                        # before the warm-up, so that short runs are sampled too
-    for s in range(W):
-        T.ndpolate(qs[s % nbuf], method, search, out=(interps, dists))
+    with torch.cuda.stream(stream):
+        for s in range(W):
+            T.ndpolate(qs[s % nbuf], method, search, out=(interps, dists))
+        T.sync()
 
     keys = ('launches', 'offgrid', 'hard', 'ties', 'slow', 'fused', 'main_ns', 'search_ns', 'finish_ns')
     acc = dict.fromkeys(keys, 0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for s in range(K):
-        T.ndpolate(qs[s % nbuf], method, search, out=(interps, dists))
-        for k in keys:
-            acc[k] += T.stat(k)
-    e1.record(stream)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for s in range(K):
+            T.ndpolate(qs[s % nbuf], method, search, out=(interps, dists))
+            if not use_async:
+                for k in keys:
+                    acc[k] += T.stat(k)
+        if use_async:
+            T.sync()                                           # completes the K stream-ordered calls, inside the timed region
+        e1.record(stream)
     barrier()
+    if use_async:
+        # per-step counters and phase times of the same steps, replayed call by call after the timed region
+        with torch.cuda.stream(stream):
+            per_buf = []
+            for b in range(nbuf):
+                T.ndpolate(qs[b], method, search, out=(interps, dists))
+                T.sync()
+                per_buf.append({k: T.stat(k) for k in keys})
+        for s in range(K):
+            for k in keys:
+                acc[k] += per_buf[s % nbuf][k]
+        T.set_option('async', 0)
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if ws > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -399,8 +430,9 @@ def run_b200(args):
     if rank == 0 and ms_total < 400.0:
         # a short timed region: keep the GPU busy with the same work until the sampler has seen it under load
         t_keep = time.perf_counter()
-        while time.perf_counter() - t_keep < 0.5:
-            T.ndpolate(qs[0], method, search, out=(interps, dists))
+        with torch.cuda.stream(stream):
+            while time.perf_counter() - t_keep < 0.5:
+                T.ndpolate(qs[0], method, search, out=(interps, dists))
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
@@ -505,6 +537,9 @@ def run_b200(args):
                              'needed_lattice_descent': acc['hard'] / (B * K), 'kd_ties': acc['ties'],
                              'left_to_exact_generic_kernel': acc['slow'] / (B * K)},
             'path': 'fused (k_fused + k_slow)' if fused else 'three-pass (gather, search, finish)',
+            'api_mode': ('async: K stream-ordered ndpolate calls on device tensors + one ndpb_table_sync, all inside the timed '
+                         'region; counters / phase times from a call-by-call replay after it' if use_async else
+                         'sync: every ndpolate call returns with its results complete'),
             'table': {'cellmajor': bool(T.stat('cellmajor')), 'build_s': build_s, 'cold_first_call_s': cold_s,
                       'note': 'build_s: upload + masks + pyramids + cell-major copy; cold_first_call_s: first ndpolate of 2^20 '
                               'queries incl. the lazy nearest-site map (the reference builds its kd-tree there)'},
@@ -547,7 +582,7 @@ def run_inprocess(args):
     from ndpolator_b200 import synth
     from ndpolator_b200.cndpolator import Group, Table
     n_dev = args.gpus
-    w = synth.workload(args.workload, args.scale, mix=args.mix)
+    w = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing)
     method = METHODS[args.method or w.method]
     search = SEARCHES[args.search]
     policy = interleave_host_memory()

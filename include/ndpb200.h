@@ -125,6 +125,17 @@ int ndpb_table_tree_topology(ndpb_table *t, int method, int32_t *parent, int32_t
  * code, src/ndp_py.c:343-409; this is the price of accepting device pointers.) */
 int ndpb_table_wait_stream(ndpb_table *t, uint64_t producer_stream);
 
+/* Stream-ordered calls.  By default every entry point returns when its results are complete -- the reference's
+ * semantics (synchronous host code, src/ndp_py.c:343-409).  With option "async" = 1, ndpb_ndpolate /
+ * ndpb_find_nearest / ndpb_distance calls whose buffers are ALL device-resident (and hold at most 2^30 queries)
+ * only enqueue their kernels on the table's compute stream (option "stream": the caller's own stream) and
+ * return; results are complete in stream order, like any CUDA library call.  The one host decision of the
+ * synchronous path (building the reference-shaped kd topology the first time an exact distance tie is met) is
+ * taken ahead of time: the first async call of a kd-search extrapolating method builds that topology
+ * (8 bytes per basic vertex and method).  ndpb_table_sync waits for the compute stream and folds the counters
+ * of the last call into ndpb_table_stat.  Calls with host buffers are unaffected.  Results are identical. */
+int ndpb_table_sync(ndpb_table *t);
+
 /* Tuning knobs that never change results.  Keys: "gather" = 0 auto | 1 strided
  * (original layout) | 2 cell-major; "linear_search" = 0 auto | 1 brute force |
  * 2 lattice; "chunk" = queries per staged chunk for host buffers; "block_order" = 0 auto | K: blocked copy of a scalar table with 2^K corners per
@@ -133,6 +144,8 @@ int ndpb_table_wait_stream(ndpb_table *t, uint64_t producer_stream);
  * fused kernel (import + mask/nearest-site-map plan + one cell gather per query); "staged" = 0 auto: one-stage
  * cp.async gather, 4 CTAs/SM | 1 never use the staged gather kernels | 2 two-stage ring | 3 one stage,
  * 5 CTAs/SM (only used when the fused kernel is off or does not apply);
+ * "nsm_subcells" = 1 | 2 | 4 | 8 | 16 (default; the largest that keeps a map under 2^21 regions is used): sub-cells per unit cell of the nearest-site maps (finer maps hold
+ * fewer candidates per region and are larger; rebuilt lazily); "async" = 0 | 1, see ndpb_table_sync;
  * "search_fast_blocks_per_sm" / "search_hard_blocks_per_sm" =
  * grid-stride CTAs per SM of the two search passes (default 64 / 256); "stream" = a
  * cudaStream_t (as integer) to launch the kernels on instead of the table's own

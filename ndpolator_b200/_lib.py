@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get('NDPB_LIB') or os.path.join(HERE, 'libndpb200.so')
 SYMBOLS = [
     'ndpb_table_create', 'ndpb_table_destroy', 'ndpb_find', 'ndpb_hypercubes', 'ndpb_find_nearest',
     'ndpb_ndpolate', 'ndpb_ndpolate_cached', 'ndpb_distance', 'ndpb_table_nverts', 'ndpb_table_masks', 'ndpb_table_tree_topology',
-    'ndpb_table_set_option', 'ndpb_table_stat', 'ndpb_table_wait_stream', 'ndpb_last_error', 'ndpb_version',
+    'ndpb_table_set_option', 'ndpb_table_stat', 'ndpb_table_wait_stream', 'ndpb_table_sync', 'ndpb_last_error', 'ndpb_version',
     'ndpb_group_create', 'ndpb_group_destroy', 'ndpb_group_size', 'ndpb_group_table', 'ndpb_group_ndpolate',
     'ndpb_group_distance', 'ndpb_group_set_option', 'ndpb_group_stat',
 ]
@@ -68,6 +68,8 @@ def lib():
     L.ndpb_table_set_option.argtypes = [_vp, C.c_char_p, C.c_int64]
     L.ndpb_table_wait_stream.restype = C.c_int
     L.ndpb_table_wait_stream.argtypes = [_vp, C.c_uint64]
+    L.ndpb_table_sync.restype = C.c_int
+    L.ndpb_table_sync.argtypes = [_vp]
     L.ndpb_table_stat.restype = C.c_int64
     L.ndpb_table_stat.argtypes = [_vp, C.c_char_p]
     L.ndpb_group_create.restype = C.c_int

@@ -128,6 +128,11 @@ class Table:
     def stat(self, key: str) -> int:
         return int(_lib.lib().ndpb_table_stat(self._h, key.encode()))
 
+    def sync(self):
+        """Completes stream-ordered calls (set_option('async', 1): calls on device tensors only enqueue their
+        kernels -- on the table's stream, or on the caller's with set_option('stream', ...) -- and return)."""
+        _lib.check(_lib.lib().ndpb_table_sync(self._h))
+
     @property
     def nverts(self) -> int:
         return int(_lib.lib().ndpb_table_nverts(self._h))

@@ -90,7 +90,7 @@ struct Slot {                               // one in-flight batch
     int *coords = nullptr;
     int *list = nullptr, *chosen = nullptr, *tielist = nullptr, *hardlist = nullptr;
     int *rec_idx = nullptr; double *rec_nrm = nullptr;             // import products of the off-grid queries
-    long long cap_q = 0, cap_work = 0, cap_coords = 0;
+    long long cap_q = 0, cap_work = 0, cap_coords = 0, cap_lists = 0;
     NdpCounters *ctr = nullptr;             // device
     NdpCounters *ctr_host = nullptr;        // pinned
     cudaEvent_t in_done = nullptr, searched = nullptr, out_ready = nullptr, out_done = nullptr;
@@ -125,7 +125,9 @@ struct ndpb_table {
     std::mutex mu;
     int sm_count = 148;
     // options
-    int opt_gather = 0, opt_linear_search = 0, opt_staged = 0, opt_fused = 0, opt_block_order = 0;
+    int opt_gather = 0, opt_linear_search = 0, opt_staged = 0, opt_fused = 0, opt_block_order = 0, opt_nsm_subcells = 16;
+    int opt_async = 0;                      // 1: device-resident calls only enqueue (ndpb_table_sync completes them)
+    bool async_pending = false;             // an enqueued call whose counters have not been folded into the stats yet
     long long opt_chunk = 1 << 20;          // profiles/r01p_sweep_chunk.txt: 1 Mi beats 2, 4 and 8 Mi end to end
     int opt_fast_blocks = 64, opt_hard_blocks = 256;   // grid-stride CTAs per SM of the two search passes (profiles/r01p_sweep_search.txt)
     // stats of the last call
@@ -364,7 +366,7 @@ static int ensure_nsm(ndpb_table *t, int geo)
     if (t->nsm_tried[geo]) return NDPB_OK;
     t->nsm_tried[geo] = true;
     NdpSiteMap M;
-    nsm_setup(t->g, t->red[geo == NSM_GEO_VERTEX ? 0 : 1].dev, geo, M);
+    nsm_setup(t->g, t->red[geo == NSM_GEO_VERTEX ? 0 : 1].dev, geo, M, t->opt_nsm_subcells);
     if (!M.valid) return NDPB_OK;
     cudaStream_t st = t->s_owned;
     int *counts = nullptr, *offs = nullptr;
@@ -526,6 +528,24 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
     if (k == "fused") {
         if (value < 0 || value > 1) return fail(NDPB_ERR_INVALID, "fused must be 0 (auto) or 1 (never use the fused kernel)");
         t->opt_fused = (int) value;
+        return NDPB_OK;
+    }
+    if (k == "nsm_subcells") {
+        if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
+            return fail(NDPB_ERR_INVALID, "nsm_subcells must be 1, 2, 4, 8 or 16");
+        CU(cudaDeviceSynchronize());
+        t->opt_nsm_subcells = (int) value;
+        for (int geo = 0; geo < 3; geo++) {          // maps are rebuilt lazily at the new resolution
+            cudaFree(t->nsm_offs[geo]); cudaFree(t->nsm_ents[geo]);
+            t->nsm_offs[geo] = nullptr; t->nsm_ents[geo] = nullptr;
+            t->nsm[geo] = NdpSiteMap{}; t->nsm_tried[geo] = false;
+        }
+        return NDPB_OK;
+    }
+    if (k == "async") {
+        if (value < 0 || value > 1) return fail(NDPB_ERR_INVALID, "async must be 0 or 1");
+        CU(cudaStreamSynchronize(t->s_compute));
+        t->opt_async = (int) value;
         return NDPB_OK;
     }
     if (k == "chunk") {
@@ -713,8 +733,10 @@ extern "C" int ndpb_table_tree_topology(ndpb_table *t, int method, int32_t *pare
 // ---------------------------------------------------------------------------
 // batches
 // ---------------------------------------------------------------------------
+// work: 0 none, 1 the fused path's lists (slow list, tie list: 8 bytes per query), 2 also the three-pass path's
+// work lists and import records (up to 84 more bytes per query with 5 axes -- only allocated when that path runs)
 static int ensure_slot(ndpb_table *t, Slot &s, long long nq, bool stage_q, bool stage_interps, bool stage_dists,
-                       bool stage_coords, bool work)
+                       bool stage_coords, int work)
 {
     const NdpGeom &g = t->g;
     if (!s.ctr) {
@@ -740,14 +762,19 @@ static int ensure_slot(ndpb_table *t, Slot &s, long long nq, bool stage_q, bool 
         CU(cudaMalloc(&s.coords, sizeof(int) * nq * g.naxes));
         s.cap_coords = nq;
     }
-    if (work && nq > s.cap_work) {
+    if (work >= 1 && nq > s.cap_lists) {
         CU(cudaStreamSynchronize(t->s_compute));
-        cudaFree(s.list); cudaFree(s.chosen); cudaFree(s.tielist); cudaFree(s.hardlist);
-        cudaFree(s.rec_idx); cudaFree(s.rec_nrm);
-        s.list = s.chosen = s.tielist = s.hardlist = s.rec_idx = nullptr; s.rec_nrm = nullptr; s.cap_work = 0;
+        cudaFree(s.list); cudaFree(s.tielist);
+        s.list = s.tielist = nullptr; s.cap_lists = 0;
         CU(cudaMalloc(&s.list, sizeof(int) * nq));
-        CU(cudaMalloc(&s.chosen, sizeof(int) * nq));
         CU(cudaMalloc(&s.tielist, sizeof(int) * nq));
+        s.cap_lists = nq;
+    }
+    if (work >= 2 && nq > s.cap_work) {
+        CU(cudaStreamSynchronize(t->s_compute));
+        cudaFree(s.chosen); cudaFree(s.hardlist); cudaFree(s.rec_idx); cudaFree(s.rec_nrm);
+        s.chosen = s.hardlist = s.rec_idx = nullptr; s.rec_nrm = nullptr; s.cap_work = 0;
+        CU(cudaMalloc(&s.chosen, sizeof(int) * nq));
         CU(cudaMalloc(&s.hardlist, sizeof(int) * nq));
         CU(cudaMalloc(&s.rec_idx, sizeof(int) * nq * g.naxes));
         CU(cudaMalloc(&s.rec_nrm, sizeof(double) * nq * g.naxes));
@@ -847,7 +874,7 @@ static bool fused_ok(ndpb_table *t, int method, int search)
     if (t->g.vdim == 1 && !t->blocks) return false;     // scalar tables gather from the blocked copy, vector tables from the grid
     if ((size_t) t->nticks * sizeof(double) > 16 * 1024) return false;
     if (method == NDPB_METHOD_NONE) return true;
-    if (use_brute(t, search)) return false;
+    if (search == NDPB_SEARCH_LINEAR && t->opt_linear_search == 1) return false;    // the literal scan was asked for
     const int geo = nsm_geo_of_mode(ndp_mode_of(method, search));
     if (ensure_nsm(t, geo) != NDPB_OK) return false;
     return t->nsm[geo].valid != 0;
@@ -1037,6 +1064,7 @@ static void reset_stats(ndpb_table *t)
 {
     t->st_launches = t->st_offgrid = t->st_hard = t->st_ties = t->st_h2d = t->st_d2h = t->st_slow = t->st_fused = 0;
     t->st_main_ms = t->st_search_ms = t->st_finish_ms = 0;
+    t->async_pending = false;
 }
 
 // Drives one API call: device-resident callers run as one batch per 2^30 queries;
@@ -1075,11 +1103,29 @@ static int run_call_inner(ndpb_table *t, Task task, const double *q, long long n
     const long long chunk = all_dev ? (1LL << 30) : t->opt_chunk;
     const long long nchunks = (n + chunk - 1) / chunk;
     const bool need_dists = true;     // the search always writes distances
+    const int work_level = (task == TASK_NDPOLATE && fused_ok(t, method, search)) ? 1 : 2;
+
+    if (t->opt_async && all_dev && nchunks == 1 && dists && (task != TASK_NEAREST || coords)) {
+        // Stream-ordered call: everything is enqueued on the compute stream and the call returns.  The one host
+        // decision of the synchronous path -- building the reference-shaped kd topology when an exact distance
+        // tie turns up -- is taken ahead of time: with the topology in place the kernels settle ties themselves.
+        Slot &s = t->slot[0];
+        int rc = ensure_slot(t, s, n, false, false, false, false, work_level);
+        if (rc) return rc;
+        if (method != NDPB_METHOD_NONE && search == NDPB_SEARCH_KDTREE) {
+            rc = ensure_topology(t, method == NDPB_METHOD_LINEAR ? 1 : 0);
+            if (rc) return rc;
+        }
+        rc = batch_enqueue(t, s, task, q, n, method, search, interps, dists, coords);
+        if (rc) return rc;
+        t->async_pending = true;
+        return NDPB_OK;
+    }
 
     auto stage_in = [&](long long c) -> int {
         Slot &s = t->slot[c & 1];
         const long long lo = c * chunk, cnt = std::min(chunk, n - lo);
-        int rc = ensure_slot(t, s, cnt, !q_dev || !i_dev || !d_dev, false, false, coords && !c_dev, true);
+        int rc = ensure_slot(t, s, cnt, !q_dev || !i_dev || !d_dev, false, false, coords && !c_dev, work_level);
         if (rc) return rc;
         if (!q_dev) {
             if (s.used) CU(cudaStreamWaitEvent(t->s_in, s.out_done, 0));   // slot's previous results are out
@@ -1099,7 +1145,7 @@ static int run_call_inner(ndpb_table *t, Task task, const double *q, long long n
         double *id = !interps ? nullptr : (i_dev ? interps + lo * g.vdim : s.interps);
         double *dd = (dists && d_dev) ? dists + lo : s.dists;
         int *cd = !coords ? nullptr : (c_dev ? coords + lo * g.naxes : s.coords);
-        if (!dd) { rc = ensure_slot(t, s, cnt, true, false, false, false, true); if (rc) return rc; dd = s.dists; }
+        if (!dd) { rc = ensure_slot(t, s, cnt, true, false, false, false, work_level); if (rc) return rc; dd = s.dists; }
         if (!q_dev) CU(cudaStreamWaitEvent(t->s_compute, s.in_done, 0));
         if (s.used) CU(cudaStreamWaitEvent(t->s_compute, s.out_done, 0));
         rc = batch_enqueue(t, s, task, qd, cnt, method, search, id, dd, cd);
@@ -1124,6 +1170,34 @@ static int run_call_inner(ndpb_table *t, Task task, const double *q, long long n
     }
     CU(cudaStreamSynchronize(t->s_compute));
     CU(cudaStreamSynchronize(t->s_out));
+    return NDPB_OK;
+}
+
+// Folds the counters of the last stream-ordered call into the stats (the stream has been drained).
+static void fold_async(ndpb_table *t)
+{
+    if (!t->async_pending) return;
+    t->async_pending = false;
+    Slot &s = t->slot[0];
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.t0, s.t1) == cudaSuccess) t->st_main_ms += ms;
+    if (cudaEventElapsedTime(&ms, s.t1, s.t2) == cudaSuccess) t->st_search_ms += ms;
+    if (cudaEventElapsedTime(&ms, s.t2, s.t3) == cudaSuccess) t->st_finish_ms += ms;
+    cudaGetLastError();
+    const NdpCounters c = *s.ctr_host;
+    t->st_offgrid += c.n_off;
+    t->st_hard += c.n_hard;
+    t->st_slow += c.n_slow;
+    t->st_ties += c.n_tie_resolved;
+}
+
+extern "C" int ndpb_table_sync(ndpb_table *t)
+{
+    if (!t) return fail(NDPB_ERR_INVALID, "table is NULL");
+    std::lock_guard<std::mutex> lk(t->mu);
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->s_compute));
+    fold_async(t);
     return NDPB_OK;
 }
 
@@ -1392,7 +1466,7 @@ extern "C" int ndpb_ndpolate_cached(ndpb_table *t, const double *normed, const i
     if ((rc = nrm.in(normed, e)) || (rc = idx.in(indices, e)) || (rc = flg.in(flags, e)) ||
         (rc = out_i.out(interps, (size_t) n * t->g.vdim)) || (rc = out_d.out(dists, (size_t) n))) return rc;
     Slot &s = t->slot[0];
-    rc = ensure_slot(t, s, n, false, false, false, false, true);
+    rc = ensure_slot(t, s, n, false, false, false, false, 1);
     if (rc) return rc;
     cudaStream_t st = t->s_compute;
     const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;

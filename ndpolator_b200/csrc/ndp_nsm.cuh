@@ -75,7 +75,7 @@ struct NdpSiteMap {
 // Fills the geometry of a map over the variant axes of reduced pyramid R (mask slice R.bits[0]);
 // offs / ents are attached by the caller once the regions have been counted.  valid = 0 when the
 // mask spans too many variant axes or regions (such tables keep the lattice search).
-inline void nsm_setup(const NdpGeom &g, const NdpPyramid &R, int geo, NdpSiteMap &M)
+inline void nsm_setup(const NdpGeom &g, const NdpPyramid &R, int geo, NdpSiteMap &M, int max_subcells = 16)
 {
     M = NdpSiteMap{};
     M.geo = geo;
@@ -91,7 +91,7 @@ inline void nsm_setup(const NdpGeom &g, const NdpPyramid &R, int geo, NdpSiteMap
         M.vlen[j] = g.len[R.var_axis[j]];
         M.sstride[j] = R.stride[0][j];
     }
-    for (int S = 4; S >= 1; S >>= 1) {
+    for (int S = max_subcells; S >= 1; S >>= 1) {
         long long total = 1;
         for (int j = 0; j < R.nvar; j++) total *= 2 * NSM_BANDS + (long long) S * (M.vlen[j] - 1);
         if (total > NSM_MAX_REGIONS) continue;

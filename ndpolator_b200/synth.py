@@ -90,13 +90,13 @@ class Workload:
     # -- table -----------------------------------------------------------------
     def grid(self, device=None):
         """The (len..., vdim) float64 grid, NaN on void vertices (component 0..vdim-1 all NaN)."""
-        builder = _GRIDS[self.name.split('@')[0]]
+        builder = _GRIDS[self.name.split('@')[0].split('/')[0]]
         return builder(self, device)
 
     # -- queries ---------------------------------------------------------------
     def queries(self, first: int, count: int, device=None):
         """Rows [first, first+count) of the (n_queries, naxes) batch."""
-        gen = _QUERIES[self.name.split('@')[0]]
+        gen = _QUERIES[self.name.split('@')[0].split('/')[0]]
         return gen(self, first, count, device)
 
 
@@ -279,10 +279,20 @@ _GRIDS = {'C1': _grid_sum, 'C2': _grid_sum, 'C3': _grid_random, 'C4': _grid_rand
 _QUERIES = {'C1': _q_box, 'C2': _q_box, 'C3': _q_corner, 'C4': _q_corner, 'C5': _q_mixed}
 
 
-def workload(name: str, scale: int | None = None, mix: str = 'near', n_queries: int | None = None) -> Workload:
+def workload(name: str, scale: int | None = None, mix: str = 'near', n_queries: int | None = None,
+             spacing: float | None = None) -> Workload:
     """name in {'C1','C2','C3','C4','C5'}.  `scale` shrinks the per-axis tick count for
-    tests (None = the size BASELINE.json names); the generated name records it ('C4@12')."""
+    tests (None = the size BASELINE.json names); the generated name records it ('C4@12').
+    `spacing` (C2, C4, C5): ticks 1.7 + spacing * i instead of the integers 0..L-1 -- a spacing that is not a
+    power of two takes the kernels' general index search (IEEE division) instead of the exact-multiply one."""
     tag = name if scale is None else f'{name}@{scale}'
+    if spacing is not None:
+        w = workload(name, scale, mix, n_queries)
+        if name not in ('C2', 'C4', 'C5'):
+            raise ValueError('spacing applies to C2, C4 and C5')
+        w.basic_axes = tuple(1.7 + spacing * np.arange(len(a), dtype=np.float64) for a in w.basic_axes)
+        w.name = f'{w.name}/dx{spacing:g}'
+        return w
     if name == 'C1':
         # README 3-D 5x5x5 linear scalar field, fully populated (reference README.md:100-127)
         ax = (np.linspace(1, 5, 5), np.linspace(10, 50, 5), np.linspace(100, 500, 5))

@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 #include <numeric>
@@ -159,7 +160,10 @@ static void build_fused(HsTable *t)
     for (int geo = 0; geo < 3; geo++) {
         const int m = geo == NSM_GEO_VERTEX ? 0 : 1;
         NdpSiteMap &M = t->nsm[geo];
-        nsm_setup(g, t->red[m].dev, geo, M);
+        // sub-cells per unit cell: 4 keeps the host-side map build of the CPU suite short; NDPB_HOSTSIM_NSM_S=16
+        // (the shipped default) is exercised by one test
+        const char *s_env = getenv("NDPB_HOSTSIM_NSM_S");
+        nsm_setup(g, t->red[m].dev, geo, M, s_env ? atoi(s_env) : 4);
         if (!M.valid) continue;
         std::vector<unsigned long long> cand(NSM_KMAX);
         std::vector<int> &offs = t->nsm_offs[geo];

@@ -171,6 +171,24 @@ def test_fused_plan_on_baseline_mixes(spec):
     assert st['slow'] < 1e-3 * st['mapped']
 
 
+def test_fused_plan_with_the_finest_site_map(monkeypatch):
+    """16 sub-cells per unit cell (the library's default resolution of the nearest-site maps; the rest of this
+    suite builds them at 4 to keep the host-side build short): same bits."""
+    from hostsim.driver import HostSim
+    from ndpolator_b200 import synth
+    monkeypatch.setenv('NDPB_HOSTSIM_NSM_S', '16')
+    w = synth.workload('C4', 10, mix='near', n_queries=40000)
+    grid, q = w.grid(), w.queries(0, 40000)
+    O, H = Oracle('port', w.axes, grid, 5), HostSim(w.axes, grid, 5)
+    assert H.nsm_info()[1]['S'] == 16
+    for m in (1, 2):
+        a, b = O.ndpolate(q, m, 0, threads=4), H.ndpolate_fused(q, m, 0)
+        assert_same_bits(a[0], b[0], f'interps {m}')
+        assert_same_bits(a[1], b[1], f'dists {m}')
+    st = H.stats()
+    assert st['slow'] < 1e-3 * st['mapped']
+
+
 @pytest.mark.parametrize('case', [c for c in build_cases(seed=3) if c[0] in ('holed3d', '4d', '5d_corner_void', '2basic_2assoc_v1')],
                          ids=lambda c: c[0])
 def test_blocked_layout_gives_the_same_cells(case):

@@ -181,6 +181,51 @@ def test_tie_pass_runs_before_topology_exists():
     T.close()
 
 
+@pytest.mark.parametrize('fused_off', [0, 1], ids=['fused', 'two-pass'])
+def test_stream_ordered_calls_async_option(fused_off):
+    """set_option('async', 1): calls on device tensors only enqueue (ndpb_table_sync completes them); exact kd
+    distance ties are settled inside the kernels because the topology is built ahead of the first such call.
+    Several calls in flight on the caller's stream, distinct outputs, identical bits to the oracle."""
+    import torch
+    name, axes, nbasic, grid = build_cases()[1]
+    rng = np.random.default_rng(5)
+    mids = [(a[1:] + a[:-1]) / 2 for a in axes]
+    ties = np.stack([rng.choice(m, 3000) for m in mids], axis=1) + np.array([7.0, 0, 0])
+    q = np.concatenate([adversarial_queries(axes, 20000, np.random.default_rng(17)), ties])
+    O = Oracle('port', axes, grid, nbasic)
+    T = _table(axes, grid, nbasic, fused=fused_off)
+    stream = torch.cuda.Stream()
+    T.set_option('stream', stream.cuda_stream)
+    T.set_option('async', 1)
+    with torch.cuda.stream(stream):
+        qd = torch.as_tensor(q, device='cuda')
+        outs = {}
+        for rep in range(2):
+            for m in (0, 1, 2):
+                for sr in (0, 1):
+                    outs[(rep, m, sr)] = T.ndpolate(qd, m, sr)          # returns at once; nothing is read back here
+        near = {(m, sr): T.find_nearest(qd, m, sr) for m in (1, 2) for sr in (0, 1)}
+        dist = T.distance(qd)
+    T.sync()
+    assert T.stat('launches') > 0
+    fo = O.find(q)
+    for (rep, m, sr), (gi, gd) in outs.items():
+        want = O.ndpolate(q, m, sr)
+        assert_same_bits(want[0], gi.cpu().numpy(), f'async interps {m}/{sr} rep {rep}')
+        assert_same_bits(want[1], gd.cpu().numpy(), f'async dists {m}/{sr} rep {rep}')
+    for (m, sr), (gc, gd) in near.items():
+        want = O.find_nearest(*fo, m, sr)
+        assert_same_bits(want[0], gc.cpu().numpy(), f'async coords {m}/{sr}')
+        assert_same_bits(want[1], gd.cpu().numpy(), f'async ndist {m}/{sr}')
+    assert_same_bits(O.distance(q), dist.cpu().numpy(), 'async distance')
+    # host buffers stay synchronous in async mode
+    hi, hd = T.ndpolate(q, 2, 0)
+    assert_same_bits(O.ndpolate(q, 2, 0)[0], hi, 'host call in async mode')
+    T.set_option('async', 0)
+    T.set_option('stream', 0)
+    T.close()
+
+
 def test_host_chunking_device_tensors_and_search_variants_agree():
     import torch
     name, axes, nbasic, grid = build_cases()[7]          # 5-D with a structured void
