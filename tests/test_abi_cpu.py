@@ -74,3 +74,19 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle', text, flags=re.M), f
                 assert 'libndp_oracle' not in text and 'libndp_ref' not in text and 'libhostsim' not in text, f
+
+
+def test_packaging_builds_and_ships_the_library(tmp_path):
+    """pyproject.toml / setup.py (reference setup.py:4-21): build_py compiles the CUDA library through
+    ndpolator_b200/build.py and the built package carries libndpb200.so, the ctypes mirror and the API class."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / 'lib'
+    res = subprocess.run([sys.executable, 'setup.py', '-q', 'build_py', '--build-lib', str(out)], cwd=root,
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    pkg = out / 'ndpolator_b200'
+    for name in ('libndpb200.so', 'cndpolator.py', 'ndpolator.py', '_lib.py', 'build.py'):
+        assert (pkg / name).exists(), f'{name} missing from the built package'
+    assert (pkg / 'csrc' / 'ndp_api.cu').exists()
