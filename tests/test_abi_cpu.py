@@ -83,7 +83,7 @@ def test_packaging_builds_and_ships_the_library(tmp_path):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = tmp_path / 'lib'
-    res = subprocess.run([sys.executable, 'setup.py', '-q', 'build_py', '--build-lib', str(out)], cwd=root,
+    res = subprocess.run([sys.executable, 'setup.py', '-q', 'egg_info', '--egg-base', str(tmp_path), 'build_py', '--build-lib', str(out)], cwd=root,
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-2000:]
     pkg = out / 'ndpolator_b200'
