@@ -918,7 +918,7 @@ static int launch_fused(ndpb_table *t, Slot &s, const double *q, long long n, in
 }
 
 // k_slow over a device list of query ids: the slow list of the fused kernel, or (tie == true) the tie list
-static int launch_slow(ndpb_table *t, Slot &s, const double *q, int method, int search, double *interps, double *dists,
+static int launch_slow(ndpb_table *t, Slot &s, const double *q, long long n, int method, int search, double *interps, double *dists,
                        bool tie, cudaStream_t st)
 {
     const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;
@@ -932,7 +932,8 @@ static int launch_slow(ndpb_table *t, Slot &s, const double *q, int method, int 
     A.count = tie ? &s.ctr->n_tie : &s.ctr->n_slow;
     A.count_host = 0; A.c_idx = nullptr; A.c_flg = nullptr; A.c_nrm = nullptr;
     A.interps = interps; A.dists = dists; A.tielist = s.tielist; A.count_searched = tie ? 0 : 1; A.ctr = s.ctr;
-    CU(ndp_launch_slow(A, t->sm_count * 2, smem_bytes(t), st));
+    const int blocks = (int) std::min<long long>((long long) t->sm_count * 2, (n + NDP_BLOCK - 1) / NDP_BLOCK);
+    CU(ndp_launch_slow(A, std::max(blocks, 1), smem_bytes(t), st));
     t->st_launches++;
     return NDPB_OK;
 }
@@ -949,7 +950,7 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
         int rc = launch_fused(t, s, q, n, method, search, interps, dists, st);
         if (rc) return rc;
         CU(cudaEventRecord(s.t1, st));
-        rc = launch_slow(t, s, q, method, search, interps, dists, false, st);
+        rc = launch_slow(t, s, q, n, method, search, interps, dists, false, st);
         if (rc) return rc;
         CU(cudaEventRecord(s.t2, st));
         CU(cudaEventRecord(s.t3, st));
@@ -1031,7 +1032,7 @@ static int batch_complete(ndpb_table *t, Slot &s, Task task, const double *q, lo
         const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;
         int rc = ensure_topology(t, m);
         if (rc) return rc;
-        rc = launch_slow(t, s, q, method, search, interps, dists, true, st);
+        rc = launch_slow(t, s, q, n, method, search, interps, dists, true, st);
         if (rc) return rc;
         t->st_ties += c.n_tie;
     } else if (c.n_tie > 0) {

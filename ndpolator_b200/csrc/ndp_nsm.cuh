@@ -23,7 +23,9 @@
 // expressions in its order, so among the candidates the decision is bit-exact; a
 // dropped site's true distance exceeds the winner's by more than NSM_EPS = 2^-20,
 // while all rounding errors of a total below NSM_TMAX = 2^20 stay under 2^-28, so
-// no dropped site can win or tie after rounding either.  Whatever the map cannot
+// no dropped site can win or tie after rounding either.  (On the closed-form axes the
+// same argument needs a margin of 2^-32 only while the winning total is below 2^8.)
+// Whatever the map cannot
 // settle -- exact ties in the kd modes (the reference's traversal order decides),
 // totals above NSM_TMAX, queries more than 32 cells outside the box on a variant
 // axis, NaN, a non-strict closed-form axis -- is reported as "not settled" and goes
@@ -36,6 +38,8 @@
 #define NSM_KMAX 160                // candidates a region may hold while being built
 #define NSM_EPS 0x1p-20
 #define NSM_TMAX 0x1p20
+#define NSM_EPS_NEAR 0x1p-32        // margin that is enough when the winning total stays below NSM_TNEAR: the rounding
+#define NSM_TNEAR 0x1p8             // errors of such ordered sums are below 12 * 2^-52 * 2^8 < 2^-40
 #define NSM_MAX_VAR 4               // variant axes a map may span (16-bit coordinates, 64-bit packing)
 
 #define NSM_GEO_VERTEX 0            // vmask sites at integer c            (modes KD_NEAREST, LS_NEAREST)
@@ -363,6 +367,7 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
     int fix[MM];
     int region = 0, base = 0;
     bool ok = true;
+    bool wide = true;                  // every closed-form axis has the NSM_EPS margin (else only NSM_EPS_NEAR)
 #pragma unroll
     for (int a = 0; a < MM; a++) {
         t0[a] = 0.0; fix[a] = 0;
@@ -382,9 +387,13 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
                     // (pos - q)^2 with pos = p or p - 0.5.  The neighbours at pos -+ 1 score 1 -+ 2 d0 more: a
                     // margin unless |d0| is within NSM_EPS of 1/2.  (|d0| > 1/2 only where p was clamped to the end
                     // of the axis, and then the one neighbour that exists lies on the far side.)
+                    // The margin must exceed twice the rounding error of the ordered totals the reference compares:
+                    // NSM_EPS whatever the total (< NSM_TMAX), NSM_EPS_NEAR when the winner's total is below NSM_TNEAR.
                     const double d0 = (cells ? p - 0.5 : p) - q;
                     t0[a] = d0 * d0;
-                    ok &= fabs(fabs(d0) - 0.5) > NSM_EPS;
+                    const double m = fabs(fabs(d0) - 0.5);
+                    ok &= m > NSM_EPS_NEAR;
+                    wide &= m > NSM_EPS;
                 } else {
                     const double t = ndp_axis_term(mode, q, c, c);
                     const double tm = (c - 1 >= lo) ? ndp_axis_term(mode, q, c - 1, c - 1) : 4.0 * NSM_TMAX;
@@ -434,6 +443,7 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
         }
     }
     if (tie || !(bestd < NSM_TMAX)) return false;                   // also: no candidate stored for this region
+    if (!wide && !(bestd < NSM_TNEAR)) return false;
     hit.vertex = kd ? -1 : best; hit.dsel = bestd; hit.status = NDP_SEARCH_OK; hit.hard = 0; hit.has_coords = 1;
 #pragma unroll
     for (int a = 0; a < MM; a++)

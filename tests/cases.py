@@ -144,3 +144,18 @@ class OracleNdpolator:
             raise ValueError('bad search_algorithm')
         interps, dists = self._o(name).ndpolate(query_pts, methods[extrapolation_method], searches[search_algorithm])
         return {'interps': interps} if extrapolation_method == 'none' else {'interps': interps, 'dists': dists}
+
+
+def bisector_queries(w, n, seed=77):
+    """C4-like workload `w` (mask depends on axes 0 and 1): queries a hair (2^-18 .. 2^-44, and exactly 0) away from
+    the bisector between two lattice points on the mask-invariant axes 2..4, half of them far outside on axis 0."""
+    rng = np.random.default_rng(seed)
+    q = w.queries(0, n).copy()
+    top = float(w.axes[0][-1])
+    q[:, 0] = np.where(rng.random(n) < 0.5, top + rng.random(n) * 20.0, q[:, 0])
+    eps = np.array([0.0] + [2.0 ** -k for k in (18, 20, 21, 24, 28, 31, 32, 33, 36, 40, 44)])
+    for a in (2, 3, 4):
+        pick = rng.random(n) < 0.6
+        base = rng.integers(0, int(top), n) + np.where(rng.random(n) < 0.5, 0.5, 0.0)   # vertex / cell-centre bisectors
+        q[:, a] = np.where(pick, base + rng.choice([-1.0, 1.0], n) * rng.choice(eps, n), q[:, a])
+    return q

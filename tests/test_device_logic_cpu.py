@@ -171,6 +171,28 @@ def test_fused_plan_on_baseline_mixes(spec):
     assert st['slow'] < 1e-3 * st['mapped']
 
 
+def test_site_map_margins_next_to_bisectors():
+    """Queries a hair (2^-18 .. 2^-44, and exactly 0) away from the bisector between two lattice points on the
+    mask-invariant axes: the map settles them while the margin exceeds what rounding can bridge (2^-20 for any
+    total, 2^-32 for totals below 2^8), the exact lattice search takes the rest -- the oracle's bits either way."""
+    from hostsim.driver import HostSim
+    from ndpolator_b200 import synth
+    from cases import bisector_queries
+    w = synth.workload('C4', 12, mix='near', n_queries=1)
+    grid = w.grid()
+    q = bisector_queries(w, 24000)
+    O, H = Oracle('port', w.axes, grid, 5), HostSim(w.axes, grid, 5)
+    for m in (1, 2):
+        for s in (0, 1):
+            qq = q if s == 0 else q[:3000]
+            a, b = O.ndpolate(qq, m, s, threads=4), H.ndpolate_fused(qq, m, s)
+            assert b is not None
+            assert_same_bits(a[0], b[0], f'interps {m}/{s}')
+            assert_same_bits(a[1], b[1], f'dists {m}/{s}')
+    st = H.stats()
+    assert st['mapped'] > 0 and st['slow'] > 0
+
+
 def test_fused_plan_with_the_finest_site_map(monkeypatch):
     """16 sub-cells per unit cell (the library's default resolution of the nearest-site maps; the rest of this
     suite builds them at 4 to keep the host-side build short): same bits."""

@@ -226,6 +226,26 @@ def test_stream_ordered_calls_async_option(fused_off):
     T.close()
 
 
+def test_site_map_margins_next_to_bisectors():
+    """GPU twin of the host-build test of the same name: queries 0 .. 2^-18 away from a bisector on the
+    mask-invariant axes (the map settles them down to a 2^-32 margin for totals below 2^8, the exact search the rest)."""
+    from cases import bisector_queries
+    from ndpolator_b200 import synth
+    w = synth.workload('C4', 12, mix='near', n_queries=1)
+    grid = w.grid()
+    q = bisector_queries(w, 60000)
+    O = Oracle('port', w.axes, grid, 5)
+    T = _table(w.axes, grid, 5)
+    for m in (1, 2):
+        for s in (0, 1):
+            qq = q if s == 0 else q[:3000]
+            a, b = O.ndpolate(qq, m, s, threads=os.cpu_count() or 1), T.ndpolate(qq, m, s)
+            assert T.stat('fused') == 1 and T.stat('slow') > 0
+            assert_same_bits(a[0], b[0], f'interps {m}/{s}')
+            assert_same_bits(a[1], b[1], f'dists {m}/{s}')
+    T.close()
+
+
 def test_host_chunking_device_tensors_and_search_variants_agree():
     import torch
     name, axes, nbasic, grid = build_cases()[7]          # 5-D with a structured void
