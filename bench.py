@@ -45,6 +45,9 @@ def parse():
     ap.add_argument('--total', type=int, default=None,
                     help='queries per step over ALL GPUs (default: the number BASELINE.json names for the workload, 10^9 for C4)')
     ap.add_argument('--batch', type=int, default=None, help='queries per GPU per step (overrides --total: weak scaling)')
+    ap.add_argument('--sweep-totals', default=None,
+                    help='comma-separated totals (e.g. 1e3,1e5,1e7,1e9): one JSON line per total on the same table; steps of '
+                         '2^24 queries per GPU and more are timed over at most 10 steps')
     ap.add_argument('--e2e-batch', type=int, default=1 << 26, help='queries per GPU per end-to-end (host buffer) step')
     ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--gather', type=int, default=0, help='0 auto, 1 strided, 2 cell-major')
@@ -365,194 +368,204 @@ def run_b200(args):
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t_build
 
-    # per-rank, per-buffer distinct rows of the global synthetic batch
-    qs = [gen_queries(w, (b * ws + rank) * B, B, dev) for b in range(nbuf)]
-    interps = torch.empty((B, w.vdim), dtype=torch.float64, device=dev)
-    dists = torch.empty((B, 1), dtype=torch.float64, device=dev)
-    stream = torch.cuda.Stream(dev)                # kernels and timing events share this stream
-    T.set_option('stream', stream.cuda_stream)
+    sweep = [int(float(x)) for x in args.sweep_totals.split(',')] if args.sweep_totals else [None]
+    for sweep_total in sweep:
+        if sweep_total is not None:                       # one JSON line per total, same table (--sweep-totals)
+            args.total, args.batch = sweep_total, None
+            B, scaling = batch_of(args, w, ws)
+            nbuf = 1 if B * w.naxes * 8 >= (1 << 30) else 2
+            K = args.steps if B < (1 << 24) else max(3, min(args.steps, 10))
+            T.set_option('stream', 0)
+            qs = interps = dists = None
+            torch.cuda.empty_cache()
+        # per-rank, per-buffer distinct rows of the global synthetic batch
+        qs = [gen_queries(w, (b * ws + rank) * B, B, dev) for b in range(nbuf)]
+        interps = torch.empty((B, w.vdim), dtype=torch.float64, device=dev)
+        dists = torch.empty((B, 1), dtype=torch.float64, device=dev)
+        stream = torch.cuda.Stream(dev)                # kernels and timing events share this stream
+        T.set_option('stream', stream.cuda_stream)
 
-    def barrier():
+        def barrier():
+            torch.cuda.synchronize()
+            if ws > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        use_async = args.api_mode == 'async' or (args.api_mode == 'auto' and B <= (1 << 24))
         torch.cuda.synchronize()
-        if ws > 1:
-            dist.barrier()
+        t_cold = time.perf_counter()
+        T.ndpolate(qs[0][:min(B, 1 << 20)], method, search)      # cold first call: lazy nearest-site map / topology builds
         torch.cuda.synchronize()
-
-    use_async = args.api_mode == 'async' or (args.api_mode == 'auto' and B <= (1 << 24))
-    torch.cuda.synchronize()
-    t_cold = time.perf_counter()
-    T.ndpolate(qs[0][:min(B, 1 << 20)], method, search)      # cold first call: lazy nearest-site map / topology builds
-    torch.cuda.synchronize()
-    cold_s = time.perf_counter() - t_cold
-    if use_async:
-        T.set_option('async', 1)
-        T.ndpolate(qs[0][:min(B, 1 << 20)], method, search)  # builds the kd topology the stream-ordered mode needs
-        T.sync()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()                                        # before the warm-up, so that short runs are sampled too
-    with torch.cuda.stream(stream):
-        for s in range(W):
-            T.ndpolate(qs[s % nbuf], method, search, out=(interps, dists))
-        T.sync()
-
-    keys = ('launches', 'offgrid', 'hard', 'ties', 'slow', 'fused', 'main_ns', 'search_ns', 'finish_ns')
-    acc = dict.fromkeys(keys, 0)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for s in range(K):
-            T.ndpolate(qs[s % nbuf], method, search, out=(interps, dists))
-            if not use_async:
-                for k in keys:
-                    acc[k] += T.stat(k)
+        cold_s = time.perf_counter() - t_cold
         if use_async:
-            T.sync()                                           # completes the K stream-ordered calls, inside the timed region
-        e1.record(stream)
-    barrier()
-    if use_async:
-        # per-step counters and phase times of the same steps, replayed call by call after the timed region
-        with torch.cuda.stream(stream):
-            per_buf = []
-            for b in range(nbuf):
-                T.ndpolate(qs[b], method, search, out=(interps, dists))
-                T.sync()
-                per_buf.append({k: T.stat(k) for k in keys})
-        for s in range(K):
-            for k in keys:
-                acc[k] += per_buf[s % nbuf][k]
-        T.set_option('async', 0)
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if ws > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    if rank == 0 and ms_total < 400.0:
-        # a short timed region: keep the GPU busy with the same work until the sampler has seen it under load
-        t_keep = time.perf_counter()
-        with torch.cuda.stream(stream):
-            while time.perf_counter() - t_keep < 0.5:
-                T.ndpolate(qs[0], method, search, out=(interps, dists))
-        torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
-    if clocks is not None:
-        clocks['note'] = ('sampled every 20 ms from before the warm-up to after the timed steps' +
-                          ('; the timed region was shorter than the sampling period, so the same step was repeated '
-                           'for 0.5 s after it to record the clocks under this load' if ms_total < 400.0 else ''))
-    value = ws * B * K / (ms_total / 1e3)
-    checksum = float(torch.nan_to_num(interps).sum().item())
-
-    # end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
-    T.set_option('stream', 0)
-    nb_e2e = min(args.e2e_batch, B)
-    qh = torch.empty((nb_e2e, w.naxes), dtype=torch.float64).pin_memory()
-    qh.copy_(qs[0][:nb_e2e])
-    ih = torch.empty((nb_e2e, w.vdim), dtype=torch.float64).pin_memory()
-    dh = torch.empty((nb_e2e, 1), dtype=torch.float64).pin_memory()
-    qn, inn, dn = qh.numpy(), ih.numpy(), dh.numpy()
-    T.ndpolate(qn, method, search, out=(inn, dn))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = 0
-    while e2e_steps < args.e2e_steps or (time.perf_counter() - t0 < 1.0 and e2e_steps < 50 * args.e2e_steps):
-        T.ndpolate(qn, method, search, out=(inn, dn))       # returns when the results are in the host arrays
-        e2e_steps += 1
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if ws > 1:                                               # every rank runs the same number of steps
-        steps_t = torch.tensor([e2e_steps], dtype=torch.int64, device=dev)
-        dist.all_reduce(steps_t, op=dist.ReduceOp.MIN)
-        e2e_steps_min = int(steps_t.item())
-    else:
-        e2e_steps_min = e2e_steps
-    h2d, d2h = T.stat('h2d_bytes'), T.stat('d2h_bytes')
-    if ws > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    # per-rank rate (its own steps over its own time), summed over ranks would double-count nothing but hide the
-    # slowest: report the conservative whole-job figure = ranks x per-rank queries x common steps / slowest time
-    e2e_value = ws * nb_e2e * e2e_steps_min / float(e2e_s.item())
-    # the pipelined host path (chunks, two slots, three streams) against a device-resident run of the same rows
-    ref_i, ref_d = T.ndpolate(qs[0][:nb_e2e], method, search)
-    same = bool(torch.equal(ih.view(torch.int64), ref_i.cpu().view(torch.int64)) and
-                torch.equal(dh.view(torch.int64), ref_d.cpu().view(torch.int64)))
-    if not same:
-        raise SystemExit('bench.py: end-to-end (host buffer) results differ from the device-resident run')
-
-    if ws > 1:    # the only collective besides timing: a final gather of per-rank checksums to rank 0
-        sums = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(ws)] if rank == 0 else None
-        dist.gather(torch.tensor([checksum], dtype=torch.float64, device=dev), sums, dst=0)
+            T.set_option('async', 1)
+            T.ndpolate(qs[0][:min(B, 1 << 20)], method, search)  # builds the kd topology the stream-ordered mode needs
+            T.sync()
+        sampler = ClockSampler(local)
         if rank == 0:
-            checksum = float(sum(t.item() for t in sums))
+            sampler.start()                                        # before the warm-up, so that short runs are sampled too
+        with torch.cuda.stream(stream):
+            for s in range(W):
+                T.ndpolate(qs[s % nbuf], method, search, out=(interps, dists))
+            T.sync()
 
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        n_fdhc = B * K - acc['offgrid']
-        main_s = acc['main_ns'] / 1e9 / K
-        cell_bytes = (1 << w.naxes) * w.vdim * 8
-        out_bytes = w.vdim * 8 + 8
-        fused = acc['fused'] == K
-        if fused:
-            # k_fused, per launch: every query row read (naxes*8), ONE gather per query -- its own cell, or for
-            # an extrapolated query the cell below the found hypercube ('linear') / the found vertex ('nearest')
-            # -- and every interps row and dist written; queries handed to k_slow gather nothing here
-            n_slow = acc['slow'] / K
-            off = acc['offgrid'] / K - n_slow
-            gather = cell_bytes if method == 2 else (w.vdim * 8 if method == 1 else 0)
-            main_bytes = B * w.naxes * 8 + (n_fdhc / K) * cell_bytes + off * gather + (B - n_slow) * out_bytes
-            kernel_name = f'k_fused<{w.naxes},{method},{(0 if search == 0 else 2) + (1 if method == 2 else 0)}>'
+        keys = ('launches', 'offgrid', 'hard', 'ties', 'slow', 'fused', 'main_ns', 'search_ns', 'finish_ns')
+        acc = dict.fromkeys(keys, 0)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for s in range(K):
+                T.ndpolate(qs[s % nbuf], method, search, out=(interps, dists))
+                if not use_async:
+                    for k in keys:
+                        acc[k] += T.stat(k)
+            if use_async:
+                T.sync()                                           # completes the K stream-ordered calls, inside the timed region
+            e1.record(stream)
+        barrier()
+        if use_async:
+            # per-step counters and phase times of the same steps, replayed call by call after the timed region
+            with torch.cuda.stream(stream):
+                per_buf = []
+                for b in range(nbuf):
+                    T.ndpolate(qs[b], method, search, out=(interps, dists))
+                    T.sync()
+                    per_buf.append({k: T.stat(k) for k in keys})
+            for s in range(K):
+                for k in keys:
+                    acc[k] += per_buf[s % nbuf][k]
+            T.set_option('async', 0)
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if ws > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = float(ms.item())
+        if rank == 0 and ms_total < 400.0:
+            # a short timed region: keep the GPU busy with the same work until the sampler has seen it under load
+            t_keep = time.perf_counter()
+            with torch.cuda.stream(stream):
+                while time.perf_counter() - t_keep < 0.5:
+                    T.ndpolate(qs[0], method, search, out=(interps, dists))
+            torch.cuda.synchronize()
+        clocks = sampler.stop() if rank == 0 else None
+        if clocks is not None:
+            clocks['note'] = ('sampled every 20 ms from before the warm-up to after the timed steps' +
+                              ('; the timed region was shorter than the sampling period, so the same step was repeated '
+                               'for 0.5 s after it to record the clocks under this load' if ms_total < 400.0 else ''))
+        value = ws * B * K / (ms_total / 1e3)
+        checksum = float(torch.nan_to_num(interps).sum().item())
+
+        # end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+        T.set_option('stream', 0)
+        nb_e2e = min(args.e2e_batch, B)
+        qh = torch.empty((nb_e2e, w.naxes), dtype=torch.float64).pin_memory()
+        qh.copy_(qs[0][:nb_e2e])
+        ih = torch.empty((nb_e2e, w.vdim), dtype=torch.float64).pin_memory()
+        dh = torch.empty((nb_e2e, 1), dtype=torch.float64).pin_memory()
+        qn, inn, dn = qh.numpy(), ih.numpy(), dh.numpy()
+        T.ndpolate(qn, method, search, out=(inn, dn))
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = 0
+        while e2e_steps < args.e2e_steps or (time.perf_counter() - t0 < 1.0 and e2e_steps < 50 * args.e2e_steps):
+            T.ndpolate(qn, method, search, out=(inn, dn))       # returns when the results are in the host arrays
+            e2e_steps += 1
+        torch.cuda.synchronize()
+        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if ws > 1:                                               # every rank runs the same number of steps
+            steps_t = torch.tensor([e2e_steps], dtype=torch.int64, device=dev)
+            dist.all_reduce(steps_t, op=dist.ReduceOp.MIN)
+            e2e_steps_min = int(steps_t.item())
         else:
-            # k_gather_staged / k_main, per launch: every query row read + for the queries it completes (fully
-            # defined hypercube) the 2^n-corner gather, the interps row and the dist
-            main_bytes = B * w.naxes * 8 + (n_fdhc / K) * (cell_bytes + out_bytes)
-            kernel_name = 'k_gather_staged<N,0> / k_main (fused import + cell gather + reduce, first of three passes)'
-        achieved = main_bytes / main_s / 1e9 if main_s > 0 else None
-        wl_key = f'{args.workload}@{args.scale}/{args.mix}/{args.method or w.method}/{args.search}'
-        traffic = measured_traffic(B, wl_key) if fused else None
-        step_gbs = B * w.bytes_per_query / (ms_total / 1e3 / K) / 1e9
-        line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': ws, 'steps': K, 'warmup': W,
-            'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args),
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'queries_per_gpu_per_step': nb_e2e, 'steps': e2e_steps_min, 'seconds': float(e2e_s.item()),
-                    'host_memory': 'pinned' + (f' ({bind_note})' if bind_note else ''),
-                    'matches_device_run': same},
-            'gpu_launches': acc['launches'],
-            'clocks': clocks,
-            'roofline': {
-                'bound': 'hbm', 'kernel': kernel_name,
-                'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': (achieved / peak) if achieved else None,
-                'traffic': traffic,
-                'traffic_source': ('profiles/r02_traffic.json (ncu --set full on these sources, scaled to this batch)'
-                                   if traffic else 'no ncu capture of exactly these kernel sources / this workload'),
-                'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': main_bytes, 'avg_launch_ms': main_s * 1e3,
-                'whole_step': {'achieved': step_gbs, 'frac': step_gbs / peak,
-                               'note': 'queries/step x SURVEY 8d bytes/query over the whole step (all kernels)'},
-                'phase_ms_per_step': {'k_main': acc['main_ns'] / 1e6 / K, 'k_search': acc['search_ns'] / 1e6 / K,
-                                      'k_finish': acc['finish_ns'] / 1e6 / K},
-            },
-            'mix_measured': {'in_fully_defined_hypercube': n_fdhc / (B * K), 'offgrid': acc['offgrid'] / (B * K),
-                             'needed_lattice_descent': acc['hard'] / (B * K), 'kd_ties': acc['ties'],
-                             'left_to_exact_generic_kernel': acc['slow'] / (B * K)},
-            'path': 'fused (k_fused + k_slow)' if fused else 'three-pass (gather, search, finish)',
-            'api_mode': ('async: K stream-ordered ndpolate calls on device tensors + one ndpb_table_sync, all inside the timed '
-                         'region; counters / phase times from a call-by-call replay after it' if use_async else
-                         'sync: every ndpolate call returns with its results complete'),
-            'table': {'cellmajor': bool(T.stat('cellmajor')), 'build_s': build_s, 'cold_first_call_s': cold_s,
-                      'note': 'build_s: upload + masks + pyramids + cell-major copy; cold_first_call_s: first ndpolate of 2^20 '
-                              'queries incl. the lazy nearest-site map (the reference builds its kd-tree there)'},
-            'checksum': checksum,
-        }
-        if ws == 1 and not args.no_cpu_baseline:
-            try:
-                cb = cpu_reference_run(args, steps=2, warmup=1)
-                line['cpu_baseline'] = {k: cb[k] for k in CPU_KEYS}
-            except Exception as e:       # the baseline is reported beside the number, never instead of it
-                line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
-                                        'sample': f'failed: {e!r}'}
-        print(json.dumps(line))
+            e2e_steps_min = e2e_steps
+        h2d, d2h = T.stat('h2d_bytes'), T.stat('d2h_bytes')
+        if ws > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        # per-rank rate (its own steps over its own time), summed over ranks would double-count nothing but hide the
+        # slowest: report the conservative whole-job figure = ranks x per-rank queries x common steps / slowest time
+        e2e_value = ws * nb_e2e * e2e_steps_min / float(e2e_s.item())
+        # the pipelined host path (chunks, two slots, three streams) against a device-resident run of the same rows
+        ref_i, ref_d = T.ndpolate(qs[0][:nb_e2e], method, search)
+        same = bool(torch.equal(ih.view(torch.int64), ref_i.cpu().view(torch.int64)) and
+                    torch.equal(dh.view(torch.int64), ref_d.cpu().view(torch.int64)))
+        if not same:
+            raise SystemExit('bench.py: end-to-end (host buffer) results differ from the device-resident run')
+
+        if ws > 1:    # the only collective besides timing: a final gather of per-rank checksums to rank 0
+            sums = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(ws)] if rank == 0 else None
+            dist.gather(torch.tensor([checksum], dtype=torch.float64, device=dev), sums, dst=0)
+            if rank == 0:
+                checksum = float(sum(t.item() for t in sums))
+
+        if rank == 0:
+            peak, peak_src = measured_peak()
+            n_fdhc = B * K - acc['offgrid']
+            main_s = acc['main_ns'] / 1e9 / K
+            cell_bytes = (1 << w.naxes) * w.vdim * 8
+            out_bytes = w.vdim * 8 + 8
+            fused = acc['fused'] == K
+            if fused:
+                # k_fused, per launch: every query row read (naxes*8), ONE gather per query -- its own cell, or for
+                # an extrapolated query the cell below the found hypercube ('linear') / the found vertex ('nearest')
+                # -- and every interps row and dist written; queries handed to k_slow gather nothing here
+                n_slow = acc['slow'] / K
+                off = acc['offgrid'] / K - n_slow
+                gather = cell_bytes if method == 2 else (w.vdim * 8 if method == 1 else 0)
+                main_bytes = B * w.naxes * 8 + (n_fdhc / K) * cell_bytes + off * gather + (B - n_slow) * out_bytes
+                kernel_name = f'k_fused<{w.naxes},{method},{(0 if search == 0 else 2) + (1 if method == 2 else 0)}>'
+            else:
+                # k_gather_staged / k_main, per launch: every query row read + for the queries it completes (fully
+                # defined hypercube) the 2^n-corner gather, the interps row and the dist
+                main_bytes = B * w.naxes * 8 + (n_fdhc / K) * (cell_bytes + out_bytes)
+                kernel_name = 'k_gather_staged<N,0> / k_main (fused import + cell gather + reduce, first of three passes)'
+            achieved = main_bytes / main_s / 1e9 if main_s > 0 else None
+            wl_key = f'{args.workload}@{args.scale}/{args.mix}/{args.method or w.method}/{args.search}'
+            traffic = measured_traffic(B, wl_key) if fused else None
+            step_gbs = B * w.bytes_per_query / (ms_total / 1e3 / K) / 1e9
+            line = {
+                'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': ws, 'steps': K, 'warmup': W,
+                'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None,
+                'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args),
+                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'queries_per_gpu_per_step': nb_e2e, 'steps': e2e_steps_min, 'seconds': float(e2e_s.item()),
+                        'host_memory': 'pinned' + (f' ({bind_note})' if bind_note else ''),
+                        'matches_device_run': same},
+                'gpu_launches': acc['launches'],
+                'clocks': clocks,
+                'roofline': {
+                    'bound': 'hbm', 'kernel': kernel_name,
+                    'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                    'frac': (achieved / peak) if achieved else None,
+                    'traffic': traffic,
+                    'traffic_source': ('profiles/r02_traffic.json (ncu --set full on these sources, scaled to this batch)'
+                                       if traffic else 'no ncu capture of exactly these kernel sources / this workload'),
+                    'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': main_bytes, 'avg_launch_ms': main_s * 1e3,
+                    'whole_step': {'achieved': step_gbs, 'frac': step_gbs / peak,
+                                   'note': 'queries/step x SURVEY 8d bytes/query over the whole step (all kernels)'},
+                    'phase_ms_per_step': {'k_main': acc['main_ns'] / 1e6 / K, 'k_search': acc['search_ns'] / 1e6 / K,
+                                          'k_finish': acc['finish_ns'] / 1e6 / K},
+                },
+                'mix_measured': {'in_fully_defined_hypercube': n_fdhc / (B * K), 'offgrid': acc['offgrid'] / (B * K),
+                                 'needed_lattice_descent': acc['hard'] / (B * K), 'kd_ties': acc['ties'],
+                                 'left_to_exact_generic_kernel': acc['slow'] / (B * K)},
+                'path': 'fused (k_fused + k_slow)' if fused else 'three-pass (gather, search, finish)',
+                'api_mode': ('async: K stream-ordered ndpolate calls on device tensors + one ndpb_table_sync, all inside the timed '
+                             'region; counters / phase times from a call-by-call replay after it' if use_async else
+                             'sync: every ndpolate call returns with its results complete'),
+                'table': {'cellmajor': bool(T.stat('cellmajor')), 'build_s': build_s, 'cold_first_call_s': cold_s,
+                          'note': 'build_s: upload + masks + pyramids + cell-major copy; cold_first_call_s: first ndpolate of 2^20 '
+                                  'queries incl. the lazy nearest-site map (the reference builds its kd-tree there)'},
+                'checksum': checksum,
+            }
+            if ws == 1 and not args.no_cpu_baseline and sweep_total is None:
+                try:
+                    cb = cpu_reference_run(args, steps=2, warmup=1)
+                    line['cpu_baseline'] = {k: cb[k] for k in CPU_KEYS}
+                except Exception as e:       # the baseline is reported beside the number, never instead of it
+                    line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                                            'sample': f'failed: {e!r}'}
+            print(json.dumps(line))
     if ws > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -368,13 +368,28 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
     int region = 0, base = 0;
     bool ok = true;
     bool wide = true;                  // every closed-form axis has the NSM_EPS margin (else only NSM_EPS_NEAR)
+    double qa[MM];
+    // variant axes first: the region, so that the loads of its candidate range are in flight during the rest
 #pragma unroll
     for (int a = 0; a < MM; a++) {
-        t0[a] = 0.0; fix[a] = 0;
+        t0[a] = 0.0; fix[a] = 0; qa[a] = 0.0;
         if (a < nb) {
             const bool nan = !(Q.qc[a] == Q.qc[a]);
-            const double q = nan ? 0.0 : Q.qc[a];
+            qa[a] = nan ? 0.0 : Q.qc[a];
             ok &= !nan;
+            const int j = VS ? (a < 2 ? a : -1) : M.jof[a];
+            if (j >= 0) {
+                const int r = nsm_region_of(M.S, g.len[a], qa[a]);
+                ok &= r >= 0;
+                region += (r < 0 ? 0 : r) * M.rstride[j];
+            }
+        }
+    }
+    const int beg = M.offs[region], end = M.offs[region + 1];
+#pragma unroll
+    for (int a = 0; a < MM; a++) {
+        if (a < nb) {
+            const double q = qa[a];
             const int j = VS ? (a < 2 ? a : -1) : M.jof[a];
             if (j < 0) {
                 // the mask does not depend on this axis: the winner takes the coordinate that minimises the
@@ -385,8 +400,8 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
                 const int c = (int) p;
                 if (point) {
                     // (pos - q)^2 with pos = p or p - 0.5.  The neighbours at pos -+ 1 score 1 -+ 2 d0 more: a
-                    // margin unless |d0| is within NSM_EPS of 1/2.  (|d0| > 1/2 only where p was clamped to the end
-                    // of the axis, and then the one neighbour that exists lies on the far side.)
+                    // margin unless |d0| is within the tolerance of 1/2.  (|d0| > 1/2 only where p was clamped to the
+                    // end of the axis, and then the one neighbour that exists lies on the far side.)
                     // The margin must exceed twice the rounding error of the ordered totals the reference compares:
                     // NSM_EPS whatever the total (< NSM_TMAX), NSM_EPS_NEAR when the winner's total is below NSM_TNEAR.
                     const double d0 = (cells ? p - 0.5 : p) - q;
@@ -403,15 +418,10 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
                 }
                 fix[a] = c;
                 if (!kd) base += c * g.bstride[a];
-            } else {
-                const int r = nsm_region_of(M.S, g.len[a], q);
-                ok &= r >= 0;
-                region += (r < 0 ? 0 : r) * M.rstride[j];
             }
         }
     }
     if (!ok) return false;
-    const int beg = M.offs[region], end = M.offs[region + 1];
     int best = 0x7fffffff;
     double bestd = 8.0 * NSM_TMAX;
     unsigned long long bestp = 0;

@@ -22,10 +22,7 @@ run --workload C5 --scale 20 --steps 8 --warmup 3 >> $OUT
 fi
 if [ "$WHAT" != "configs" ]; then
 : > $SWEEP
-for n in 1000 10000 100000 1000000 10000000 100000000 1000000000; do
-  steps=$(( n < 1000000 ? 500 : (n < 100000000 ? 50 : 5) ))
-  run --workload C5 --total $n --steps $steps --warmup 5 >> $SWEEP
-  run --workload C5 --method nearest --total $n --steps $steps --warmup 5 >> $SWEEP
-done
+run --workload C5 --sweep-totals 1e3,1e4,1e5,1e6,1e7,1e8,1e9 --steps 500 --warmup 5 >> $SWEEP
+run --workload C5 --method nearest --sweep-totals 1e3,1e4,1e5,1e6,1e7,1e8,1e9 --steps 500 --warmup 5 >> $SWEEP
 fi
 wc -l $OUT $SWEEP 2>/dev/null
