@@ -356,8 +356,10 @@ def run_b200(args):
     bind_note = bind_to_gpu_numa_node(local)          # host buffers of the end-to-end leg land next to this GPU
     t_build = time.perf_counter()
     grid = w.grid(dev)
+    torch.cuda.empty_cache()                       # the generator's temporaries: the table sizes its cell copy by the free memory
     T = Table(w.axes, grid, len(w.basic_axes), device=local)
     del grid
+    torch.cuda.empty_cache()
     if args.gather:
         T.set_option('gather', args.gather)
     if args.staged:

@@ -292,7 +292,7 @@ static void drop_cells(ndpb_table *t)
 }
 
 // The gather-friendly copy of the grid.  Scalar tables: the blocked layout of ndp_fused.cuh with the largest block
-// order whose copy (2^order times the grid) fits in half of the free device memory -- order == naxes is the
+// order whose copy (2^order times the grid) fits in 60 % of the free device memory -- order == naxes is the
 // cell-major copy (one contiguous (8 << n)-byte burst per query), smaller orders cost 2^(n - order) bursts of
 // (8 << order) bytes per query and serve tables whose full copy would not fit.  Small-vector tables (vdim * 8 <
 // 128): the full cell-major copy when it fits.  Vectors of a full line and more are gathered from the grid itself.
@@ -317,7 +317,7 @@ static int maybe_build_cells(ndpb_table *t)
     for (int k = g.naxes; k >= 1; k--) {
         if (t->opt_block_order && k != t->opt_block_order) continue;
         ndp_blocks_setup(g, k, B);
-        if (((B.nblocks << k) * (long long) sizeof(double)) <= (long long) (free_b / 2)) { order = k; break; }
+        if (((B.nblocks << k) * (long long) sizeof(double)) <= (long long) (free_b / 10 * 6)) { order = k; break; }
     }
     if (!order) return NDPB_OK;
     CU(cudaMalloc(&t->blocks, (size_t) (B.nblocks << order) * sizeof(double)));
@@ -880,14 +880,17 @@ static bool fused_ok(ndpb_table *t, int method, int search)
     return t->nsm[geo].valid != 0;
 }
 
+struct CachedImport { const int *idx = nullptr, *flg = nullptr; const double *nrm = nullptr; };
+
 static int launch_fused(ndpb_table *t, Slot &s, const double *q, long long n, int method, int search,
-                        double *interps, double *dists, cudaStream_t st)
+                        double *interps, double *dists, cudaStream_t st, const CachedImport &cache = CachedImport())
 {
     const NdpGeom &g = t->g;
     const int mode = ndp_mode_of(method, search);
     FusedArgs A{};
     A.g = g; A.ticks = t->ticks; A.nticks = t->nticks; A.cells = t->blocks; A.grid = t->grid;
     A.q = q; A.n = n; A.interps = interps; A.dists = dists;
+    A.c_idx = cache.idx; A.c_flg = cache.flg; A.c_nrm = cache.nrm;
     if (g.vdim == 1) {
         // the plan's cell number is a block number of the blocked copy
         ndp_blocks_setup(g, t->block_order, A.B);
@@ -919,7 +922,7 @@ static int launch_fused(ndpb_table *t, Slot &s, const double *q, long long n, in
 
 // k_slow over a device list of query ids: the slow list of the fused kernel, or (tie == true) the tie list
 static int launch_slow(ndpb_table *t, Slot &s, const double *q, long long n, int method, int search, double *interps, double *dists,
-                       bool tie, cudaStream_t st)
+                       bool tie, cudaStream_t st, const CachedImport &cache = CachedImport())
 {
     const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;
     SlowArgs A{};
@@ -930,7 +933,7 @@ static int launch_slow(ndpb_table *t, Slot &s, const double *q, long long n, int
     A.grid = t->grid; A.q = q; A.method = method; A.search = search;
     A.list = tie ? s.tielist : s.list;
     A.count = tie ? &s.ctr->n_tie : &s.ctr->n_slow;
-    A.count_host = 0; A.c_idx = nullptr; A.c_flg = nullptr; A.c_nrm = nullptr;
+    A.count_host = 0; A.c_idx = cache.idx; A.c_flg = cache.flg; A.c_nrm = cache.nrm;
     A.interps = interps; A.dists = dists; A.tielist = s.tielist; A.count_searched = tie ? 0 : 1; A.ctr = s.ctr;
     const int blocks = (int) std::min<long long>((long long) t->sm_count * 2, (n + NDP_BLOCK - 1) / NDP_BLOCK);
     CU(ndp_launch_slow(A, std::max(blocks, 1), smem_bytes(t), st));
@@ -1446,8 +1449,10 @@ extern "C" int ndpb_group_distance(ndpb_group *g, const double *query_pts, int64
 // ---------------------------------------------------------------------------
 // Hypercube-caching path (reference README "Hypercube caching", ndpolator/ndpolator.py:110-187): the caller
 // keeps the import products of a batch (ndpb_find) -- on the device, if it passes device pointers -- and
-// interpolates from them, e.g. on several tables that share their axes.  Runs the exact generic kernel
-// (k_slow) over all queries; identical results to ndpb_ndpolate on the original query points.
+// interpolates from them, e.g. on several tables that share their axes.  Tables the fused path serves run
+// k_fused / k_fused_vec with the cached products in place of the import (then k_slow for the few the plan
+// cannot settle), the others the exact generic kernel (k_slow) over all queries; identical results to
+// ndpb_ndpolate on the original query points.
 // ---------------------------------------------------------------------------
 extern "C" int ndpb_ndpolate_cached(ndpb_table *t, const double *normed, const int32_t *indices, const int32_t *flags,
                                     int64_t n, int method, int search, double *interps, double *dists)
@@ -1471,6 +1476,30 @@ extern "C" int ndpb_ndpolate_cached(ndpb_table *t, const double *normed, const i
     if (rc) return rc;
     cudaStream_t st = t->s_compute;
     const int m = method == NDPB_METHOD_LINEAR ? 1 : 0;
+    CachedImport cache;
+    cache.idx = idx.dev; cache.flg = flg.dev; cache.nrm = nrm.dev;
+    if (fused_ok(t, method, search)) {
+        // the fused kernels with the cached import products in place of the import; what their plan cannot settle
+        // goes through k_slow (also on the cached products), kd ties through the topology as in ndpb_ndpolate
+        CU(cudaMemsetAsync(s.ctr, 0, sizeof(NdpCounters), st));
+        rc = launch_fused(t, s, nullptr, n, method, search, out_i.dev, out_d.dev, st, cache);
+        if (rc) return rc;
+        rc = launch_slow(t, s, nullptr, n, method, search, out_i.dev, out_d.dev, false, st, cache);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(s.ctr_host, s.ctr, sizeof(NdpCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        t->st_fused++;
+        t->st_slow += s.ctr_host->n_slow;
+        t->st_offgrid += s.ctr_host->n_off;
+        if (s.ctr_host->n_tie > 0) {
+            t->st_ties += s.ctr_host->n_tie;
+            rc = ensure_topology(t, m);
+            if (rc) return rc;
+            rc = launch_slow(t, s, nullptr, n, method, search, out_i.dev, out_d.dev, true, st, cache);
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(st));
+        }
+    } else
     for (int pass = 0; pass < 2; pass++) {
         if (pass == 0) CU(cudaMemsetAsync(s.ctr, 0, sizeof(NdpCounters), st));
         SlowArgs A{};

@@ -29,6 +29,7 @@ struct FusedArgs {
     const double *ticks; int nticks;
     const double *cells; const double *grid;
     const double *q; long long n;
+    const int *c_idx; const int *c_flg; const double *c_nrm;   // CACHED kernels: import products (n x naxes) instead of q
     double *interps; double *dists;
     NdpHcSlice H; int hc_in_smem;
     NdpSiteMap M;
@@ -142,9 +143,12 @@ struct NdpFusedItem {
 //         shared memory, so the long plan section has the whole register file.
 // PIPE 2: the same pipeline with the waiting plan kept in registers (less shared memory, one more CTA per SM).
 // VS: see ndp_nsm_search.
-template <int N, int METHOD, int MODE, int OCC, int VS, int PIPE>
+// CACHED: the import products of the queries (ndpb_find: indices, flags, normed) are read instead of the query
+//         points -- the hypercube-caching path (ndpb_ndpolate_cached); runs the PIPE 0 loop.
+template <int N, int METHOD, int MODE, int OCC, int VS, int PIPE_, int CACHED = 0>
 __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __grid_constant__ FusedArgs A)
 {
+    constexpr int PIPE = CACHED ? 0 : PIPE_;
     constexpr unsigned CELL_BYTES = 8u << N;
     constexpr unsigned SLOT = CELL_BYTES + 16u;           // +16: the 128-bit shared loads of a quarter warp hit distinct bank groups
     constexpr int CHUNKS = (int) (CELL_BYTES / 16u);
@@ -194,10 +198,14 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
     // import + plan of this lane's query of `tile`; qrow: its N coordinates (registers or shared memory)
     auto make_plan = [&](long long tile, const double *qrow, NdpPlan<N> &P) {
         P.kind = NDP_PLAN_IDLE; P.cell = 0; P.vflat = 0; P.pin = 0; P.sel = 0; P.dist = 0.0; P.searched = 0;
-        if (tile * 32 + lane < A.n) {
+        const long long w = tile * 32 + lane;
+        if (w < A.n) {
             int idx[N], flg[N];
             double nrm[N];
-            ndp_import_query<N>(g, s_ticks, qrow, idx, flg, nrm);
+            if (CACHED) {
+#pragma unroll
+                for (int a = 0; a < N; a++) { idx[a] = A.c_idx[w * N + a]; flg[a] = A.c_flg[w * N + a]; nrm[a] = A.c_nrm[w * N + a]; }
+            } else ndp_import_query<N>(g, s_ticks, qrow, idx, flg, nrm);
             ndp_fused_plan<N, METHOD, MODE, VS>(g, A.H, hcbits, A.M, idx, flg, nrm, P);
         }
     };
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
         for (long long tile = tile0; tile < ntiles; tile += tile_stride) {
             const long long w = tile * 32 + lane;
             double qv[N];
-            if (w < A.n) {
+            if (!CACHED && w < A.n) {
 #pragma unroll
                 for (int a = 0; a < N; a++) qv[a] = A.q[w * N + a];
             }
@@ -423,12 +431,17 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, 4) k_fused_vec(const __g
 #pragma unroll
         for (int a = 0; a < N; a++) P.x[a] = 0.0;
         if (w < A.n) {
-            double qv[N];
-#pragma unroll
-            for (int a = 0; a < N; a++) qv[a] = A.q[w * N + a];
             int idx[N], flg[N];
             double nrm[N];
-            ndp_import_query<N>(g, s_ticks, qv, idx, flg, nrm);
+            if (A.c_idx) {            // hypercube-caching path: cached import products instead of query points
+#pragma unroll
+                for (int a = 0; a < N; a++) { idx[a] = A.c_idx[w * N + a]; flg[a] = A.c_flg[w * N + a]; nrm[a] = A.c_nrm[w * N + a]; }
+            } else {
+                double qv[N];
+#pragma unroll
+                for (int a = 0; a < N; a++) qv[a] = A.q[w * N + a];
+                ndp_import_query<N>(g, s_ticks, qv, idx, flg, nrm);
+            }
             ndp_fused_plan<N, METHOD, MODE, VS>(g, A.H, hcbits, A.M, idx, flg, nrm, P);
         }
         const long long mybase = P.kind == NDP_PLAN_VALUE ? P.vflat : P.cell;

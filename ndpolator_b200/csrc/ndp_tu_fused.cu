@@ -22,12 +22,12 @@
 #endif
 #endif
 
-template <int METHOD, int MODE, int VS>
+template <int METHOD, int MODE, int VS, int CACHED = 0>
 static cudaError_t go(const FusedArgs &A, int sm_count, size_t smem_fixed, cudaStream_t st)
 {
     constexpr int N = NDP_FUSED_N;
-    auto kern = k_fused<N, METHOD, MODE, NDP_FUSED_OCC, VS, NDP_FUSED_PIPE>;
-    const size_t smem = smem_fixed + (size_t) NDP_FUSED_WARPS * ndpf_warp_bytes(N, NDP_FUSED_PIPE);
+    auto kern = k_fused<N, METHOD, MODE, NDP_FUSED_OCC, VS, NDP_FUSED_PIPE, CACHED>;
+    const size_t smem = smem_fixed + (size_t) NDP_FUSED_WARPS * ndpf_warp_bytes(N, CACHED ? 0 : NDP_FUSED_PIPE);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
@@ -68,14 +68,14 @@ static cudaError_t by_mode_vec(const FusedArgs &A, int method, int mode, int sm_
     }
 }
 
-template <int VS>
+template <int VS, int CACHED = 0>
 static cudaError_t by_mode(const FusedArgs &A, int method, int mode, int sm_count, size_t smem_fixed, cudaStream_t st)
 {
     switch (mode) {
-    case NDP_MODE_KD_NEAREST: return go<NDP_M_NEAREST, NDP_MODE_KD_NEAREST, VS>(A, sm_count, smem_fixed, st);
-    case NDP_MODE_KD_LINEAR: return go<NDP_M_LINEAR, NDP_MODE_KD_LINEAR, VS>(A, sm_count, smem_fixed, st);
-    case NDP_MODE_LS_NEAREST: return go<NDP_M_NEAREST, NDP_MODE_LS_NEAREST, VS>(A, sm_count, smem_fixed, st);
-    default: return go<NDP_M_LINEAR, NDP_MODE_LS_LINEAR, VS>(A, sm_count, smem_fixed, st);
+    case NDP_MODE_KD_NEAREST: return go<NDP_M_NEAREST, NDP_MODE_KD_NEAREST, VS, CACHED>(A, sm_count, smem_fixed, st);
+    case NDP_MODE_KD_LINEAR: return go<NDP_M_LINEAR, NDP_MODE_KD_LINEAR, VS, CACHED>(A, sm_count, smem_fixed, st);
+    case NDP_MODE_LS_NEAREST: return go<NDP_M_NEAREST, NDP_MODE_LS_NEAREST, VS, CACHED>(A, sm_count, smem_fixed, st);
+    default: return go<NDP_M_LINEAR, NDP_MODE_LS_LINEAR, VS, CACHED>(A, sm_count, smem_fixed, st);
     }
 }
 
@@ -87,6 +87,10 @@ cudaError_t NDP_CAT(ndp_launch_fused_, NDP_FUSED_N)(const FusedArgs &A, int meth
         if (method == NDP_M_NONE) return go_vec<NDP_M_NONE, 0, 0>(A, sm_count, smem_fixed, st);
         return nsm_leading_pair(A.M) ? by_mode_vec<1>(A, method, mode, sm_count, smem_fixed, st)
                                      : by_mode_vec<0>(A, method, mode, sm_count, smem_fixed, st);
+    }
+    if (A.c_idx) {               // cached import products (ndpb_ndpolate_cached): the general candidate loop only
+        if (method == NDP_M_NONE) return go<NDP_M_NONE, 0, 0, 1>(A, sm_count, smem_fixed, st);
+        return by_mode<0, 1>(A, method, mode, sm_count, smem_fixed, st);
     }
     if (method == NDP_M_NONE) return go<NDP_M_NONE, 0, 0>(A, sm_count, smem_fixed, st);
     // tables whose voids depend on exactly their two leading axes take the specialised candidate loop

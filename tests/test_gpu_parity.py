@@ -434,6 +434,8 @@ def test_device_resident_cache_path(case):
     for method, m in (('none', 0), ('nearest', 1), ('linear', 2)):
         got = ndp.ndpolate_cached('t', nrm, idx, flg, extrapolation_method=method)
         want = O.ndpolate(q, m, 0)
+        if name in ('holed3d', '5d_corner_void', 'c3_like_v16'):       # served by k_fused / k_fused_vec on the cached products
+            assert ndp.table['t']['capsule'].stat('fused') == 1
         assert got['interps'].is_cuda
         assert_same_bits(want[0], got['interps'].cpu().numpy(), f'cached interps {method}')
         if m:
