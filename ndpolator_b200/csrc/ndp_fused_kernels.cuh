@@ -124,7 +124,7 @@ __device__ __forceinline__ void ndpf_mbar_wait(unsigned bar, unsigned parity)
 // shared memory per warp: 32 copy slots; PIPE: + 2 query tiles + their 2 mbarriers; PIPE 1: + 2 tiles of saved plans
 __host__ __device__ constexpr unsigned ndpf_warp_bytes(int n, int pipe)
 {
-    return 32u * ((8u << n) + 16u) + (pipe ? 2u * 32u * 8u * (unsigned) n + 16u : 0u) +
+    return 32u * ((8u << n) + 16u) + (pipe ? (pipe == 3 ? 1u : 2u) * 32u * 8u * (unsigned) n + 16u : 0u) +
            (pipe == 1 ? 2u * 32u * (8u * ((unsigned) n + 1u) + 16u) : 0u);
 }
 
@@ -142,6 +142,8 @@ struct NdpFusedItem {
 //         of tile t+1 run while the cell copies of tile t are in flight; the plan of the tile in flight waits in
 //         shared memory, so the long plan section has the whole register file.
 // PIPE 2: the same pipeline with the waiting plan kept in registers (less shared memory, one more CTA per SM).
+// PIPE 3: PIPE 2 with ONE query buffer per warp (refilled as soon as the import has read it): 1.3 KB less shared
+//         memory per warp, which is what a fifth CTA per SM needs for 5 axes.
 // VS: see ndp_nsm_search.
 // CACHED: the import products of the queries (ndpb_find: indices, flags, normed) are read instead of the query
 //         points -- the hypercube-caching path (ndpb_ndpolate_cached); runs the PIPE 0 loop.
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
     unsigned char *s_slots = s_warp;
     unsigned char *s_q = s_warp + 32u * SLOT;                       // PIPE: [2][32][N] doubles
     const unsigned s_bar = ndpf_smem_u32(s_q + 2u * QTILE);         // PIPE: one mbarrier per query buffer
+    const unsigned s_bar_1 = ndpf_smem_u32(s_q + QTILE);            // PIPE 3: the mbarrier of its one query buffer
     unsigned char *s_item = s_q + 2u * QTILE + 16u;                 // PIPE 1: [2][N + 1][32] doubles + [2][32] uint4
     const unsigned char *my_slot = s_slots + (size_t) lane * SLOT;
     // cooperative copy: a cell is fetched by LPB consecutive lanes, 16 bytes each, i.e. as ONE contiguous (8 << N)-
@@ -261,7 +264,83 @@ __global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __gri
         it.dist = P.dist; it.pin = P.pin; it.sel = P.sel; it.kind = P.kind; it.searched = P.searched;
     };
 
-    if (!PIPE) {
+    if (PIPE == 3) {
+        // one query buffer: {q(t)} lands -> plan(t) -> the buffer is refilled with q(t + 1) at once.  cp.async groups
+        // alternate {q(next + 1)} {cells(next)}: "all but the newest" (wait_group 1) is the cells before a finish and
+        // the queries before a plan; with a TMA tile the query group is empty and its mbarrier is waited for instead.
+        unsigned by_tma = 0, phase = 0;
+        if (lane == 0) { ndpf_mbar_init(s_bar_1, 1); ndpf_mbar_fence_init(); }
+        __syncwarp();
+        auto prefetch_q1 = [&](long long tile) {
+            by_tma = 0;
+            if (tile >= ntiles) return;
+            const unsigned dst = ndpf_smem_u32(s_q);
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(A.q) + tile * (long long) QTILE;
+            const long long left = (A.n - tile * 32) * (long long) QROW;
+            if (NDP_FUSED_TMAQ && q_aligned && left >= (long long) QTILE) {
+                by_tma = 1;
+                if (lane == 0) { ndpf_mbar_expect_tx(s_bar_1, QTILE); ndpf_bulk_g2s(dst, src, QTILE, s_bar_1); }
+            } else if (q_aligned) {
+#pragma unroll
+                for (unsigned c = 0; c < (QCHUNKS + 31u) / 32u; c++) {
+                    const unsigned piece = c * 32u + lane;
+                    const long long off = (long long) piece * 16;
+                    if (piece < QCHUNKS && off < left) ndpf_cp_async16_part(dst + piece * 16u, src + off, left - off >= 16 ? 16u : 8u);
+                }
+            } else {
+#pragma unroll
+                for (unsigned c = 0; c < N; c++) {
+                    const long long off = (long long) (c * 32u + lane) * 8;
+                    if (off < left) ndpf_cp_async8(dst + (c * 32u + lane) * 8u, src + off);
+                }
+            }
+        };
+        auto await_q1 = [&]() {
+            if (by_tma) { ndpf_mbar_wait(s_bar_1, phase); phase ^= 1u; }
+        };
+        if (tile0 < ntiles) {
+            prefetch_q1(tile0);
+            ndpf_cp_async_commit();
+            ndpf_cp_async_wait0();
+            await_q1();
+            __syncwarp();
+            NdpPlan<N> P;
+            make_plan(tile0, reinterpret_cast<const double *>(s_q) + lane * N, P);
+            __syncwarp();                          // every lane has read its row of the query buffer
+            prefetch_q1(tile0 + tile_stride);
+            ndpf_cp_async_commit();                // {q(t1)}
+            issue_cells(P);
+            ndpf_cp_async_commit();                // {cells(t0)}
+            NdpFusedItem<N> it_cur;
+            item_of(P, it_cur);
+            for (long long tile = tile0; tile < ntiles; tile += tile_stride) {
+                const long long next = tile + tile_stride;
+                NdpPlan<N> Pn;
+                Pn.kind = NDP_PLAN_IDLE; Pn.cell = 0; Pn.vflat = 0;
+                NdpFusedItem<N> itn;
+                itn.kind = NDP_PLAN_IDLE; itn.pin = 0; itn.sel = 0; itn.searched = 0; itn.dist = 0.0;
+                if (next < ntiles) {
+                    ndpf_cp_async_wait1();         // q(next) is in the group before cells(tile)
+                    await_q1();
+                    __syncwarp();
+                    make_plan(next, reinterpret_cast<const double *>(s_q) + lane * N, Pn);
+                    item_of(Pn, itn);
+                    __syncwarp();                  // the query buffer has been read by every lane
+                    prefetch_q1(next + tile_stride);
+                    ndpf_cp_async_commit();        // {q(next + 1)}: now the newest group, cells(tile) the one before
+                    ndpf_cp_async_wait1();
+                } else ndpf_cp_async_wait0();
+                __syncwarp();                      // the cells of `tile` have landed, for every lane
+                finish(tile, it_cur);
+                it_cur = itn;
+                __syncwarp();                      // the slots are free again
+                if (next < ntiles) {
+                    issue_cells(Pn);
+                    ndpf_cp_async_commit();        // {cells(next)}
+                }
+            }
+        }
+    } else if (!PIPE) {
         for (long long tile = tile0; tile < ntiles; tile += tile_stride) {
             const long long w = tile * 32 + lane;
             double qv[N];

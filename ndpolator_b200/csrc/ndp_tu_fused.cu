@@ -8,7 +8,10 @@
 #endif
 // software pipeline inside a warp (plan of the next tile while this tile's cells are in flight): see k_fused
 #ifndef NDP_FUSED_PIPE
-#define NDP_FUSED_PIPE 2      // profiles/r02c_variants.jsonl: 8.93 ms per 2^27 C4 queries against 9.43 (PIPE 0) and 9.82 (PIPE 1)
+// 2..4 axes: PIPE 2 (profiles/r02c_variants.jsonl).  5 and 6 axes: PIPE 3 -- one query buffer; for 6 axes its smaller
+// footprint lets a third CTA fit on an SM (profiles/r02n_variants_pipe3.jsonl: C5 linear +9.7 %, C5 nearest +27 %,
+// C4 +2.1 %, C2 -1.4 % -- hence not for the small cells)
+#define NDP_FUSED_PIPE (NDP_FUSED_N >= 5 ? 3 : 2)
 #endif
 // resident CTAs per SM the kernel is compiled for (register budget 65536 / (128 * OCC); shared memory per
 // CTA: 4 warps x ndpf_warp_bytes)
@@ -16,9 +19,9 @@
 #if NDP_FUSED_N <= 4
 #define NDP_FUSED_OCC (NDP_FUSED_PIPE ? 5 : 6)
 #elif NDP_FUSED_N == 5
-#define NDP_FUSED_OCC (NDP_FUSED_PIPE == 1 ? 3 : (NDP_FUSED_PIPE == 2 ? 4 : 5))
+#define NDP_FUSED_OCC (NDP_FUSED_PIPE == 1 ? 3 : (NDP_FUSED_PIPE == 0 ? 5 : 4))
 #else
-#define NDP_FUSED_OCC (NDP_FUSED_PIPE ? 2 : 3)
+#define NDP_FUSED_OCC (NDP_FUSED_PIPE == 3 ? 3 : (NDP_FUSED_PIPE ? 2 : 3))
 #endif
 #endif
 

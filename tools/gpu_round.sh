@@ -24,7 +24,7 @@ ncu)
   timeout 300 $CMD > $OUT/${TAG}_ncu_plain.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
   echo "ncu launches rc=$?" | tee -a $OUT/${TAG}_status.txt
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fused -s 1 -c 2 -f -o $OUT/${TAG}_prof $CMD > $OUT/${TAG}_ncu_full.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fused -s 3 -c 2 -f -o $OUT/${TAG}_prof $CMD > $OUT/${TAG}_ncu_full.log 2>&1
   echo "ncu full rc=$?" | tee -a $OUT/${TAG}_status.txt ;;
 esac
 done
