@@ -117,6 +117,7 @@ struct ndpb_table {
     bool nsm_tried[3] = {false, false, false};
     int *nsm_offs[3] = {nullptr, nullptr, nullptr};
     uint32_t *nsm_ents[3] = {nullptr, nullptr, nullptr};
+    uint32_t *nsm_head[3] = {nullptr, nullptr, nullptr};
     NdpHcSlice hcs{};
     bool use_hc = false;                    // hypercube-mask bit <=> hypercube fully defined
     cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
@@ -275,7 +276,7 @@ extern "C" int ndpb_table_destroy(ndpb_table *t)
             cudaFree(set[m].d_desc);
         }
     for (auto &T : t->topo) { cudaFree(T.parent); cudaFree(T.depth); }
-    for (int geo = 0; geo < 3; geo++) { cudaFree(t->nsm_offs[geo]); cudaFree(t->nsm_ents[geo]); }
+    for (int geo = 0; geo < 3; geo++) { cudaFree(t->nsm_offs[geo]); cudaFree(t->nsm_ents[geo]); cudaFree(t->nsm_head[geo]); }
     for (auto &s : t->slot) free_slot(s);
     if (t->s_owned) cudaStreamDestroy(t->s_owned);
     if (t->s_in) cudaStreamDestroy(t->s_in);
@@ -383,13 +384,17 @@ static int ensure_nsm(ndpb_table *t, int geo)
     if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, offs, M.nregions + 1, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&total, offs + M.nregions, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    uint32_t *head = nullptr;
+    const size_t head_bytes = sizeof(uint32_t) * (size_t) M.nregions * nsm_head_words(M.ew);
     if (e == cudaSuccess) e = cudaMalloc(&ents, sizeof(uint32_t) * ((size_t) std::max(total, 1) * M.ew));
-    if (e == cudaSuccess) { M.offs = offs; e = ndp_launch_nsm_fill(M, ents, st); }
+    if (e == cudaSuccess) e = cudaMalloc(&head, head_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(head, 0, head_bytes, st);
+    if (e == cudaSuccess) { M.offs = offs; e = ndp_launch_nsm_fill(M, ents, head, st); }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(counts); cudaFree(tmp);
-    if (e != cudaSuccess) { cudaFree(offs); cudaFree(ents); CU(e); }
-    M.ents = ents;
-    t->nsm[geo] = M; t->nsm_offs[geo] = offs; t->nsm_ents[geo] = ents;
+    if (e != cudaSuccess) { cudaFree(offs); cudaFree(ents); cudaFree(head); CU(e); }
+    M.ents = ents; M.head = head;
+    t->nsm[geo] = M; t->nsm_offs[geo] = offs; t->nsm_ents[geo] = ents; t->nsm_head[geo] = head;
     return NDPB_OK;
 }
 
@@ -536,8 +541,8 @@ extern "C" int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t val
         CU(cudaDeviceSynchronize());
         t->opt_nsm_subcells = (int) value;
         for (int geo = 0; geo < 3; geo++) {          // maps are rebuilt lazily at the new resolution
-            cudaFree(t->nsm_offs[geo]); cudaFree(t->nsm_ents[geo]);
-            t->nsm_offs[geo] = nullptr; t->nsm_ents[geo] = nullptr;
+            cudaFree(t->nsm_offs[geo]); cudaFree(t->nsm_ents[geo]); cudaFree(t->nsm_head[geo]);
+            t->nsm_offs[geo] = nullptr; t->nsm_ents[geo] = nullptr; t->nsm_head[geo] = nullptr;
             t->nsm[geo] = NdpSiteMap{}; t->nsm_tried[geo] = false;
         }
         return NDPB_OK;

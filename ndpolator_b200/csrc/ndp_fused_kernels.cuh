@@ -673,15 +673,18 @@ __global__ void __launch_bounds__(128) k_nsm_count(const __grid_constant__ NdpSi
 }
 
 // pass 2: M.offs holds the exclusive scan of the counts; the candidates are recomputed and written
-__global__ void __launch_bounds__(128) k_nsm_fill(const __grid_constant__ NdpSiteMap M, uint32_t *ents)
+__global__ void __launch_bounds__(128) k_nsm_fill(const __grid_constant__ NdpSiteMap M, uint32_t *ents, uint32_t *head)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= M.nregions) return;
     const int beg = M.offs[r], n = M.offs[r + 1] - beg;
-    if (n == 0) return;
+    if (n == 0) return;                                  // head[] was zeroed: no candidate, the lattice search decides
     unsigned long long cand[NSM_KMAX];
     const int got = nsm_region_candidates(M, r, cand);
-    if (got == n) nsm_write_entries(M, cand, n, ents + (long long) beg * M.ew);
+    if (got == n) {
+        nsm_write_entries(M, cand, n, ents + (long long) beg * M.ew);
+        nsm_write_head(M, cand, n, beg, head + (long long) r * nsm_head_words(M.ew));
+    }
 }
 
 // *flag is cleared when component 0 of some basic vertex is NaN at one associated index but not at another

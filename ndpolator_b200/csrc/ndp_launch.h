@@ -21,5 +21,5 @@ NDP_FUSED_DECL(2) NDP_FUSED_DECL(3) NDP_FUSED_DECL(4) NDP_FUSED_DECL(5) NDP_FUSE
 #undef NDP_FUSED_DECL
 cudaError_t ndp_launch_slow(const SlowArgs &A, int blocks, size_t smem, cudaStream_t st);
 cudaError_t ndp_launch_nsm_count(const NdpSiteMap &M, int *counts, cudaStream_t st);
-cudaError_t ndp_launch_nsm_fill(const NdpSiteMap &M, uint32_t *ents, cudaStream_t st);
+cudaError_t ndp_launch_nsm_fill(const NdpSiteMap &M, uint32_t *ents, uint32_t *head, cudaStream_t st);
 cudaError_t ndp_launch_assoc_consistent(const double *grid, int nverts, long long per_vertex, int vdim, int *flag, int blocks, cudaStream_t st);

@@ -71,6 +71,8 @@ struct NdpSiteMap {
     int lo;                           // lowest site coordinate: 0 (vertices) or 1 (cells)
     const int *offs;                  // nregions + 1 entries
     const uint32_t *ents;
+    const uint32_t *head;             // per region 2 * ew + 2 words (16 / 32 bytes with padding): its first TWO candidates, its
+                                      // candidate count and the start of its list in ents: one load settles most regions
     const uint32_t *slice;            // the slice mask itself (level 0 of the reduced pyramid)
 };
 
@@ -264,6 +266,20 @@ NDP_HD void nsm_write_entries(const NdpSiteMap &M, const unsigned long long *can
         for (int w = 0; w < M.ew; w++) dst[i * M.ew + w] = (uint32_t) (cand[i] >> (32 * w));
 }
 
+// Words per region of the head table: ew == 1: c0, c1, count, beg (16 bytes); ew == 2: c0 (2), c1 (2), count, beg, 0, 0 (32 bytes).
+NDP_HD int nsm_head_words(int ew) { return ew == 1 ? 4 : 8; }
+
+// Writes one region's head: first two candidates, count, start of the region's list in ents.
+NDP_HD void nsm_write_head(const NdpSiteMap &M, const unsigned long long *cand, int n, int beg, uint32_t *dst)
+{
+    const unsigned long long c0 = n > 0 ? cand[0] : 0ull, c1 = n > 1 ? cand[1] : 0ull;
+    if (M.ew == 1) { dst[0] = (uint32_t) c0; dst[1] = (uint32_t) c1; dst[2] = (uint32_t) n; dst[3] = (uint32_t) beg; }
+    else {
+        dst[0] = (uint32_t) c0; dst[1] = (uint32_t) (c0 >> 32); dst[2] = (uint32_t) c1; dst[3] = (uint32_t) (c1 >> 32);
+        dst[4] = (uint32_t) n; dst[5] = (uint32_t) beg; dst[6] = 0u; dst[7] = 0u;
+    }
+}
+
 // int in [0, 2^31) -> double, exactly.  On the device: a bit pattern + one DADD instead of I2F.F64
 // (which runs on the slow conversion pipe); both give the same value.
 NDP_HD double nsm_i2d(int c)
@@ -385,7 +401,25 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
             }
         }
     }
-    const int beg = M.offs[region], end = M.offs[region + 1];
+    // one 16-byte load (two for two-word entries) gives the region's first two candidates, its candidate count and the
+    // start of its list: regions with at most two candidates -- nearly all -- need no dependent load
+    unsigned long long cand0, cand1;
+    int count, beg;
+    if (VS || M.ew == 1) {
+#if defined(__CUDA_ARCH__)
+        const ulonglong2 hv = *reinterpret_cast<const ulonglong2 *>(M.head + (long long) region * 4);     // one 128-bit load
+        const unsigned long long h0 = hv.x, h1 = hv.y;
+#else
+        const unsigned long long *hp = reinterpret_cast<const unsigned long long *>(M.head + (long long) region * 4);
+        const unsigned long long h0 = hp[0], h1 = hp[1];
+#endif
+        cand0 = h0 & 0xffffffffull; cand1 = h0 >> 32; count = (int) (h1 & 0xffffffffull); beg = (int) (h1 >> 32);
+    } else {
+        const unsigned long long *hp = reinterpret_cast<const unsigned long long *>(M.head + (long long) region * 8);
+        cand0 = hp[0]; cand1 = hp[1];
+        const unsigned long long h2 = hp[2];
+        count = (int) (h2 & 0xffffffffull); beg = (int) (h2 >> 32);
+    }
 #pragma unroll
     for (int a = 0; a < MM; a++) {
         if (a < nb) {
@@ -426,11 +460,14 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
     double bestd = 8.0 * NSM_TMAX;
     unsigned long long bestp = 0;
     bool tie = false;
-    const uint32_t *ep = M.ents + (long long) beg * (VS ? 1 : M.ew);
-    for (int e = beg; e < end; e++) {
-        unsigned long long p = ep[0];
-        if (!VS && M.ew > 1) p |= (unsigned long long) ep[1] << 32;
-        ep += VS ? 1 : M.ew;
+    const uint32_t *ep = M.ents + (long long) (beg + 2) * (VS ? 1 : M.ew);
+    for (int e = 0; e < count; e++) {
+        unsigned long long p = e == 0 ? cand0 : cand1;
+        if (e > 1) {
+            p = ep[0];
+            if (!VS && M.ew > 1) p |= (unsigned long long) ep[1] << 32;
+            ep += VS ? 1 : M.ew;
+        }
         // the reference's sum, in its axis order: closed-form axes contribute their fixed term (associated axes
         // and axes beyond nbasic add +0.0, which changes nothing)
         double d = 0.0;

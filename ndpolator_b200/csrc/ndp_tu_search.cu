@@ -74,9 +74,9 @@ cudaError_t ndp_launch_nsm_count(const NdpSiteMap &M, int *counts, cudaStream_t 
     return cudaGetLastError();
 }
 
-cudaError_t ndp_launch_nsm_fill(const NdpSiteMap &M, uint32_t *ents, cudaStream_t st)
+cudaError_t ndp_launch_nsm_fill(const NdpSiteMap &M, uint32_t *ents, uint32_t *head, cudaStream_t st)
 {
-    k_nsm_fill<<<(M.nregions + 127) / 128, 128, 0, st>>>(M, ents);
+    k_nsm_fill<<<(M.nregions + 127) / 128, 128, 0, st>>>(M, ents, head);
     return cudaGetLastError();
 }
 

@@ -31,6 +31,7 @@ struct HsTable {
     NdpSiteMap nsm[3];                       // nearest-site maps per geometry (ndp_nsm.cuh)
     std::vector<int> nsm_offs[3];
     std::vector<uint32_t> nsm_ents[3];
+    std::vector<uint64_t> nsm_head[3];       // 8-byte aligned storage of the per-region heads
     NdpHcSlice hcs;
     bool use_hc = false;                     // hypercube-mask bit <=> fully defined hypercube (see build_fused)
     NdpBlocks B{};                           // blocked copy of a scalar table (mirrors k_build_blocks); order 0 = none
@@ -169,6 +170,8 @@ static void build_fused(HsTable *t)
         std::vector<int> &offs = t->nsm_offs[geo];
         std::vector<uint32_t> &ents = t->nsm_ents[geo];
         offs.assign(M.nregions + 1, 0);
+        std::vector<uint64_t> &head = t->nsm_head[geo];
+        head.assign((size_t) M.nregions * nsm_head_words(M.ew) / 2, 0);
         for (int r = 0; r < M.nregions; r++) {
             int n = nsm_region_candidates(M, r, cand.data());
             if (n < 0) n = 0;
@@ -176,9 +179,10 @@ static void build_fused(HsTable *t)
             const size_t at = ents.size();
             ents.resize(at + (size_t) n * M.ew);
             nsm_write_entries(M, cand.data(), n, ents.data() + at);
+            if (n > 0) nsm_write_head(M, cand.data(), n, offs[r], reinterpret_cast<uint32_t *>(head.data()) + (size_t) r * nsm_head_words(M.ew));
         }
         if (ents.empty()) ents.push_back(0);
-        M.offs = offs.data(); M.ents = ents.data();
+        M.offs = offs.data(); M.ents = ents.data(); M.head = reinterpret_cast<const uint32_t *>(head.data());
     }
     const NdpPyramid &R = t->red[1].dev;
     t->hcs = NdpHcSlice{};

@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--queries', type=int, required=True, help='queries per launch (per-tile = per 32 queries)')
     ap.add_argument('--top', type=int, default=50)
     ap.add_argument('--launch', type=int, default=0, help='which captured launch of the kernel')
+    ap.add_argument('--stalls', action='store_true', help='also rank source lines by warp-stall samples (with the reasons)')
     args, defines = ap.parse_known_args()
     from ndpolator_b200 import build
     tmp = tempfile.mkdtemp()
@@ -83,6 +84,31 @@ def main():
             if os.path.exists(path):
                 src = open(path).read().split('\n')[k[1] - 1].strip()[:100]
         print(f'{v / tiles:8.1f} {aggt[k] / max(v, 1):5.1f}  {k[0] if k else "?"}:{k[1] if k else 0}  {src}')
+    if args.stalls:
+        cols = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
+        per_line, reasons = collections.Counter(), collections.defaultdict(collections.Counter)
+        by_off = {int(r[ia], 16) - base: r for r in blk['rows']}
+        for off, cur, _ in insts:
+            r = by_off.get(off)
+            if r is None:
+                continue
+            for i, name in cols:
+                try:
+                    v = int(r[i])
+                except ValueError:
+                    v = 0
+                per_line[cur] += v
+                reasons[cur][name] += v
+        tot = sum(per_line.values()) or 1
+        print(f'\nwarp-stall samples by source line (total {tot}):')
+        for k, v in per_line.most_common(args.top):
+            src = ''
+            if k:
+                path = os.path.join(build.CSRC, k[0])
+                if os.path.exists(path):
+                    src = open(path).read().split('\n')[k[1] - 1].strip()[:90]
+            why = ', '.join(f'{n} {100 * c / max(v, 1):.0f}%' for n, c in reasons[k].most_common(3))
+            print(f'{100 * v / tot:6.2f}%  {k[0] if k else "?"}:{k[1] if k else 0}  [{why}]  {src}')
 
 
 if __name__ == '__main__':
