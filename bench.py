@@ -505,6 +505,9 @@ def run_b200(args):
             main_s = acc['main_ns'] / 1e9 / K
             cell_bytes = (1 << w.naxes) * w.vdim * 8
             out_bytes = w.vdim * 8 + 8
+            table_bytes = w.vdim * 8
+            for ax in w.axes:
+                table_bytes *= len(ax)
             fused = acc['fused'] == K
             if fused:
                 # k_fused, per launch: every query row read (naxes*8), ONE gather per query -- its own cell, or for
@@ -539,12 +542,17 @@ def run_b200(args):
                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                     'frac': (achieved / peak) if achieved else None,
                     'traffic': traffic,
-                    'traffic_source': ('profiles/r02_traffic.json (ncu --set full on these sources, scaled to this batch)'
+                'note': ('table larger than L2: every gather is HBM traffic' if table_bytes > 126 * 2**20 else
+                         'table fits in the 126 MB L2: gathers are served from L2, so the fraction of the HBM roofline can exceed 1'),
+                'traffic_source': ('profiles/r02_traffic.json (ncu --set full on these sources, scaled to this batch)'
                                        if traffic else 'no ncu capture of exactly these kernel sources / this workload'),
                     'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': main_bytes, 'avg_launch_ms': main_s * 1e3,
                     'whole_step': {'achieved': step_gbs, 'frac': step_gbs / peak,
-                                   'note': 'queries/step x SURVEY 8d bytes/query over the whole step (all kernels)'},
+                                   'note': 'queries/step x SURVEY 8d bytes/query (query + full 2^n cell + outputs for EVERY query) over '
+                                           'the whole step, all kernels; frac_algorithmic counts what this method really has to move '
+                                           "(a 'nearest'-extrapolated query fetches one vertex, not a cell)",
+                                   'frac_algorithmic': main_bytes / (ms_total / 1e3 / K) / 1e9 / peak},
                     'phase_ms_per_step': {'k_main': acc['main_ns'] / 1e6 / K, 'k_search': acc['search_ns'] / 1e6 / K,
                                           'k_finish': acc['finish_ns'] / 1e6 / K},
                 },

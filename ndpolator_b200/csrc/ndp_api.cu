@@ -901,7 +901,9 @@ static int launch_fused(ndpb_table *t, Slot &s, const double *q, long long n, in
         ndp_blocks_setup(g, t->block_order, A.B);
         for (int a = 0; a < g.naxes; a++) { A.g.cstride[a] = A.B.stride[a]; A.g.cstride32[a] = g.small ? (int) A.B.stride[a] : 0; }
     }
-    A.H = t->hcs; A.hc_in_smem = t->hcs.nwords * sizeof(uint32_t) <= 8 * 1024;
+    // the hypercube-mask slice sits in shared memory when small (<= 3 axes have the room for 16 KB at full occupancy)
+    const size_t hc_limit = (g.naxes <= 3 ? 16 : 8) * 1024;
+    A.H = t->hcs; A.hc_in_smem = t->hcs.nwords * sizeof(uint32_t) <= hc_limit;
     if (method != NDPB_METHOD_NONE) A.M = t->nsm[nsm_geo_of_mode(mode)];
     A.slowlist = s.list; A.ctr = s.ctr;
     if (g.vdim > 1) {

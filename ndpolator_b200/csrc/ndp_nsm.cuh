@@ -415,9 +415,16 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
 #endif
         cand0 = h0 & 0xffffffffull; cand1 = h0 >> 32; count = (int) (h1 & 0xffffffffull); beg = (int) (h1 >> 32);
     } else {
+#if defined(__CUDA_ARCH__)
+        const ulonglong2 *hq = reinterpret_cast<const ulonglong2 *>(M.head + (long long) region * 8);     // two 128-bit loads
+        const ulonglong2 ha = hq[0], hb = hq[1];
+        cand0 = ha.x; cand1 = ha.y;
+        const unsigned long long h2 = hb.x;
+#else
         const unsigned long long *hp = reinterpret_cast<const unsigned long long *>(M.head + (long long) region * 8);
         cand0 = hp[0]; cand1 = hp[1];
         const unsigned long long h2 = hp[2];
+#endif
         count = (int) (h2 & 0xffffffffull); beg = (int) (h2 >> 32);
     }
 #pragma unroll
