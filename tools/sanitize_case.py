@@ -31,6 +31,19 @@ for name, axes, nbasic, grid in build_cases():
         T.distance(q)
         idx, flg, nrm = T.find(q)
         T.hypercubes_raw(nrm, idx, flg)
+        for m in (0, 1, 2):
+            T.ndpolate_cached(nrm, idx, flg, m, 0)           # k_fused<..., CACHED> / k_fused_vec / k_slow on cached products
+        if len(axes) <= 6 and grid.shape[-1] == 1 and gather != 1:
+            for order in range(1, len(axes) + 1):            # every blocked layout k_fused gathers from
+                T.set_option('block_order', order)
+                T.ndpolate(q, 2, 0)
+        import torch
+        qd = torch.as_tensor(q, device='cuda')
+        T.set_option('async', 1)                             # stream-ordered calls
+        outs = [T.ndpolate(qd, m, 0) for m in (0, 1, 2)]
+        T.sync()
+        T.set_option('async', 0)
+        del outs
         T.masks()
         T.tree_topology(1)
         T.close()
