@@ -99,6 +99,14 @@ NDP_HD void ndp_fused_plan(const NdpGeom &g, const NdpHcSlice &H, const uint32_t
 {
     constexpr int MM = N ? N : NDP_MAX_AXES;
     const int n = N ? N : g.naxes;
+    // the head of the query's site-map region is requested first, for every query: its L2 round trip then runs
+    // beside everything up to the candidate loop (and costs in-grid lanes nothing: they would idle meanwhile)
+    NdpQuery Q;
+    NdpNsmProbe pr;
+    if (METHOD != NDP_M_NONE) {
+        ndp_make_query_n<N>(g, idx, nrm, Q);
+        ndp_nsm_probe<N, MODE, VS>(g, M, Q, pr);
+    }
     const bool oob = ndp_classify<N>(g, flg, nrm, P.pin, P.sel);
     P.dist = 0.0;
     P.searched = 0;
@@ -120,10 +128,8 @@ NDP_HD void ndp_fused_plan(const NdpGeom &g, const NdpHcSlice &H, const uint32_t
     }
     if (METHOD == NDP_M_NONE) { P.kind = NDP_PLAN_NAN; return; }
     P.searched = 1;
-    NdpQuery Q;
-    ndp_make_query_n<N>(g, idx, nrm, Q);
     NdpHit hit;
-    if (!ndp_nsm_search<N, MODE, VS>(g, M, Q, hit)) { P.kind = NDP_PLAN_SLOW; return; }
+    if (!ndp_nsm_search<N, MODE, VS>(g, M, Q, pr, hit)) { P.kind = NDP_PLAN_SLOW; return; }
     int coords[MM];
 #pragma unroll
     for (int a = 0; a < MM; a++) if (a < n) coords[a] = a < g.nbasic ? hit.coords[a] : Q.acoord[a];

@@ -369,8 +369,65 @@ NDP_HD double ndp_reported_dist_n(const NdpGeom &g, const NdpQuery &Q, const int
 // what the reference's search returns (hit.vertex is filled for the full-scan modes only, whose tie rule
 // needs it).  false: take the lattice search.
 // ---------------------------------------------------------------------------
+// What the probe leaves for the search: the region's head, loaded as early as the plan allows so that its L2
+// round trip is covered by the classification and the closed-form axes.
+struct NdpNsmProbe {
+    unsigned long long cand0, cand1;
+    int count, beg;
+    bool ok;                           // no NaN on a basic axis, every variant axis inside the map's bands
+};
+
+// Region of the query on the variant axes + the load of the region's head.  Valid for ANY imported query (the
+// region index is clamped into the map), so the plan issues it before it knows whether the query needs a search.
 template <int N, int MODE, int VS = 0>
-NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery &Q, NdpHit &hit)
+NDP_HD void ndp_nsm_probe(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery &Q, NdpNsmProbe &pr)
+{
+    constexpr int MM = N ? N : NDP_MAX_AXES;
+    const int nb = g.nbasic;
+    int region = 0;
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < MM; a++) {
+        if (a < nb) {
+            const bool nan = !(Q.qc[a] == Q.qc[a]);
+            ok &= !nan;
+            const int j = VS ? (a < 2 ? a : -1) : M.jof[a];
+            if (j >= 0) {
+                const int r = nsm_region_of(M.S, g.len[a], nan ? 0.0 : Q.qc[a]);
+                ok &= r >= 0;
+                region += (r < 0 ? 0 : r) * M.rstride[j];
+            }
+        }
+    }
+    pr.ok = ok;
+    // one 16-byte load (two for two-word entries) gives the region's first two candidates, its candidate count and the
+    // start of its list: regions with at most two candidates -- nearly all -- need no dependent load
+    if (VS || M.ew == 1) {
+#if defined(__CUDA_ARCH__)
+        const ulonglong2 hv = *reinterpret_cast<const ulonglong2 *>(M.head + (long long) region * 4);     // one 128-bit load
+        const unsigned long long h0 = hv.x, h1 = hv.y;
+#else
+        const unsigned long long *hp = reinterpret_cast<const unsigned long long *>(M.head + (long long) region * 4);
+        const unsigned long long h0 = hp[0], h1 = hp[1];
+#endif
+        pr.cand0 = h0 & 0xffffffffull; pr.cand1 = h0 >> 32; pr.count = (int) (h1 & 0xffffffffull); pr.beg = (int) (h1 >> 32);
+    } else {
+#if defined(__CUDA_ARCH__)
+        const ulonglong2 *hq = reinterpret_cast<const ulonglong2 *>(M.head + (long long) region * 8);     // two 128-bit loads
+        const ulonglong2 ha = hq[0], hb = hq[1];
+        pr.cand0 = ha.x; pr.cand1 = ha.y;
+        const unsigned long long h2 = hb.x;
+#else
+        const unsigned long long *hp = reinterpret_cast<const unsigned long long *>(M.head + (long long) region * 8);
+        pr.cand0 = hp[0]; pr.cand1 = hp[1];
+        const unsigned long long h2 = hp[2];
+#endif
+        pr.count = (int) (h2 & 0xffffffffull); pr.beg = (int) (h2 >> 32);
+    }
+}
+
+template <int N, int MODE, int VS = 0>
+NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery &Q, const NdpNsmProbe &pr, NdpHit &hit)
 {
     constexpr int MM = N ? N : NDP_MAX_AXES;
     constexpr int mode = MODE;
@@ -381,52 +438,17 @@ NDP_HD bool ndp_nsm_search(const NdpGeom &g, const NdpSiteMap &M, const NdpQuery
     const int nb = g.nbasic;
     double t0[MM];                     // closed-form axes: the term of the chosen coordinate (0 elsewhere)
     int fix[MM];
-    int region = 0, base = 0;
-    bool ok = true;
+    int base = 0;
+    bool ok = pr.ok;
     bool wide = true;                  // every closed-form axis has the NSM_EPS margin (else only NSM_EPS_NEAR)
     double qa[MM];
-    // variant axes first: the region, so that the loads of its candidate range are in flight during the rest
 #pragma unroll
     for (int a = 0; a < MM; a++) {
-        t0[a] = 0.0; fix[a] = 0; qa[a] = 0.0;
-        if (a < nb) {
-            const bool nan = !(Q.qc[a] == Q.qc[a]);
-            qa[a] = nan ? 0.0 : Q.qc[a];
-            ok &= !nan;
-            const int j = VS ? (a < 2 ? a : -1) : M.jof[a];
-            if (j >= 0) {
-                const int r = nsm_region_of(M.S, g.len[a], qa[a]);
-                ok &= r >= 0;
-                region += (r < 0 ? 0 : r) * M.rstride[j];
-            }
-        }
+        t0[a] = 0.0; fix[a] = 0;
+        qa[a] = (a < nb && Q.qc[a] == Q.qc[a]) ? Q.qc[a] : 0.0;
     }
-    // one 16-byte load (two for two-word entries) gives the region's first two candidates, its candidate count and the
-    // start of its list: regions with at most two candidates -- nearly all -- need no dependent load
-    unsigned long long cand0, cand1;
-    int count, beg;
-    if (VS || M.ew == 1) {
-#if defined(__CUDA_ARCH__)
-        const ulonglong2 hv = *reinterpret_cast<const ulonglong2 *>(M.head + (long long) region * 4);     // one 128-bit load
-        const unsigned long long h0 = hv.x, h1 = hv.y;
-#else
-        const unsigned long long *hp = reinterpret_cast<const unsigned long long *>(M.head + (long long) region * 4);
-        const unsigned long long h0 = hp[0], h1 = hp[1];
-#endif
-        cand0 = h0 & 0xffffffffull; cand1 = h0 >> 32; count = (int) (h1 & 0xffffffffull); beg = (int) (h1 >> 32);
-    } else {
-#if defined(__CUDA_ARCH__)
-        const ulonglong2 *hq = reinterpret_cast<const ulonglong2 *>(M.head + (long long) region * 8);     // two 128-bit loads
-        const ulonglong2 ha = hq[0], hb = hq[1];
-        cand0 = ha.x; cand1 = ha.y;
-        const unsigned long long h2 = hb.x;
-#else
-        const unsigned long long *hp = reinterpret_cast<const unsigned long long *>(M.head + (long long) region * 8);
-        cand0 = hp[0]; cand1 = hp[1];
-        const unsigned long long h2 = hp[2];
-#endif
-        count = (int) (h2 & 0xffffffffull); beg = (int) (h2 >> 32);
-    }
+    const unsigned long long cand0 = pr.cand0, cand1 = pr.cand1;
+    const int count = pr.count, beg = pr.beg;
 #pragma unroll
     for (int a = 0; a < MM; a++) {
         if (a < nb) {
