@@ -19,7 +19,9 @@
 #include "ndp_fused.cuh"
 #include "ndp_kernels.cuh"
 
-#define NDP_FUSED_WARPS 4
+#ifndef NDP_FUSED_WARPS
+#define NDP_FUSED_WARPS 4       // warps per CTA (tuning variants: -DNDP_FUSED_WARPS=3 -DNDP_FUSED_OCC=6 = 18 warps per SM at 112 registers)
+#endif
 #ifndef NDP_FUSED_TMAQ
 #define NDP_FUSED_TMAQ 1      // query tiles by TMA bulk copy + mbarrier (0: per-lane cp.async pieces; same results)
 #endif
@@ -147,8 +149,13 @@ struct NdpFusedItem {
 // VS: see ndp_nsm_search.
 // CACHED: the import products of the queries (ndpb_find: indices, flags, normed) are read instead of the query
 //         points -- the hypercube-caching path (ndpb_ndpolate_cached); runs the PIPE 0 loop.
+#ifdef NDP_FUSED_MAXNREG       // tuning variants: an explicit register cap instead of the one launch bounds imply
+#define NDP_FUSED_BOUNDS(occ) __maxnreg__(NDP_FUSED_MAXNREG)
+#else
+#define NDP_FUSED_BOUNDS(occ) __launch_bounds__(NDP_FUSED_WARPS * 32, occ)
+#endif
 template <int N, int METHOD, int MODE, int OCC, int VS, int PIPE_, int CACHED = 0>
-__global__ void __launch_bounds__(NDP_FUSED_WARPS * 32, OCC) k_fused(const __grid_constant__ FusedArgs A)
+__global__ void NDP_FUSED_BOUNDS(OCC) k_fused(const __grid_constant__ FusedArgs A)
 {
     constexpr int PIPE = CACHED ? 0 : PIPE_;
     constexpr unsigned CELL_BYTES = 8u << N;
