@@ -5,7 +5,4 @@ bash tools/gpu_round.sh $TAG tests bench ncu
 bash tools/bench_configs.sh $TAG all
 for wl in C4 C5 C3; do timeout 300 python tools/bench_cached.py --workload $wl >> $OUT/${TAG}_cached.jsonl 2>> $OUT/${TAG}_cached.err; done; cat $OUT/${TAG}_cached.jsonl
 bash tools/gpu_exp.sh $TAG "--scale 60" "--spacing 0.3" "--api-mode async --batch 8388608"
-# compute-sanitizer (closed on this pool in round 1: try, keep whatever it says)
-NDPB_SANITIZE_QUICK=1 timeout 400 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_case.py > $OUT/${TAG}_sanitizer.log 2>&1; echo "sanitizer rc=$?" | tee -a $OUT/${TAG}_sanitizer.log
-tail -5 $OUT/${TAG}_sanitizer.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/${TAG}_smoke.log
