@@ -117,6 +117,12 @@ __device__ __forceinline__ void ndpf_bulk_g2s(unsigned dst, const void *src, uns
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// A bulk copy (async proxy) that refills a shared-memory buffer must not be issued while a lane's reads of that buffer
+// are still in flight.  Program order issues the reads first, but only a register dependency makes the warp WAIT for
+// their data (a refill placed right after the bare loads was measured to overtake them under load: whole tiles of
+// wrong rows, profiles/r02w).  Passing a value computed from everything that was read through this empty asm is
+// that dependency; every lane passes it before the (converged) warp reaches the copy.
+__device__ __forceinline__ void ndpf_settle(int v) { asm volatile("" ::"r"(v) : "memory"); }
 __device__ __forceinline__ void ndpf_mbar_wait(unsigned bar, unsigned parity)
 {
     asm volatile("{\n\t.reg .pred p;\n\tNDPF_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra NDPF_DONE;\n\t"
@@ -313,6 +319,7 @@ __global__ void NDP_FUSED_BOUNDS(OCC) k_fused(const __grid_constant__ FusedArgs 
             __syncwarp();
             NdpPlan<N> P;
             make_plan(tile0, reinterpret_cast<const double *>(s_q) + lane * N, P);
+            ndpf_settle(P.kind);
             __syncwarp();                          // every lane has read its row of the query buffer
             prefetch_q1(tile0 + tile_stride);
             ndpf_cp_async_commit();                // {q(t1)}
@@ -332,6 +339,7 @@ __global__ void NDP_FUSED_BOUNDS(OCC) k_fused(const __grid_constant__ FusedArgs 
                     __syncwarp();
                     make_plan(next, reinterpret_cast<const double *>(s_q) + lane * N, Pn);
                     item_of(Pn, itn);
+                    ndpf_settle(Pn.kind);
                     __syncwarp();                  // the query buffer has been read by every lane
                     prefetch_q1(next + tile_stride);
                     ndpf_cp_async_commit();        // {q(next + 1)}: now the newest group, cells(tile) the one before
@@ -436,6 +444,7 @@ __global__ void NDP_FUSED_BOUNDS(OCC) k_fused(const __grid_constant__ FusedArgs 
             __syncwarp();
             NdpPlan<N> P;
             make_plan(tile0, reinterpret_cast<const double *>(s_q) + lane * N, P);
+            ndpf_settle(P.kind);
             __syncwarp();                          // every lane has read its row of query buffer 0
             issue_cells(P);
             prefetch_q(tile0 + 2 * tile_stride, 0);
@@ -457,6 +466,7 @@ __global__ void NDP_FUSED_BOUNDS(OCC) k_fused(const __grid_constant__ FusedArgs 
                     __syncwarp();
                     make_plan(next, reinterpret_cast<const double *>(s_q + (unsigned) (cur ^ 1) * QTILE) + lane * N, Pn);
                     item_of(Pn, itn);
+                    ndpf_settle(Pn.kind);
                     if (PIPE == 1) save_item(cur ^ 1, itn);
                 }
                 ndpf_cp_async_wait0();
