@@ -37,6 +37,9 @@ def parse():
     ap.add_argument('--workload', default='C4')
     ap.add_argument('--scale', type=int, default=None, help='ticks per axis (default: the size BASELINE.json names)')
     ap.add_argument('--mix', default='near', choices=['near', 'deep'])
+    ap.add_argument('--variant', default=None, choices=[None, 'iid', 'allbasic'],
+                    help="SURVEY 8d variants: 'iid' = C4 with i.i.d. 30 %% voids (mask depends on all axes, ~100 %% off-grid), "
+                         "'allbasic' = C3 with mu as a fourth basic axis")
     ap.add_argument('--spacing', type=float, default=None,
                     help='tick spacing of the synthetic axes (default: 1, the integers); e.g. 0.3 exercises the general '
                          'index search with IEEE divisions instead of the exact power-of-two-spacing multiply')
@@ -178,7 +181,7 @@ def cpu_reference_run(args, steps, warmup):
     from oracle import oracle as orc
     kind = 'reference' if orc.have('reference') else 'port'
     scale = cpu_scale_of(args)
-    w = synth.workload(args.workload, scale, mix=args.mix, n_queries=args.cpu_queries, spacing=args.spacing)
+    w = synth.workload(args.workload, scale, mix=args.mix, n_queries=args.cpu_queries, spacing=args.spacing, variant=args.variant)
     method = METHODS[args.method or w.method]
     search = SEARCHES[args.search]
     cores = os.cpu_count() or 1
@@ -217,7 +220,7 @@ def cpu_reference_run(args, steps, warmup):
     finally:
         _POOL_STATE = None
     grid_txt = 'x'.join(str(len(a)) for a in w.axes)
-    full = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing)
+    full = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing, variant=args.variant)
     subst = ('' if len(full.axes[0]) == len(w.axes[0]) else
              f' -- SUBSTITUTED for the {"x".join(str(len(a)) for a in full.axes)} grid, whose reference kd-tree takes ~12 min '
              f'and ~8 GB per process to build (BASELINE.md 4.5)')
@@ -272,7 +275,7 @@ def batch_of(args, w, ws):
 
 def workload_config(args):
     from ndpolator_b200 import synth
-    w = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing)
+    w = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing, variant=args.variant)
     B, scaling = batch_of(args, w, max(1, args.gpus))
     nbuf = 1 if B * w.naxes * 8 >= (1 << 30) else 2
     return {
@@ -346,7 +349,7 @@ def run_b200(args):
     if ws > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    w = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing)
+    w = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing, variant=args.variant)
     method = METHODS[args.method or w.method]
     search = SEARCHES[args.search]
     B, scaling = batch_of(args, w, ws)
@@ -605,7 +608,7 @@ def run_inprocess(args):
     from ndpolator_b200 import synth
     from ndpolator_b200.cndpolator import Group, Table
     n_dev = args.gpus
-    w = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing)
+    w = synth.workload(args.workload, args.scale, mix=args.mix, spacing=args.spacing, variant=args.variant)
     method = METHODS[args.method or w.method]
     search = SEARCHES[args.search]
     policy = interleave_host_memory()

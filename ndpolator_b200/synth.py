@@ -280,12 +280,26 @@ _QUERIES = {'C1': _q_box, 'C2': _q_box, 'C3': _q_corner, 'C4': _q_corner, 'C5': 
 
 
 def workload(name: str, scale: int | None = None, mix: str = 'near', n_queries: int | None = None,
-             spacing: float | None = None) -> Workload:
+             spacing: float | None = None, variant: str | None = None) -> Workload:
     """name in {'C1','C2','C3','C4','C5'}.  `scale` shrinks the per-axis tick count for
     tests (None = the size BASELINE.json names); the generated name records it ('C4@12').
     `spacing` (C2, C4, C5): ticks 1.7 + spacing * i instead of the integers 0..L-1 -- a spacing that is not a
     power of two takes the kernels' general index search (IEEE division) instead of the exact-multiply one."""
     tag = name if scale is None else f'{name}@{scale}'
+    if variant is not None:
+        # SURVEY 8d variants: 'iid' (C4): i.i.d. voids u(405, v) < 0.3 instead of the structured corner -- 0.7^32 = 1e-5 of
+        # the hypercubes are fully defined, ~100 % of the queries extrapolate and the mask depends on all five axes;
+        # 'allbasic' (C3): mu taken as a fourth basic axis (nbasic = 4)
+        w = workload(name, scale, mix, n_queries, spacing)
+        if variant == 'iid' and name == 'C4':
+            w.extra = {'iid_void': 0.3, 'void_seed': 405}
+        elif variant == 'allbasic' and name == 'C3':
+            w.basic_axes = w.basic_axes + w.associated_axes
+            w.associated_axes = None
+        else:
+            raise ValueError(f'variant {variant!r} does not apply to {name}')
+        w.name = f'{w.name}/{variant}'
+        return w
     if spacing is not None:
         w = workload(name, scale, mix, n_queries)
         if name not in ('C2', 'C4', 'C5'):

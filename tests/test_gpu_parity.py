@@ -299,6 +299,27 @@ def test_baseline_configs_scaled_vs_oracle(spec, fused_off):
     T.close()
 
 
+@pytest.mark.parametrize('spec', [('C4', 9, 'iid', 40000), ('C3', 24, 'allbasic', 40000)], ids=lambda s: f'{s[0]}@{s[1]}-{s[2]}')
+def test_survey_variants_vs_oracle(spec):
+    """SURVEY 8d variants: C4 with i.i.d. 30 % voids (the mask depends on all five axes -- no nearest-site map, the
+    three-pass path with the exact lattice search; ~100 % of the queries extrapolate, the hypercube mask is nearly
+    empty) and C3 with mu as a fourth basic axis."""
+    from ndpolator_b200 import synth
+    name, scale, variant, n = spec
+    w = synth.workload(name, scale, n_queries=n, variant=variant)
+    grid, q = w.grid(), w.queries(0, n)
+    nb = len(w.basic_axes)
+    O = Oracle('port', w.axes, grid, nb)
+    T = _table(w.axes, grid, nb)
+    for m in (0, 1, 2):
+        a, b = O.ndpolate(q, m, 0, threads=os.cpu_count() or 1), T.ndpolate(q, m, 0)
+        assert_same_bits(a[0], b[0], f'{w.name} interps method {m}')
+        assert_same_bits(a[1], b[1], f'{w.name} dists method {m}')
+    if variant == 'iid':
+        assert T.stat('fused') == 0 and T.stat('variant_axes_linear') == 5
+    T.close()
+
+
 def test_c4_full_size_properties():
     """BASELINE.json's headline configuration at full size (40^5 grid, 819 MB; cell-major
     copy 23 GB): size-independent properties, plus a small sub-sample pinned to the oracle
