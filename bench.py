@@ -65,6 +65,10 @@ def parse():
                          "semantics), 'async' = stream-ordered calls (table option async=1) and ONE ndpb_table_sync after the K "
                          "steps, inside the timed region; auto = async for steps of at most 2^24 queries per GPU, where the "
                          "per-call host round trip is a visible share of the step")
+    ap.add_argument('--presort', action='store_true',
+                    help='experiment (SURVEY 8 f3): order each device-resident batch by the cell its query falls into before '
+                         'timing -- the ceiling of what a query-binning front end could give the gather; the time of the '
+                         'sort itself (torch.sort of the cell keys + the row gather) is reported as presort_ms')
     ap.add_argument('--inprocess', action='store_true',
                     help='ONE process, --gpus N devices through ndpb_group (one ndpolate call split over N GPUs): end-to-end '
                          'from pinned host arrays only; launch with plain python, not torchrun')
@@ -385,6 +389,26 @@ def run_b200(args):
             torch.cuda.empty_cache()
         # per-rank, per-buffer distinct rows of the global synthetic batch
         qs = [gen_queries(w, (b * ws + rank) * B, B, dev) for b in range(nbuf)]
+        presort_ms = None
+        if args.presort:
+            lo = torch.as_tensor([a[0] for a in w.axes], dtype=torch.float64, device=dev)
+            step = torch.as_tensor([(a[-1] - a[0]) / (len(a) - 1) for a in w.axes], dtype=torch.float64, device=dev)
+            ncell = torch.as_tensor([len(a) - 1 for a in w.axes], dtype=torch.int64, device=dev)
+            for b in range(nbuf):
+                torch.cuda.synchronize()
+                t_sort = time.perf_counter()
+                key = torch.zeros(B, dtype=torch.int64, device=dev)
+                for a in range(w.naxes):                   # cell number of the (clamped) query, axis 0 most significant
+                    c = ((qs[b][:, a] - lo[a]) / step[a]).floor_().clamp_(0, float(ncell[a].item() - 1)).to(torch.int64)
+                    key.mul_(int(ncell[a].item())).add_(c)
+                    del c
+                order = torch.sort(key).indices
+                del key
+                qs[b] = qs[b][order]
+                del order
+                torch.cuda.synchronize()
+                presort_ms = (time.perf_counter() - t_sort) * 1e3
+            torch.cuda.empty_cache()
         interps = torch.empty((B, w.vdim), dtype=torch.float64, device=dev)
         dists = torch.empty((B, 1), dtype=torch.float64, device=dev)
         stream = torch.cuda.Stream(dev)                # kernels and timing events share this stream
@@ -571,6 +595,10 @@ def run_b200(args):
                                   'queries incl. the lazy nearest-site map (the reference builds its kd-tree there)'},
                 'checksum': checksum,
             }
+            if presort_ms is not None:
+                line['presort'] = {'presort_ms_per_batch': presort_ms,
+                                   'note': 'queries ordered by cell before the timed region (torch: cell keys, sort, row gather); '
+                                           'value / ms_per_step do NOT include it'}
             if ws == 1 and not args.no_cpu_baseline and sweep_total is None:
                 try:
                     cb = cpu_reference_run(args, steps=2, warmup=1)

@@ -161,7 +161,9 @@ int ndpb_table_set_option(ndpb_table *t, const char *key, int64_t value);
  * "main_ns" / "search_ns" / "finish_ns" device time (CUDA events) of the gather kernel
  * (fused or staged), of the search / slow-list kernels and of the extrapolation finish,
  * "nsm_regions_nearest" / "nsm_regions_linear" regions of the nearest-site maps built so
- * far, "variant_axes_*", "tree_levels_*".  Unknown keys return -1. */
+ * far, "variant_axes_*", "tree_levels_*", "mask_count_nearest" / "mask_count_linear" set vertices of the vertex /
+ * hypercube mask, "sparse_search_*" (0/1: that mask is searched by scoring its few set vertices, k_search_sparse).
+ * Unknown keys return -1. */
 int64_t ndpb_table_stat(const ndpb_table *t, const char *key);
 
 /* ---- one call, several GPUs -------------------------------------------------------------------

@@ -112,6 +112,8 @@ struct ndpb_table {
     Pyramid pyr[2];                         // [0] vmask, [1] hcmask: over the whole basic lattice
     Pyramid red[2];                         // the same masks over their variant axes only
     Topology topo[2];
+    int *sparse_ids[2] = {nullptr, nullptr};   // ascending ids of a SPARSE mask's set vertices (lazy; see sparse_ready)
+    bool sparse_tried[2] = {false, false};
     // fused path (ndp_fused_kernels.cuh): nearest-site maps per geometry (lazy), hypercube-mask slice
     NdpSiteMap nsm[3]{};
     bool nsm_tried[3] = {false, false, false};
@@ -191,14 +193,17 @@ static int build_pyramid(ndpb_table *t, Pyramid &P, uint32_t *level0, int nvar, 
     uint32_t top = 0;
     int first = INT_MAX;
     if (full) {
-        int *d_first = nullptr;
-        CU(cudaMalloc(&d_first, sizeof(int)));
-        CU(cudaMemcpyAsync(d_first, &first, sizeof(int), cudaMemcpyHostToDevice, t->s_compute));
+        int *d_first = nullptr, both[2] = {INT_MAX, 0};     // [0] first clear bit, [1] number of set bits
+        CU(cudaMalloc(&d_first, 2 * sizeof(int)));
+        CU(cudaMemcpyAsync(d_first, both, sizeof(both), cudaMemcpyHostToDevice, t->s_compute));
         k_first_clear<<<blocks_for((g.nverts + 31) / 32), NDP_BLOCK, 0, t->s_compute>>>(level0, g.nverts, d_first);
+        k_count_bits<<<blocks_for((g.nverts + 31) / 32), NDP_BLOCK, 0, t->s_compute>>>(level0, g.nverts, d_first + 1);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(&first, d_first, sizeof(int), cudaMemcpyDeviceToHost, t->s_compute));
+        CU(cudaMemcpyAsync(both, d_first, sizeof(both), cudaMemcpyDeviceToHost, t->s_compute));
         CU(cudaStreamSynchronize(t->s_compute));
         CU(cudaFree(d_first));
+        first = both[0];
+        P.count = both[1];
     }
     CU(cudaMemcpyAsync(&top, D.bits[D.nlev - 1], sizeof(uint32_t), cudaMemcpyDeviceToHost, t->s_compute));
     CU(cudaStreamSynchronize(t->s_compute));
@@ -276,6 +281,7 @@ extern "C" int ndpb_table_destroy(ndpb_table *t)
             cudaFree(set[m].d_desc);
         }
     for (auto &T : t->topo) { cudaFree(T.parent); cudaFree(T.depth); }
+    for (int m = 0; m < 2; m++) cudaFree(t->sparse_ids[m]);
     for (int geo = 0; geo < 3; geo++) { cudaFree(t->nsm_offs[geo]); cudaFree(t->nsm_ents[geo]); cudaFree(t->nsm_head[geo]); }
     for (auto &s : t->slot) free_slot(s);
     if (t->s_owned) cudaStreamDestroy(t->s_owned);
@@ -606,6 +612,10 @@ extern "C" int64_t ndpb_table_stat(const ndpb_table *t, const char *key)
     if (k == "variant_axes_linear") return t->red[1].dev.nvar;
     if (k == "tree_levels_nearest") return t->topo[0].levels;
     if (k == "tree_levels_linear") return t->topo[1].levels;
+    if (k == "mask_count_nearest") return t->pyr[0].count;
+    if (k == "mask_count_linear") return t->pyr[1].count;
+    if (k == "sparse_search_nearest") return t->sparse_ids[0] ? 1 : 0;
+    if (k == "sparse_search_linear") return t->sparse_ids[1] ? 1 : 0;
     return -1;
 }
 
@@ -844,6 +854,32 @@ static bool use_brute(const ndpb_table *t, int search)
     return t->g.nverts <= 4096;      // the literal scan only where it is cheap; identical results either way
 }
 
+// A mask with at most NDP_SPARSE_MAX set vertices, fewer than one in 64: the nearest search scores the set vertices
+// themselves (k_search_sparse) instead of descending a pyramid that is empty almost everywhere.
+#define NDP_SPARSE_MAX 16384
+static bool sparse_ready(ndpb_table *t, int m)
+{
+    const Pyramid &P = t->pyr[m];
+    if (P.count > NDP_SPARSE_MAX || (long long) P.count * 64 > t->g.nverts) return false;
+    if (t->sparse_tried[m]) return t->sparse_ids[m] != nullptr;
+    t->sparse_tried[m] = true;
+    DevTemps hold;
+    int *ids = nullptr, *d_count = nullptr;
+    void *tmp = nullptr;
+    size_t need = 0;
+    cudaStream_t st = t->s_owned;
+    thrust::counting_iterator<int> counting(0);
+    BitSet pred{P.dev.bits[0]};
+    if (hold.alloc(&ids, (size_t) std::max(P.count, 1)) != cudaSuccess || hold.alloc(&d_count, 1) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cub::DeviceSelect::If(nullptr, need, counting, ids, d_count, t->g.nverts, pred, st) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (hold.alloc((unsigned char **) &tmp, need) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cub::DeviceSelect::If(tmp, need, counting, ids, d_count, t->g.nverts, pred, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return false; }
+    hold.release(ids);
+    t->sparse_ids[m] = ids;
+    return true;
+}
+
 // hard == false: pass 1 over the work list (or the literal scan); hard == true: the descent over A.sublist
 static int launch_search(ndpb_table *t, SearchArgs &A, long long upper, bool hard, cudaStream_t st)
 {
@@ -860,6 +896,10 @@ static int launch_search(ndpb_table *t, SearchArgs &A, long long upper, bool har
     } else if (use_brute(t, A.search)) {
         const int blocks = (int) std::min<long long>((upper * 32 + NDP_BLOCK - 1) / NDP_BLOCK, cap);
         CU(ndp_launch_search_brute(A, std::max(blocks, 1), smem, st));
+    } else if (sparse_ready(t, m)) {
+        A.sparse_ids = t->sparse_ids[m]; A.sparse_n = t->pyr[m].count;
+        const int blocks = (int) std::min<long long>((upper * 32 + NDP_BLOCK - 1) / NDP_BLOCK, (long long) t->sm_count * 8);
+        CU(ndp_launch_search_sparse(A, std::max(blocks, 1), smem, st));
     } else {
         const int blocks = (int) std::min<long long>((upper + NDP_BLOCK - 1) / NDP_BLOCK, cap);
         CU(ndp_launch_search_fast(A, t->g.naxes, std::max(blocks, 1), smem, st));
@@ -998,7 +1038,7 @@ static int batch_enqueue(ndpb_table *t, Slot &s, Task task, const double *q, lon
         S.rec_idx = s.rec_idx; S.rec_nrm = s.rec_nrm;
         int rc = launch_search(t, S, n, false, st);
         if (rc) return rc;
-        if (!use_brute(t, search)) {                  // pass 2: whatever pass 1 could not prove
+        if (!use_brute(t, search) && !sparse_ready(t, method == NDPB_METHOD_LINEAR ? 1 : 0)) {   // pass 2: whatever pass 1 could not prove
             S.sublist = s.hardlist; S.count = &s.ctr->n_hard;
             rc = launch_search(t, S, n, true, st);
             if (rc) return rc;

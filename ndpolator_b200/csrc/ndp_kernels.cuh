@@ -252,6 +252,7 @@ struct SearchArgs {
     int *hardlist;          // positions whose fast path failed
     int *tielist;           // positions whose kd tie could not be settled yet
     const int *rec_idx; const double *rec_nrm;   // import products by list position (valid when list != nullptr), or nullptr
+    const int *sparse_ids; int sparse_n;         // k_search_sparse: ascending ids of the mask's set vertices
     NdpCounters *ctr;
 };
 
@@ -405,6 +406,74 @@ __global__ void __launch_bounds__(NDP_BLOCK) k_search_brute(const __grid_constan
             NdpHit hit; hit.vertex = best; hit.dsel = bestd; hit.status = NDP_SEARCH_OK; hit.hard = 0; hit.has_coords = 0;
             ndp_publish(A, Q, t, i, hit);
         }
+    }
+}
+
+// Sparse masks (a hypercube mask with a handful of fully defined cells among 10^8: SURVEY 8d's i.i.d.-void stress
+// table): one warp per query scores the set vertices themselves -- the reference's candidates, with its distance
+// expression -- instead of descending a pyramid that is empty almost everywhere.  Full-scan modes take the lowest id
+// among equals (:101-112, ids ascend); kd modes settle exact ties by the reference's traversal order (topology) or
+// hand them to the tie pass when the topology does not exist yet.
+template <int MODE>
+__global__ void __launch_bounds__(NDP_BLOCK) k_search_sparse(const __grid_constant__ SearchArgs A)
+{
+    extern __shared__ double s_ticks[];
+    const double *tk = ndp_stage_ticks(A.ticks, A.nticks, A.ticks_in_smem, s_ticks);
+    const NdpGeom &g = A.g;
+    const int n = g.naxes;
+    constexpr bool kd = MODE < NDP_MODE_LS_NEAREST;
+    const unsigned lane = threadIdx.x & 31;
+    const long long total = A.count ? (long long) *A.count : A.count_host;
+    const long long warps = ((long long) gridDim.x * blockDim.x) >> 5;
+    for (long long t = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < total; t += warps) {
+        const long long i = A.list ? A.list[t] : t;
+        int idx[NDP_MAX_AXES], flg[NDP_MAX_AXES];
+        double nrm[NDP_MAX_AXES];
+        ndp_import_query<0>(g, tk, A.q + i * n, idx, flg, nrm);
+        NdpQuery Q;
+        ndp_make_query(g, idx, nrm, Q);
+
+        int best = -1;
+        double bestd = 0.0;
+        bool tie = false;
+        for (int j = (int) lane; j < A.sparse_n; j += 32) {
+            const int v = A.sparse_ids[j];
+            int c[NDP_MAX_AXES];
+            ndp_decode_vertex(g, v, c);
+            const double d = ndp_metric_vertex(g, MODE, Q, c);
+            if (best < 0 || d < bestd) { best = v; bestd = d; tie = false; }
+            else if (kd && d == bestd) tie = true;                       // LS: ids ascend per lane, the first keeps the tie
+        }
+        for (int off = 16; off; off >>= 1) {
+            const int ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const double od = __shfl_xor_sync(0xffffffffu, bestd, off);
+            const bool ot = __shfl_xor_sync(0xffffffffu, (int) tie, off) != 0;
+            if (ob >= 0) {
+                if (best < 0 || od < bestd) { best = ob; bestd = od; tie = ot; }
+                else if (od == bestd) { if (kd) tie = true; else if (ob < best) best = ob; }
+            }
+        }
+        if (lane != 0) continue;
+        NdpHit hit;
+        hit.vertex = best; hit.dsel = bestd; hit.status = best < 0 ? NDP_SEARCH_EMPTY : NDP_SEARCH_OK; hit.hard = 0; hit.has_coords = 0;
+        if (kd && tie && best >= 0) {
+            if (!A.have_topo) {
+                A.chosen[t] = best;                                      // provisional (valid) vertex; redone by the tie pass
+                A.tielist[atomicAdd(&A.ctr->n_tie, 1)] = (int) t;
+                continue;
+            }
+            int first = -1;                                              // rare: one lane walks the tied candidates
+            for (int j = 0; j < A.sparse_n; j++) {
+                const int v = A.sparse_ids[j];
+                int c[NDP_MAX_AXES];
+                ndp_decode_vertex(g, v, c);
+                if (ndp_metric_vertex(g, MODE, Q, c) == bestd && (first < 0 || ndp_tree_beats(g, MODE, A.topo, Q, v, first))) first = v;
+            }
+            hit.vertex = first;
+            atomicAdd(&A.ctr->n_tie_resolved, 1);
+        }
+        ndp_scan_sentinel(*A.F, MODE, hit);
+        ndp_publish(A, Q, t, i, hit);
     }
 }
 

@@ -13,6 +13,7 @@ cudaError_t ndp_launch_finish(const FinishArgs &A, int naxes, int G, bool cellma
 cudaError_t ndp_launch_search_fast(const SearchArgs &A, int naxes, int blocks, size_t smem, cudaStream_t st);
 cudaError_t ndp_launch_search_hard(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st);
 cudaError_t ndp_launch_search_brute(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st);
+cudaError_t ndp_launch_search_sparse(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st);
 // mode 0: k_main work, mode 1: linear-extrapolation finish; picks the grid from the occupancy
 cudaError_t ndp_launch_staged(const StagedArgs &A, int naxes, int mode, int stages, int sm_count, long long items, size_t smem, cudaStream_t st);
 // fused path (ndp_fused_kernels.cuh): one translation unit per axis count

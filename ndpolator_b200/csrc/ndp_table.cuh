@@ -147,6 +147,21 @@ __global__ void k_first_clear(const uint32_t *__restrict__ bits, int nverts, int
     if (word) atomicMin(out, (int) (w * 32 + (__ffs(word) - 1)));
 }
 
+// number of set bits among the first nverts (pads of the last word are clear by construction); *out preset to 0
+__global__ void k_count_bits(const uint32_t *__restrict__ bits, int nverts, int *out)
+{
+    const long long w = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const int nwords = (nverts + 31) >> 5;
+    int c = 0;
+    if (w < nwords) {
+        uint32_t word = bits[w];
+        if (w == nwords - 1 && (nverts & 31)) word &= (1u << (nverts & 31)) - 1u;
+        c = __popc(word);
+    }
+    for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 __global__ void k_unpack_bits(const uint32_t *__restrict__ bits, int n, int32_t *out)
 {
     const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;

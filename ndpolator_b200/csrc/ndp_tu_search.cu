@@ -57,6 +57,17 @@ cudaError_t ndp_launch_search_brute(const SearchArgs &A, int blocks, size_t smem
     return cudaGetLastError();
 }
 
+cudaError_t ndp_launch_search_sparse(const SearchArgs &A, int blocks, size_t smem, cudaStream_t st)
+{
+    switch (ndp_mode_of(A.method, A.search)) {
+    case NDP_MODE_KD_NEAREST: k_search_sparse<NDP_MODE_KD_NEAREST><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case NDP_MODE_KD_LINEAR: k_search_sparse<NDP_MODE_KD_LINEAR><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    case NDP_MODE_LS_NEAREST: k_search_sparse<NDP_MODE_LS_NEAREST><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    default: k_search_sparse<NDP_MODE_LS_LINEAR><<<blocks, NDP_BLOCK, smem, st>>>(A); break;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t ndp_launch_slow(const SlowArgs &A, int blocks, size_t smem, cudaStream_t st)
 {
     switch (ndp_mode_of(A.method, A.search)) {

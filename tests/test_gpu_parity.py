@@ -316,7 +316,45 @@ def test_survey_variants_vs_oracle(spec):
         assert_same_bits(a[0], b[0], f'{w.name} interps method {m}')
         assert_same_bits(a[1], b[1], f'{w.name} dists method {m}')
     if variant == 'iid':
-        assert T.stat('fused') == 0 and T.stat('variant_axes_linear') == 5
+        assert T.stat('fused') == 0 and T.stat('variant_axes_nearest') == 5
+    T.close()
+
+
+@pytest.mark.parametrize('void', [0.25, 0.45], ids=['146-cells', 'almost-empty'])
+def test_sparse_hypercube_mask_search(void):
+    """A hypercube mask with a handful of fully defined cells (i.i.d. voids: 0.75^16 = 1 % of the 4-D cells, or almost
+    none): 'linear' scores the set cells themselves (k_search_sparse) -- kd and full-scan tie rules, exact ticks and
+    mid-points among the queries, topology missing on the first call and present on the second, stream-ordered too."""
+    import torch
+    rng = np.random.default_rng(11)
+    axes = [np.arange(12, dtype=np.float64) * s + o for s, o in ((1.0, 0.0), (0.5, 2.0), (2.0, -3.0), (1.0, 5.0))]
+    grid = rng.random((12, 12, 12, 12, 1))
+    grid[rng.random((12, 12, 12, 12)) < void] = np.nan
+    q = np.concatenate([adversarial_queries(axes, 20000, np.random.default_rng(12)),
+                        np.stack([rng.choice(a, 3000) for a in axes], axis=1) + rng.choice([-0.0, 7.0], (3000, 1)) * np.array([1.0, 0, 0, 0])])
+    O = Oracle('port', axes, grid, 4)
+    T = _table(axes, grid, 4, fused=1)                     # the three-pass path: its search is what is under test
+    assert T.stat('mask_count_linear') * 64 <= T.nverts
+    for rep in range(2):                                   # rep 0 meets kd ties without the topology, rep 1 with it
+        for s in (0, 1):
+            qq = q if s == 0 else q[:4000]
+            a, b = O.ndpolate(qq, 2, s, threads=os.cpu_count() or 1), T.ndpolate(qq, 2, s)
+            assert T.stat('sparse_search_linear') == 1 and T.stat('fused') == 0
+            assert_same_bits(a[0], b[0], f'interps linear/{s} rep {rep}')
+            assert_same_bits(a[1], b[1], f'dists linear/{s} rep {rep}')
+    T.set_option('fused', 0)                               # and the fused path on the same table (map + k_slow)
+    a, b = O.ndpolate(q, 2, 0, threads=os.cpu_count() or 1), T.ndpolate(q, 2, 0)
+    assert_same_bits(a[0], b[0], 'interps linear, fused'); assert_same_bits(a[1], b[1], 'dists linear, fused')
+    T.set_option('fused', 1)
+    fo = O.find(q)
+    a, b = O.find_nearest(*fo, 2, 0), T.find_nearest(q, 2, 0)
+    assert_same_bits(a[0], b[0], 'coords'); assert_same_bits(a[1], b[1], 'ndist')
+    assert_same_bits(O.distance(q), T.distance(q), 'distance')
+    T.set_option('async', 1)
+    gi, gd = T.ndpolate(torch.as_tensor(q, device='cuda'), 2, 0)
+    T.sync()
+    a = O.ndpolate(q, 2, 0, threads=os.cpu_count() or 1)
+    assert_same_bits(a[0], gi.cpu().numpy(), 'async interps'); assert_same_bits(a[1], gd.cpu().numpy(), 'async dists')
     T.close()
 
 
