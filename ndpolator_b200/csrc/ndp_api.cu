@@ -222,7 +222,10 @@ static int build_pyramid(ndpb_table *t, Pyramid &P, uint32_t *level0, int nvar, 
         D.prevv = P.prevv; D.nextv = P.nextv;
     }
     CU(cudaMalloc(&P.d_desc, sizeof(NdpPyramid)));
-    CU(cudaMemcpy(P.d_desc, &D, sizeof(NdpPyramid), cudaMemcpyHostToDevice));
+    // (copies the kernels of the table's non-blocking stream depend on are issued on that stream and waited for:
+    // a plain cudaMemcpy is ordered on the legacy default stream only and may return before the DMA has finished)
+    CU(cudaMemcpyAsync(P.d_desc, &D, sizeof(NdpPyramid), cudaMemcpyHostToDevice, t->s_compute));
+    CU(cudaStreamSynchronize(t->s_compute));
     return NDPB_OK;
 }
 
@@ -469,12 +472,19 @@ extern "C" int ndpb_table_create(const double *const *axes, const int32_t *axlen
     for (int a = 0; a < naxes; a++) { g.vstride32[a] = g.small ? (int) g.vstride[a] : 0; g.cstride32[a] = g.small ? (int) g.cstride[a] : 0; }
     for (int a = 0; a < nbasic; a++) g.inv_bstride[a] = 1.0 / (double) g.bstride[a];
     CUT(cudaMalloc(&t->ticks, sizeof(double) * nticks));
-    CUT(cudaMemcpy(t->ticks, flat.data(), sizeof(double) * nticks, cudaMemcpyHostToDevice));
+    CUT(cudaMemcpyAsync(t->ticks, flat.data(), sizeof(double) * nticks, cudaMemcpyHostToDevice, t->s_compute));
+    CUT(cudaStreamSynchronize(t->s_compute));
 
     if (grid) {
         t->has_grid = true;
         CUT(cudaMalloc(&t->grid, sizeof(double) * t->grid_doubles));
-        CUT(cudaMemcpy(t->grid, grid, sizeof(double) * t->grid_doubles, cudaMemcpyDefault));
+        // A device-resident grid: cudaMemcpy of device memory returns before the copy has run and is ordered on the
+        // legacy default stream only -- the table's kernels run on a NON-BLOCKING stream and would read the copy's
+        // destination too early (masks computed from whatever the recycled pages held; seen as 1 flaky run in 17).
+        // Registering a table is a one-off: wait for the grid's producer, copy on the table's stream, wait again.
+        if (is_device_ptr(grid)) CUT(cudaDeviceSynchronize());
+        CUT(cudaMemcpyAsync(t->grid, grid, sizeof(double) * t->grid_doubles, cudaMemcpyDefault, t->s_compute));
+        CUT(cudaStreamSynchronize(t->s_compute));
         const long long words = (nverts + 31) / 32;
         uint32_t *vbits = nullptr, *hbits = nullptr;
         CUT(cudaMalloc(&vbits, sizeof(uint32_t) * words));
@@ -1301,12 +1311,13 @@ extern "C" int ndpb_distance(ndpb_table *t, const double *query_pts, int64_t n, 
 template <class T>
 struct Staged {
     T *dev = nullptr; T *user = nullptr; size_t count = 0; bool own = false;
-    int in(const T *p, size_t n) {
+    int in(const T *p, size_t n, cudaStream_t st) {       // st: the stream of the kernels that will read the copy
         user = const_cast<T *>(p); count = n;
         if (is_device_ptr(p) || n == 0) { dev = user; return NDPB_OK; }
         own = true;
         CU(cudaMalloc(&dev, sizeof(T) * n));
-        CU(cudaMemcpy(dev, p, sizeof(T) * n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(dev, p, sizeof(T) * n, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
         return NDPB_OK;
     }
     int out(T *p, size_t n) {
@@ -1335,7 +1346,7 @@ extern "C" int ndpb_find(ndpb_table *t, const double *query_pts, int64_t n,
     if (n == 0) return NDPB_OK;
     const size_t e = (size_t) n * t->g.naxes;
     Staged<double> q, nrm; Staged<int32_t> idx, flg;
-    if ((rc = q.in(query_pts, e)) || (rc = idx.out(indices, e)) || (rc = flg.out(flags, e)) || (rc = nrm.out(normed, e))) return rc;
+    if ((rc = q.in(query_pts, e, t->s_compute)) || (rc = idx.out(indices, e)) || (rc = flg.out(flags, e)) || (rc = nrm.out(normed, e))) return rc;
     ImportArgs A{};
     A.g = t->g; A.ticks = t->ticks; A.nticks = t->nticks; A.ticks_in_smem = ticks_in_smem(t);
     A.q = q.dev; A.n = n; A.indices = idx.dev; A.flags = flg.dev; A.normed = nrm.dev;
@@ -1360,7 +1371,7 @@ extern "C" int ndpb_hypercubes(ndpb_table *t, const double *normed, const int32_
     const size_t e = (size_t) n * t->g.naxes;
     const size_t slot = ((size_t) 1 << t->g.naxes) * t->g.vdim;
     Staged<double> nrm, vv; Staged<int32_t> idx, flg, dm, fd;
-    if ((rc = nrm.in(normed, e)) || (rc = idx.in(indices, e)) || (rc = flg.in(flags, e)) ||
+    if ((rc = nrm.in(normed, e, t->s_compute)) || (rc = idx.in(indices, e, t->s_compute)) || (rc = flg.in(flags, e, t->s_compute)) ||
         (rc = dm.out(dim, n)) || (rc = fd.out(fdhc, n)) || (rc = vv.out(v, (size_t) n * slot))) return rc;
     HypercubeArgs A{};
     A.g = t->g; A.grid = t->grid; A.normed = nrm.dev; A.indices = idx.dev; A.flags = flg.dev; A.n = n;
@@ -1516,7 +1527,7 @@ extern "C" int ndpb_ndpolate_cached(ndpb_table *t, const double *normed, const i
     if (n == 0) return NDPB_OK;
     const size_t e = (size_t) n * t->g.naxes;
     Staged<double> nrm, out_i, out_d; Staged<int32_t> idx, flg;
-    if ((rc = nrm.in(normed, e)) || (rc = idx.in(indices, e)) || (rc = flg.in(flags, e)) ||
+    if ((rc = nrm.in(normed, e, t->s_compute)) || (rc = idx.in(indices, e, t->s_compute)) || (rc = flg.in(flags, e, t->s_compute)) ||
         (rc = out_i.out(interps, (size_t) n * t->g.vdim)) || (rc = out_d.out(dists, (size_t) n))) return rc;
     Slot &s = t->slot[0];
     rc = ensure_slot(t, s, n, false, false, false, false, 1);

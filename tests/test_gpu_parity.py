@@ -113,6 +113,31 @@ def test_device_inputs_are_ordered_after_their_producer():
     T.close()
 
 
+def test_device_grid_registration_is_ordered():
+    """Registering a table from a DEVICE-resident grid while other work is still queued on the producer's stream: the
+    library's copy of the grid must be complete before its (non-blocking-stream) kernels derive the masks from it.
+    (A plain cudaMemcpy of device memory returns early and is ordered on the legacy default stream only: masks were
+    computed from whatever the recycled pages held -- one flaky suite run in 17 before the fix.)"""
+    import torch
+    from ndpolator_b200 import synth
+    w = synth.workload('C3', None)
+    nb = len(w.basic_axes)
+    vm, hm = Oracle('port', w.axes, w.grid(), nb).masks()
+    grid_d = w.grid('cuda')
+    torch.cuda.synchronize()
+    for it in range(6):
+        ones = torch.ones_like(grid_d)                  # pages full of finite values go back to the driver ...
+        del ones
+        torch.cuda.empty_cache()
+        pending = [torch.full((1 << 26,), float('nan'), dtype=torch.float64, device='cuda') for _ in range(4)]   # ... 2 GB of writes queued
+        T = _table(w.axes, grid_d, nb)
+        a, b = T.masks()
+        assert_same_bits(vm, a, f'vmask, iteration {it}')
+        assert_same_bits(hm, b, f'hcmask, iteration {it}')
+        T.close()
+        del pending
+
+
 def test_bad_device_arguments_raise():
     import torch
     name, axes, nbasic, grid = build_cases()[1]
