@@ -324,7 +324,7 @@ def test_baseline_configs_scaled_vs_oracle(spec, fused_off):
     T.close()
 
 
-@pytest.mark.parametrize('spec', [('C4', 9, 'iid', 40000), ('C3', 24, 'allbasic', 40000)], ids=lambda s: f'{s[0]}@{s[1]}-{s[2]}')
+@pytest.mark.parametrize('spec', [('C4', 14, 'iid', 40000), ('C3', 24, 'allbasic', 40000)], ids=lambda s: f'{s[0]}@{s[1]}-{s[2]}')
 def test_survey_variants_vs_oracle(spec):
     """SURVEY 8d variants: C4 with i.i.d. 30 % voids (the mask depends on all five axes -- no nearest-site map, the
     three-pass path with the exact lattice search; ~100 % of the queries extrapolate, the hypercube mask is nearly

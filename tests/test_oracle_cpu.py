@@ -94,6 +94,28 @@ def test_port_matches_live_reference(case):
     assert_same_bits(P.distance(q), R.distance(q), 'distance')
 
 
+@pytest.mark.skipif(not have('reference'), reason='oracle/_ref/libndp_ref.so not built (needs /root/reference)')
+@pytest.mark.parametrize('spec', [('C4', 14, 'iid'), ('C3', 24, 'allbasic'), ('C2', 14, None), ('C5', 6, None)],
+                         ids=lambda s: f'{s[0]}@{s[1]}-{s[2]}')
+def test_port_matches_live_reference_on_survey_variants(spec):
+    """The oracle port against the live reference on the SURVEY 8d workloads and variants the GPU tests check against
+    the port: C4 with i.i.d. voids (sparse hypercube mask; a scale where it is not empty), C3 all-basic, scaled C2 / C5."""
+    from ndpolator_b200 import synth
+    name, scale, variant = spec
+    n = 3000
+    w = synth.workload(name, scale, n_queries=n, variant=variant)
+    grid, q = w.grid(), w.queries(0, n)
+    nb = len(w.basic_axes)
+    P, R = Oracle('port', w.axes, grid, nb), Oracle('reference', w.axes, grid, nb)
+    for a, b, what in zip(P.masks(), R.masks(), ('vmask', 'hcmask')):
+        assert_same_bits(a, b, what)
+    empty_hc = not R.masks()[1].any()          # the reference crashes on an empty kd-tree (kd_res_free(NULL)): skip 'linear' there
+    for m in (0, 1) + (() if empty_hc else (2,)):
+        a, b = P.ndpolate(q, m, 0), R.ndpolate(q, m, 0)
+        assert_same_bits(a[0], b[0], f'{w.name} interps {m}')
+        assert_same_bits(a[1], b[1], f'{w.name} dists {m}')
+
+
 def test_threaded_oracle_equals_serial():
     name, axes, nbasic, grid = build_cases()[1]
     q = adversarial_queries(axes, 4000, np.random.default_rng(5))
