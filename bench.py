@@ -130,13 +130,46 @@ def kernel_source_digest():
     return h.hexdigest()[:16]
 
 
+def mangled_fused(name):
+    """'void k_fused<5, 2, 1, 4, 1, 3, 0>(FusedArgs)' (ncu's kernel name) -> its mangled symbol."""
+    import re
+    m = re.search(r'k_fused<([0-9, ]+)>', name or '')
+    if not m:
+        return None
+    return '_Z7k_fusedI' + ''.join(f'Li{int(x)}E' for x in m.group(1).split(',')) + 'Ev9FusedArgs'
+
+
+def kernel_sass_digest(mangled, lib=None):
+    """sha256 over the SASS instruction text of one kernel of the built library (cuobjdump -sass -fun): a traffic
+    capture stays valid exactly as long as the machine code of the kernel it was taken on is unchanged."""
+    import hashlib
+    import re
+    if not mangled:
+        return None
+    lib = lib or os.environ.get('NDPB_LIB') or os.path.join(ROOT, 'ndpolator_b200', 'libndpb200.so')
+    try:
+        out = subprocess.run(['cuobjdump', '-sass', '-fun', mangled, lib], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    ins = [re.sub(r'/\*[0-9a-f]+\*/', '', l).strip() for l in out.splitlines() if re.match(r'^\s+/\*[0-9a-f]{4,}\*/', l)]
+    if not ins:
+        return None
+    return hashlib.sha256('\n'.join(ins).encode()).hexdigest()[:16]
+
+
 def measured_traffic(batch, workload_key):
-    """DRAM bytes of one launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum from
-    an `ncu --set full` capture, tools/traffic_from_ncu.py -> profiles/r02_traffic.json), scaled to this
-    batch.  None unless the capture was taken on exactly these kernel sources and this workload."""
+    """DRAM bytes of one launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum from an
+    `ncu --set full` capture, tools/ncu_summary.py --traffic-json -> profiles/r02_traffic.json), scaled to this batch.
+    None unless the capture was taken on exactly this kernel's machine code (SASS digest of the built library; the
+    digest of the CUDA sources when the capture carries no SASS digest) and this workload."""
     try:
         t = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
-        if t.get('source_digest') != kernel_source_digest() or t.get('workload') != workload_key:
+        if t.get('workload') != workload_key:
+            return None
+        if t.get('sass_digest'):
+            if kernel_sass_digest(t.get('kernel_mangled')) != t['sass_digest']:
+                return None
+        elif t.get('source_digest') != kernel_source_digest():
             return None
         return t['dram_bytes_per_launch'] * batch / t['queries_per_launch']
     except Exception:

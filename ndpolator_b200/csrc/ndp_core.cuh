@@ -508,6 +508,7 @@ struct NdpHit {
     double dsel;     // its selection metric
     int status;
     int hard;        // 1 when step (2) ran
+    int tied;        // 1 when another candidate scored exactly the winning (rounded) total during the search
     int has_coords;  // coords[] below already holds the basic coordinates of `vertex`
     int coords[NDP_MAX_AXES];
 };
@@ -653,8 +654,10 @@ NDP_HD_CALL void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode
     int best = seeded ? hit.vertex : -1;
     double bestd = seeded ? hit.dsel : 0.0;
     bool tie = seeded && hit.status == NDP_SEARCH_TIE;
+    bool eq = seeded && hit.tied;             // an equal total was met at the current minimum (any mode)
 
     hit.hard = 1;
+    hit.tied = 0;
     if (!P.any_set) { hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_EMPTY; return; }
 
     int lev = top;
@@ -711,8 +714,9 @@ NDP_HD_CALL void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode
             // a level-0 block is one vertex and its bound is the reference's distance expression
             int vid = base;
             for (int j = 0; j < nv; j++) vid += cb[j] * g.bstride[P.var_axis[j]];
-            if (best < 0 || bound < bestd) { best = vid; bestd = bound; tie = false; }
+            if (best < 0 || bound < bestd) { best = vid; bestd = bound; tie = false; eq = false; }
             else if (bound == bestd && vid != best) {
+                eq = true;
                 if (!kd) { if (vid < best) best = vid; }                 // _compare_indexed_dists, :101-112
                 else if (topo) { if (ndp_tree_beats(g, mode, *topo, Q, vid, best)) best = vid; }
                 else tie = true;
@@ -726,6 +730,7 @@ NDP_HD_CALL void ndp_search_hard(const NdpGeom &g, const NdpPyramid &P, int mode
     hit.vertex = best;
     hit.dsel = bestd;
     hit.status = tie ? NDP_SEARCH_TIE : NDP_SEARCH_OK;
+    hit.tied = eq ? 1 : 0;
 }
 
 // Expanding-shell search around the lattice point p0 the query rounds to, over the
@@ -754,7 +759,7 @@ NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode
     double term[NDP_MAX_AXES];        // per basic axis: the term of the row being scanned (row axis: unused)
     int base = 0;
 
-    hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_OK; hit.hard = 1;
+    hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_OK; hit.hard = 1; hit.tied = 0;
     if (nv < 1 || !P.prevv) return false;
     for (int a = 0; a < nb; a++) jof[a] = -1;
     for (int j = 0; j < nv; j++) jof[P.var_axis[j]] = j;
@@ -780,7 +785,7 @@ NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode
 
     int best = -1;
     double bestd = 0.0;
-    bool tie = false;
+    bool tie = false, eq = false;
     int rows = 0;
 
     // scores the set coordinate c of the current row (row_vid = vertex id without the row axis):
@@ -791,8 +796,9 @@ NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode
         for (int a = 0; a < nb; a++) d += (a == aL) ? tL : term[a];
         d = ndp_add_assoc(g, mode, Q, d);
         const int vid = row_vid + c * strideL;
-        if (best < 0 || d < bestd) { best = vid; bestd = d; tie = false; }
+        if (best < 0 || d < bestd) { best = vid; bestd = d; tie = false; eq = false; }
         else if (d == bestd && vid != best) {
+            eq = true;
             if (!kd) { if (vid < best) best = vid; }                     // _compare_indexed_dists, :101-112
             else if (topo) { if (ndp_tree_beats(g, mode, *topo, Q, vid, best)) best = vid; }
             else tie = true;
@@ -862,7 +868,7 @@ NDP_HD_CALL bool ndp_search_ring(const NdpGeom &g, const NdpPyramid &P, int mode
                 any_beyond = true;
             }
         }
-        hit.vertex = best; hit.dsel = bestd; hit.status = tie ? NDP_SEARCH_TIE : NDP_SEARCH_OK;
+        hit.vertex = best; hit.dsel = bestd; hit.status = tie ? NDP_SEARCH_TIE : NDP_SEARCH_OK; hit.tied = eq ? 1 : 0;
         if (!any_beyond) {                       // every row of the slice has been scanned
             if (best < 0) hit.status = NDP_SEARCH_EMPTY;
             return true;
@@ -886,7 +892,7 @@ NDP_HD_CALL bool ndp_search_ring_nb(const NdpGeom &g, const NdpPyramid &P, const
     constexpr bool kd = mode < NDP_MODE_LS_NEAREST;
     constexpr int lo = cells ? 1 : 0;
 
-    hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_OK; hit.hard = 1;
+    hit.vertex = -1; hit.dsel = 0.0; hit.status = NDP_SEARCH_OK; hit.hard = 1; hit.tied = 0;
     if (nv < 1 || !P.prevv) return false;
 
     int kind[NB], pstr[NB], p0[NB], off[NB], len[NB], bstr[NB];
@@ -934,7 +940,7 @@ NDP_HD_CALL bool ndp_search_ring_nb(const NdpGeom &g, const NdpPyramid &P, const
 
     int best = -1;
     double bestd = 0.0;
-    bool tie = false;
+    bool tie = false, eq = false;
     int rows = 0;
 
     auto score = [&](int row_vid, int c) -> double {
@@ -944,8 +950,9 @@ NDP_HD_CALL bool ndp_search_ring_nb(const NdpGeom &g, const NdpPyramid &P, const
         for (int a = 0; a < NB; a++) d += (kind[a] == 2) ? tL : term[a];
         d = ndp_add_assoc(g, mode, Q, d);
         const int vid = row_vid + c * bstrrow;
-        if (best < 0 || d < bestd) { best = vid; bestd = d; tie = false; }
+        if (best < 0 || d < bestd) { best = vid; bestd = d; tie = false; eq = false; }
         else if (d == bestd && vid != best) {
+            eq = true;
             if (!kd) { if (vid < best) best = vid; }                     // _compare_indexed_dists, :101-112
             else if (topo) { if (ndp_tree_beats(g, mode, *topo, Q, vid, best)) best = vid; }
             else tie = true;
@@ -1021,7 +1028,7 @@ NDP_HD_CALL bool ndp_search_ring_nb(const NdpGeom &g, const NdpPyramid &P, const
                     }
                 }
             }
-        hit.vertex = best; hit.dsel = bestd; hit.status = tie ? NDP_SEARCH_TIE : NDP_SEARCH_OK;
+        hit.vertex = best; hit.dsel = bestd; hit.status = tie ? NDP_SEARCH_TIE : NDP_SEARCH_OK; hit.tied = eq ? 1 : 0;
         if (!any_beyond) {                       // every row of the slice has been scanned
             if (best < 0) hit.status = NDP_SEARCH_EMPTY;
             return true;
@@ -1090,7 +1097,11 @@ NDP_HD void ndp_search_descend(const NdpGeom &g, const NdpPyramid &F, const NdpP
         if (ok) {
             if (!ndp_search_ring_any<MODE>(g, R, mode, Q, fixed, topo, NDP_RING_BUDGET, hit))
                 ndp_search_hard<MODE>(g, R, mode, Q, fixed, topo, hit, hit.vertex >= 0);
-            if (hit.status != NDP_SEARCH_EMPTY && hit.vertex >= 0) {
+            // Another candidate of the slice scored exactly the winning total: the re-summation below vouches for the
+            // reported winner only, while a tied candidate's neighbour along a closed-form axis may tie too (absorbed
+            // terms) and win by the reference's tie rule -- found by tools/fuzz_hostsim.py: the full lattice decides.
+            if (hit.tied) ok = false;
+            if (ok && hit.status != NDP_SEARCH_EMPTY && hit.vertex >= 0) {
                 // the closed-form axes must also be strict minimisers of the rounded total: re-sum the
                 // winner's terms in order with one fixed axis' term swapped for a neighbour's
                 int c[NDP_MAX_AXES];

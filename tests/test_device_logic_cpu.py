@@ -6,6 +6,8 @@ strided, cell-major and runtime-n gather variants.  This is a development check 
 the kernel logic in the GPU-less container; the GPU parity suite is test_gpu_parity.py."""
 import shutil
 
+import os
+
 import numpy as np
 import pytest
 
@@ -191,6 +193,39 @@ def test_site_map_margins_next_to_bisectors():
             assert_same_bits(a[1], b[1], f'dists {m}/{s}')
     st = H.stats()
     assert st['mapped'] > 0 and st['slow'] > 0
+
+
+def _absorbed_tie_case():
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fuzz_absorbed_tie_case.npz'))
+    return [z['ax0'], z['ax1'], z['ax2']], int(z['nbasic']), z['grid'], z['q']
+
+
+def test_absorbed_tie_beside_a_closed_form_axis():
+    """Found by tools/fuzz_hostsim.py: a query within 1e-8 of a vertex on two basic axes and far outside on the
+    associated one -- the tiny basic-axis terms are absorbed by the associated-axis term, so cells on BOTH sides of the
+    mask-invariant axis tie with the cell the query sits in; the full scan takes the lowest id among them, which lies
+    across that axis.  The closed-form treatment of the invariant axis must give way to the full lattice then."""
+    from hostsim.driver import HostSim
+    axes, nbasic, grid, q = _absorbed_tie_case()
+    O, H = Oracle('port', axes, grid, nbasic), HostSim(axes, grid, nbasic)
+    from oracle.oracle import have
+    R = Oracle('reference', axes, grid, nbasic) if have('reference') else None
+    fo = O.find(q)
+    for m in (1, 2):
+        for s in (0, 1):
+            a, b, f = O.ndpolate(q, m, s), H.ndpolate(q, m, s, 0), H.ndpolate_fused(q, m, s)
+            if R is not None:                                # what is expected is what the reference itself returns
+                r = R.ndpolate(q, m, s)
+                assert_same_bits(r[0], a[0], f'port vs reference interps {m}/{s}')
+                assert_same_bits(r[1], a[1], f'port vs reference dists {m}/{s}')
+            assert_same_bits(a[0], b[0], f'interps {m}/{s}')
+            assert_same_bits(a[1], b[1], f'dists {m}/{s}')
+            if f is not None:
+                assert_same_bits(a[0], f[0], f'fused interps {m}/{s}')
+                assert_same_bits(a[1], f[1], f'fused dists {m}/{s}')
+            a, b = O.find_nearest(*fo, m, s), H.find_nearest(q, m, s)
+            assert_same_bits(a[0], b[0], f'coords {m}/{s}')
+            assert_same_bits(a[1], b[1], f'ndist {m}/{s}')
 
 
 def test_fused_plan_with_the_finest_site_map(monkeypatch):

@@ -271,6 +271,26 @@ def test_site_map_margins_next_to_bisectors():
     T.close()
 
 
+def test_absorbed_tie_beside_a_closed_form_axis():
+    """GPU twin of the host-build test of the same name (a case tools/fuzz_hostsim.py found): exact ties created by
+    absorbed terms across a mask-invariant axis, every path -- fused + k_slow, three-pass, find_nearest."""
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fuzz_absorbed_tie_case.npz'))
+    axes, nbasic, grid, q = [z['ax0'], z['ax1'], z['ax2']], int(z['nbasic']), z['grid'], z['q']
+    O = Oracle('port', axes, grid, nbasic)
+    fo = O.find(q)
+    for fused_off in (0, 1):
+        T = _table(axes, grid, nbasic, fused=fused_off)
+        for m in (1, 2):
+            for s in (0, 1):
+                a, b = O.ndpolate(q, m, s), T.ndpolate(q, m, s)
+                assert_same_bits(a[0], b[0], f'interps {m}/{s} fused_off={fused_off}')
+                assert_same_bits(a[1], b[1], f'dists {m}/{s} fused_off={fused_off}')
+                a, b = O.find_nearest(*fo, m, s), T.find_nearest(q, m, s)
+                assert_same_bits(a[0], b[0], f'coords {m}/{s}')
+                assert_same_bits(a[1], b[1], f'ndist {m}/{s}')
+        T.close()
+
+
 def test_host_chunking_device_tensors_and_search_variants_agree():
     import torch
     name, axes, nbasic, grid = build_cases()[7]          # 5-D with a structured void

@@ -79,6 +79,8 @@ def main():
     if args.traffic_json and traffic:
         import bench
         traffic['source_digest'] = bench.kernel_source_digest()
+        traffic['kernel_mangled'] = bench.mangled_fused(traffic['kernel'])
+        traffic['sass_digest'] = bench.kernel_sass_digest(traffic['kernel_mangled'])
         traffic['report'] = os.path.basename(args.rep)
         json.dump(traffic, open(args.traffic_json, 'w'), indent=1)
 
