@@ -604,8 +604,8 @@ def run_b200(args):
                     'traffic': traffic,
                 'note': ('table larger than L2: every gather is HBM traffic' if table_bytes > 126 * 2**20 else
                          'table fits in the 126 MB L2: gathers are served from L2, so the fraction of the HBM roofline can exceed 1'),
-                'traffic_source': ('profiles/r02_traffic.json (ncu --set full on these sources, scaled to this batch)'
-                                       if traffic else 'no ncu capture of exactly these kernel sources / this workload'),
+                'traffic_source': ('profiles/r02_traffic.json (ncu --set full on this kernel: same SASS digest; scaled to this batch)'
+                                       if traffic else 'no ncu capture of exactly this kernel / this workload'),
                     'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': main_bytes, 'avg_launch_ms': main_s * 1e3,
                     'whole_step': {'achieved': step_gbs, 'frac': step_gbs / peak,
