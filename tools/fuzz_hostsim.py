@@ -20,10 +20,13 @@ from hostsim.driver import HostSim  # noqa: E402
 from oracle.oracle import Oracle, have  # noqa: E402
 
 
+MAXDIM, MAXLEN = 5, 9
+
+
 def random_table(rng):
-    n = int(rng.integers(1, 6))
+    n = int(rng.integers(1, MAXDIM + 1))
     nbasic = int(rng.integers(1, n + 1))
-    lens = [int(rng.integers(2, 10 if n <= 3 else 7)) for _ in range(n)]
+    lens = [int(rng.integers(2, MAXLEN + 1 if n <= 3 else max(4, MAXLEN - 3 - (n > 4)))) for _ in range(n)]
     axes = []
     for L in lens:
         kind = rng.integers(0, 4)
@@ -61,7 +64,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--minutes', type=float, default=20)
     ap.add_argument('--seed', type=int, default=1)
+    ap.add_argument('--maxdim', type=int, default=5)
+    ap.add_argument('--maxlen', type=int, default=9)
     args = ap.parse_args()
+    global MAXDIM, MAXLEN
+    MAXDIM, MAXLEN = args.maxdim, args.maxlen
     rng = np.random.default_rng(args.seed)
     use_ref = have('reference')
     t_end = time.time() + args.minutes * 60
@@ -73,7 +80,14 @@ def main():
         k = rng.integers(0, len(axes), len(far))
         span = np.array([a[-1] - a[0] for a in axes])
         far[np.arange(len(far)), k] += rng.choice([-1.0, 1.0], len(far)) * span[k] * rng.uniform(0.5, 40, len(far))
-        q = np.concatenate([q, far[:200]])
+        # a family a hair away from lattice points and cell centres (bisectors of the two metrics), on every axis
+        bis = q[:200].copy()
+        for a_i, ax in enumerate(axes):
+            pick = rng.random(200) < 0.5
+            j = rng.integers(0, len(ax) - 1, 200)
+            frac = rng.choice([0.0, 0.5, 1.0], 200) + rng.choice([-1.0, 1.0], 200) * rng.choice([0.0, 1e-16, 1e-12, 1e-9, 3e-7], 200)
+            bis[:, a_i] = np.where(pick, ax[j] + frac * (ax[j + 1] - ax[j]), bis[:, a_i])
+        q = np.concatenate([q, far[:200], bis])
         P = Oracle('port', axes, grid, nbasic)
         H = HostSim(axes, grid, nbasic)
         vm, hm = P.masks()
