@@ -96,6 +96,21 @@ def main():
         for a, b, what in zip(P.masks(), H.masks(), ('vmask', 'hcmask')):
             if not np.array_equal(a, b):
                 print('MISMATCH', what, 'seed', args.seed, 'table', ntab); return 1
+        if ntab % 4 == 0 and vm.any() and hm.any():        # the taps: nearest coordinates, rebuilt kd topology
+            fo = P.find(q)
+            for m in (1, 2):
+                for s in (0, 1):
+                    a, b = P.find_nearest(*fo, m, s), H.find_nearest(q, m, s)
+                    if not (np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64))):
+                        print(f'MISMATCH find_nearest method {m} search {s}: seed {args.seed} table {ntab}')
+                        np.savez(os.path.join(ROOT, 'gpurun_out', f'fuzz_fail_{args.seed}_{ntab}.npz'), q=q, grid=grid, nbasic=nbasic,
+                                 **{f'ax{i}': a for i, a in enumerate(axes)})
+                        return 1
+                pp, dp = P.tree_topology(m)
+                ph, dh = H.topology(m)
+                if not (np.array_equal(pp, ph.astype(np.int64)) and np.array_equal(dp, dh)):
+                    print(f'MISMATCH topology method {m}: seed {args.seed} table {ntab}')
+                    return 1
         for m in (0, 1, 2):
             for s in (0, 1):
                 want = P.ndpolate(q, m, s)
